@@ -1,0 +1,184 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED CoDEPS reference on seeded inputs.
+
+Run in the build container only (needs /root/reference; the GPU box does not have it):
+
+    python oracle/make_golden.py
+
+The reference has no golden vectors of its own, so these fixtures are the
+parity pin: outputs of the reference's own ``ReconstructionLoss`` / ``SSIMLoss`` /
+``EdgeAwareSmoothnessLoss`` / ``ImageWarper`` / ``CameraModel`` classes (torch CPU, fp32, plus
+an fp64 run used as tie arbiter) together with the exact inputs, so that both the oracle
+(tests/test_oracle_golden.py) and the CUDA kernels (tests/test_gpu_golden.py) can be checked
+against the reference without the reference being present.
+
+Two modules that are imported by the reference package ``__init__`` files but are not on the
+hot path (``yacs.config``, ``skimage.exposure``) are absent from this image and are stubbed.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference"
+sys.path.insert(0, REPO)
+
+
+def import_reference():
+    if not os.path.isdir(REFERENCE):
+        raise SystemExit(f"{REFERENCE} not found: fixtures can only be generated in the build container")
+    sys.path.insert(0, REFERENCE)
+    yacs_cfg = types.ModuleType("yacs.config")
+    yacs_cfg.CfgNode = type("CfgNode", (dict,), {})
+    sys.modules.setdefault("yacs", types.ModuleType("yacs"))
+    sys.modules.setdefault("yacs.config", yacs_cfg)
+    exposure = types.ModuleType("skimage.exposure")
+    exposure.match_histograms = exposure.is_low_contrast = None
+    sys.modules.setdefault("skimage", types.ModuleType("skimage"))
+    sys.modules.setdefault("skimage.exposure", exposure)
+    import algos.depth as ref_depth  # noqa: E402
+    import misc as ref_misc  # noqa: E402
+    return ref_depth, ref_misc
+
+
+def run_reference(ref_depth, ref_misc, batch, num_scales, seed, dtype, noise=None):
+    """One forward+backward of the reference classes; returns outputs as numpy arrays.
+    ``noise`` (fp64 run only) replays the fp32 run's tie-break draws: ``torch.randn`` yields
+    different numbers in fp64 for the same seed, and the arbiter must see the same inputs."""
+    w, h = batch.width, batch.height
+    cast = lambda t: t.detach().clone().to(dtype)
+    images = tuple(cast(i) for i in batch.images)
+    depth = cast(batch.depth).requires_grad_(True)
+    disp = cast(batch.disp).requires_grad_(True)
+    poses = [cast(p).requires_grad_(True) for p in batch.poses]
+    cams = [ref_misc.CameraModel.from_tensor(w, h, k) for k in batch.intrinsics]
+
+    recon_fn = ref_depth.ReconstructionLoss(w, h, ref_depth.SSIMLoss(), num_scales,
+                                            torch.device("cpu"))
+    if dtype == torch.float64:
+        # the reference builds its pixel grids with .float() (misc/image_warper.py:62-66);
+        # promote them so the fp64 run is a true fp64 arbiter.
+        for warper in recon_fn.image_warpers.values():
+            i2p = warper.coordinate_warper.image_to_pointcloud
+            i2p.u2d_vals = i2p.u2d_vals.double()
+            i2p.v2d_vals = i2p.v2d_vals.double()
+
+    captured = []
+    real_min = torch.min
+
+    def recording_min(*args, **kwargs):
+        out = real_min(*args, **kwargs)
+        if len(args) >= 1 and torch.is_tensor(args[0]) and args[0].dim() == 4 and \
+                kwargs.get("dim", args[1] if len(args) > 1 else None) == 1:
+            captured.append((args[0].detach().clone(), out[1].detach().clone()))
+        return out
+
+    default = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)  # randn / zeros at algos/depth.py:270,317 follow the default
+    torch.min = recording_min
+    real_randn = torch.randn
+    if noise is not None:
+        replay = iter(noise)
+        torch.randn = lambda *a, **k: next(replay).to(dtype)
+    try:
+        torch.manual_seed(seed)
+        recon = recon_fn(cams, images, depth, poses)
+    finally:
+        torch.min = real_min
+        torch.randn = real_randn
+        torch.set_default_dtype(default)
+    smooth = ref_depth.EdgeAwareSmoothnessLoss()(images[0], disp)
+    (recon + smooth).backward()
+    assert len(captured) == num_scales
+    out = {
+        "recon": recon.detach().numpy(),
+        "smooth": smooth.detach().numpy(),
+        "grad_depth": depth.grad.numpy(),
+        "grad_disp": disp.grad.numpy(),
+        "grad_pose0": poses[0].grad.numpy(),
+        "grad_pose1": poses[1].grad.numpy(),
+    }
+    for s, (cands, which) in enumerate(captured):
+        out[f"cand{s}"] = cands.numpy()
+        out[f"argmin{s}"] = which.numpy().astype(np.uint8)
+    return out
+
+
+def standalone_ops(ref_depth, ref_misc, batch):
+    """Outputs of the individually exported operators at full resolution."""
+    w, h = batch.width, batch.height
+    cams = [ref_misc.CameraModel.from_tensor(w, h, k) for k in batch.intrinsics]
+    warper = ref_misc.ImageWarper(w, h, torch.device("cpu"))
+    depth = batch.depth.clone().requires_grad_(True)
+    pose = batch.poses[1].clone().requires_grad_(True)
+    grid = warper.coordinate_warper(cams, depth, pose)
+    warped = warper(cams, batch.images[2], depth, pose)
+    nearest = warper(cams, batch.images[2], depth.detach(), pose.detach(), interp_mode="nearest")
+    upstream = torch.linspace(-1, 1, warped.numel()).view_as(warped).roll(7)
+    (warped * upstream).sum().backward()
+    x = batch.images[1].clone().requires_grad_(True)
+    y = batch.images[0].clone().requires_grad_(True)
+    ssim = ref_depth.SSIMLoss()(x, y)
+    (ssim * upstream).sum().backward()
+    return {
+        "op_grid": grid.detach().numpy(), "op_warped": warped.detach().numpy(),
+        "op_nearest": nearest.numpy(), "op_upstream": upstream.numpy(),
+        "op_warp_grad_depth": depth.grad.numpy(), "op_warp_grad_pose": pose.grad.numpy(),
+        "op_ssim": ssim.detach().numpy(), "op_ssim_grad_x": x.grad.numpy(),
+        "op_ssim_grad_y": y.grad.numpy(),
+    }
+
+
+CASES = {
+    # name: (batch, W, H, intrinsics@WxH, num_scales, data seed, noise seed, kwargs)
+    "city_near": (2, 96, 48, (106.06, 106.19, 51.42, 24.05), 5, 11, 1234, dict(depth_range="near")),
+    "kitti_odd": (2, 132, 70, (51.8, 102.87, 63.94, 44.45), 5, 12, 99,
+                  dict(depth_range="near", flip_every_other=True)),
+    "city_wide": (1, 64, 32, (70.7, 70.8, 34.3, 16.0), 4, 13, 7, dict(depth_range="wide")),
+}
+
+
+def main():
+    from codeps_b200.synthetic import make_batch
+    from oracle.photo_oracle import draw_noise
+    ref_depth, ref_misc = import_reference()
+    out_dir = os.path.join(REPO, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    torch.set_num_threads(1)  # fixed reduction order for the committed numbers
+    for name, (b, w, h, k, scales, seed, noise_seed, kw) in CASES.items():
+        batch = make_batch(b, w, h, k, seed=seed, **kw)
+        blob = {
+            "width": w, "height": h, "num_scales": scales, "noise_seed": noise_seed,
+            "tgt": batch.images[0].numpy(), "prev": batch.images[1].numpy(),
+            "next": batch.images[2].numpy(), "disp": batch.disp.numpy(),
+            "depth": batch.depth.numpy(), "pose0": batch.poses[0].numpy(),
+            "pose1": batch.poses[1].numpy(), "intrinsics": batch.intrinsics.numpy(),
+        }
+        noise = draw_noise(b, w, h, scales, noise_seed)
+        for s, n in enumerate(noise):
+            blob[f"noise{s}"] = n.numpy()
+        ref32 = run_reference(ref_depth, ref_misc, batch, scales, noise_seed, torch.float32)
+        ref64 = run_reference(ref_depth, ref_misc, batch, scales, noise_seed, torch.float64, noise)
+        blob.update({f"ref32_{k_}": v for k_, v in ref32.items()})
+        # fp64: keep what the tie arbiter and tolerance checks need, in fp64
+        for key in ("recon", "smooth", "grad_depth", "grad_disp", "grad_pose0", "grad_pose1"):
+            blob[f"ref64_{key}"] = ref64[key]
+        for s in range(scales):
+            top2 = np.sort(ref64[f"cand{s}"], axis=1)[:, :2]
+            blob[f"ref64_gap{s}"] = (top2[:, 1] - top2[:, 0]).astype(np.float32)
+            blob[f"ref64_argmin{s}"] = ref64[f"argmin{s}"]
+        if name == "city_near":
+            blob.update(standalone_ops(ref_depth, ref_misc, batch))
+        path = os.path.join(out_dir, f"{name}.npz")
+        np.savez_compressed(path, **blob)
+        print(f"{name}: recon={float(ref32['recon']):.9f} smooth={float(ref32['smooth']):.9f} "
+              f"hist0={np.bincount(ref32['argmin0'].ravel(), minlength=4).tolist()} "
+              f"-> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,218 @@
+"""CPU oracle for the photometric-loss hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, op for op, what the CoDEPS reference computes on the path
+``ReconstructionLoss`` + ``SSIMLoss`` + ``EdgeAwareSmoothnessLoss`` on top of
+``ImageWarper`` / ``CameraModel``.  It exists to check the CUDA kernels; it is imported
+only by ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs, never
+by the ``codeps_b200`` package (which has no CPU path at all).
+
+Parity pin: the reference has no tests or golden vectors for this path,
+but it is importable in the build container.  ``oracle/make_golden.py`` runs the *reference
+itself* (imported from /root/reference) on seeded inputs and commits its outputs under
+``tests/golden/``; ``tests/test_oracle_golden.py`` requires this oracle to reproduce them
+(bit-for-bit on the argmin, to float rounding on values).  So: parity pinned against
+outputs of the reference run in the build container.
+
+The arithmetic all lives in PyTorch ATen ops (reference pins torch==1.12.1,
+/root/reference/requirements.txt:1; validated here with torch 2.11): ``upsample_bilinear2d``
+(align_corners=False), ``bmm``, ``grid_sampler_2d`` (bilinear, border, align_corners=True),
+``reflection_pad2d``, ``avg_pool2d``, ``clamp``, ``min``.  The oracle calls the same ATen ops
+in the same order so that in fp32 it tracks the reference to rounding, and it is
+dtype-generic: run it in fp64 (``dtype=torch.float64``) to arbitrate near-ties.
+
+Functions take intrinsics as a ``[B,4]`` array-like of (fx, fy, cx, cy) already scaled to the
+image size of the call.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+SSIM_C1 = 0.01**2  # /root/reference/algos/depth.py:125
+SSIM_C2 = 0.03**2  # /root/reference/algos/depth.py:126
+Z_MIN = 1e-5  # /root/reference/misc/image_warper.py:32
+
+
+def _k_columns(intrinsics, like: torch.Tensor):
+    """[B,4] intrinsics -> four [B,1,1] tensors in ``like``'s dtype (each value is first
+    rounded to fp32, which is what the reference's python-scalar-meets-fp32-tensor rule does)."""
+    k = torch.as_tensor(intrinsics, dtype=torch.float32).to(like.dtype).to(like.device)
+    return [k[:, i].view(-1, 1, 1) for i in range(4)]
+
+
+def unit_rays(intrinsics, height: int, width: int, like: torch.Tensor):
+    """Unit viewing ray per pixel: /root/reference/misc/camera_model.py:52-71 evaluated on
+    the pixel grid of /root/reference/misc/image_warper.py:62-66.  Returns three [B,H,W]."""
+    fx, fy, cx, cy = _k_columns(intrinsics, like)
+    u = torch.arange(width, dtype=like.dtype, device=like.device).view(1, 1, width)
+    v = torch.arange(height, dtype=like.dtype, device=like.device).view(1, height, 1)
+    rx = ((u - cx) / fx).expand(-1, height, -1)
+    ry = ((v - cy) / fy).expand(-1, -1, width)
+    norm = torch.sqrt(rx**2 + ry**2 + 1.0)
+    return rx / norm, ry / norm, 1.0 / norm
+
+
+def backproject(depth: torch.Tensor, intrinsics) -> torch.Tensor:
+    """depth [B,1,H,W] -> point cloud [B,3,H,W] (image_warper.py:68-87): the ray is scaled so
+    that its z component equals the depth value."""
+    _, _, h, w = depth.shape
+    rx, ry, rz = (r.unsqueeze(1) for r in unit_rays(intrinsics, h, w, depth))
+    return torch.cat((depth / rz.abs() * rx, depth / rz.abs() * ry, depth / rz.abs() * rz), dim=1)
+
+
+def reproject_grid(depth: torch.Tensor, pose: torch.Tensor, intrinsics,
+                   motion: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Normalised sampling grid [B,H,W,2] (image_warper.py:100-144 and :20-51)."""
+    b, _, h, w = depth.shape
+    cloud = backproject(depth, intrinsics)
+    homo = torch.cat((cloud, torch.ones_like(depth)), dim=1).view(b, 4, -1)
+    moved = torch.bmm(pose, homo).view(b, 4, h, w)
+    if motion is not None:
+        moved = torch.cat((moved[:, :3] + motion, moved[:, 3:]), dim=1)
+    eucl = moved[:, :3] / moved[:, 3:4]
+    fx, fy, cx, cy = _k_columns(intrinsics, depth)
+    z = eucl[:, 2].clamp(min=Z_MIN)
+    u = (eucl[:, 0] / z) * fx + cx
+    v = (eucl[:, 1] / z) * fy + cy
+    gx = (u / (w - 1) - 0.5) * 2
+    gy = (v / (h - 1) - 0.5) * 2
+    return torch.stack((gx, gy), dim=3)
+
+
+def warp_image(src: torch.Tensor, depth: torch.Tensor, pose: torch.Tensor, intrinsics,
+               mode: str = "bilinear", motion: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ImageWarper.forward (image_warper.py:153-184)."""
+    grid = reproject_grid(depth, pose, intrinsics, motion)
+    return F.grid_sample(src, grid, mode=mode, padding_mode="border", align_corners=True)
+
+
+def ssim_loss_map(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """SSIMLoss.__call__ (algos/depth.py:128-155): 3x3 box statistics on reflect-padded
+    inputs; returns clamp((1-SSIM)/2, 0, 1) per channel."""
+    xp = F.pad(x, (1, 1, 1, 1), mode="reflect")
+    yp = F.pad(y, (1, 1, 1, 1), mode="reflect")
+    box = lambda t: F.avg_pool2d(t, 3, 1)
+    mu_x, mu_y = box(xp), box(yp)
+    var_x = box(xp**2) - mu_x**2
+    var_y = box(yp**2) - mu_y**2
+    cov = box(xp * yp) - mu_x * mu_y
+    num = (2 * mu_x * mu_y + SSIM_C1) * (2 * cov + SSIM_C2)
+    den = (mu_x**2 + mu_y**2 + SSIM_C1) * (var_x + var_y + SSIM_C2)
+    return torch.clamp((1 - num / den) / 2, 0, 1)
+
+
+def photometric_error(pred: torch.Tensor, tgt: torch.Tensor, alpha: float = 0.85) -> torch.Tensor:
+    """ReconstructionLoss._compute_loss (algos/depth.py:221-237) -> [B,1,H,W]."""
+    l1 = (pred - tgt).abs().mean(1, True)
+    ssim = ssim_loss_map(pred, tgt).mean(1, True)
+    return alpha * ssim + (1 - alpha) * l1
+
+
+def resize_bilinear(x: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """Interpolate(..., "bilinear") (algos/depth.py:158-173): always from full resolution."""
+    return F.interpolate(x, (height, width), mode="bilinear", align_corners=False)
+
+
+def scaled_intrinsics(intrinsics, full_wh: Tuple[int, int], level_wh: Tuple[int, int]):
+    """camera_model.py:36-41 applied to a [B,4] fp32 table: focal length and principal point
+    scale with the ratio of image sizes (python-float ratio, fp32 product)."""
+    import numpy as np
+    k = np.asarray(intrinsics, dtype=np.float32)
+    su = level_wh[0] / full_wh[0]
+    sv = level_wh[1] / full_wh[1]
+    out = np.empty_like(k)
+    out[:, 0] = k[:, 0] * np.float32(su)
+    out[:, 1] = k[:, 1] * np.float32(sv)
+    out[:, 2] = k[:, 2] * np.float32(su)
+    out[:, 3] = k[:, 3] * np.float32(sv)
+    return out
+
+
+def reconstruction_loss(intrinsics, images: Sequence[torch.Tensor], depth: torch.Tensor,
+                        poses: Sequence[torch.Tensor], noise: Sequence[torch.Tensor],
+                        num_scales: int = 5, alpha: float = 0.85,
+                        motions: Optional[Sequence[torch.Tensor]] = None,
+                        level_intrinsics: Optional[Sequence] = None, details: bool = False):
+    """ReconstructionLoss.__call__ (algos/depth.py:239-326), auto-mask branch.
+
+    ``noise[s]`` is the [B,2,H_s,W_s] tensor the reference would draw with ``torch.randn`` at
+    level s (depth.py:317) -- *unscaled*; it is multiplied by 1e-5 here.  ``level_intrinsics``
+    optionally overrides the per-level [B,4] tables (used when the caller has CameraModel
+    objects and wants the exact python-side rounding).  With ``details`` also returns, per
+    level, the stacked candidate losses [B,4,H_s,W_s] and the argmin [B,H_s,W_s] (index 0/1 =
+    reprojection from t-1/t+1, 2/3 = identity, i.e. auto-masked), which the reference
+    computes and discards (depth.py:323).
+    """
+    _, _, h, w = depth.shape
+    total = torch.zeros(1, dtype=depth.dtype, device=depth.device)
+    per_level = []
+    for s in range(num_scales):
+        ws, hs = w // 2**s, h // 2**s
+        k_s = (level_intrinsics[s] if level_intrinsics is not None else scaled_intrinsics(
+            intrinsics, (w, h), (ws, hs)))
+        tgt_s = resize_bilinear(images[0], hs, ws)
+        depth_s = resize_bilinear(depth, hs, ws)
+        cands = []
+        for i, frame in enumerate(images[1:]):
+            src_s = resize_bilinear(frame, hs, ws)
+            motion_s = None if motions is None else resize_bilinear(motions[i], hs, ws)
+            warped = warp_image(src_s, depth_s, poses[i], k_s, motion=motion_s)
+            cands.append(photometric_error(warped, tgt_s, alpha))
+        ident = [photometric_error(resize_bilinear(frame, hs, ws), tgt_s, alpha)
+                 for frame in images[1:]]
+        ident = torch.cat(ident, 1) + noise[s].to(depth.dtype) * 0.00001
+        stacked = torch.cat(cands + [ident], dim=1)
+        best, which = torch.min(stacked, dim=1)
+        total = total + best.mean() / (2**s)
+        per_level.append((stacked, which))
+    loss = total[0] / num_scales
+    return (loss, per_level) if details else loss
+
+
+def smoothness_loss(target_image: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
+    """EdgeAwareSmoothnessLoss.__call__ (algos/depth.py:58-107)."""
+    mean_disp = disp.mean(2, True).mean(3, True)
+    d = disp / (mean_disp + 1e-7)
+    ddx = (d[:, :, :, :-1] - d[:, :, :, 1:]).abs()
+    ddy = (d[:, :, :-1, :] - d[:, :, 1:, :]).abs()
+    idx = (target_image[:, :, :, :-1] - target_image[:, :, :, 1:]).abs().mean(1, True)
+    idy = (target_image[:, :, :-1, :] - target_image[:, :, 1:, :]).abs().mean(1, True)
+    return (ddx * torch.exp(-idx)).mean() + (ddy * torch.exp(-idy)).mean()
+
+
+def draw_noise(batch: int, width: int, height: int, num_scales: int, seed: int,
+               device="cpu") -> List[torch.Tensor]:
+    """The tie-break noise sequence the reference consumes (depth.py:317): one
+    ``torch.randn(B,2,H_s,W_s)`` per level, in level order, from ``torch.manual_seed(seed)``."""
+    torch.manual_seed(seed)
+    return [torch.randn(batch, 2, height // 2**s, width // 2**s, device=device)
+            for s in range(num_scales)]
+
+
+def loss_and_grads(intrinsics, images, depth, disp, poses, noise, num_scales=5, alpha=0.85,
+                   dtype=torch.float32, recon_weight: float = 1.0, smooth_weight: float = 1.0,
+                   level_intrinsics=None):
+    """Forward + autograd backward of (recon, smooth) on the CPU.  Returns a dict with the two
+    loss values, per-level argmin/candidates and dL/d depth, dL/d disp, dL/dT_0, dL/dT_1 of
+    ``recon_weight*recon + smooth_weight*smooth`` (depth and disp are treated as independent
+    leaves, as at the boundary of the CUDA op)."""
+    cast = lambda t: t.detach().to(dtype)
+    images = [cast(i) for i in images]
+    depth = cast(depth).requires_grad_(True)
+    disp = cast(disp).requires_grad_(True)
+    poses = [cast(p).requires_grad_(True) for p in poses]
+    recon, levels = reconstruction_loss(intrinsics, images, depth, poses, noise, num_scales,
+                                        alpha, level_intrinsics=level_intrinsics, details=True)
+    smooth = smoothness_loss(images[0], disp)
+    (recon_weight * recon + smooth_weight * smooth).backward()
+    return {
+        "recon": recon.detach(),
+        "smooth": smooth.detach(),
+        "argmin": [w.to(torch.uint8) for _, w in levels],
+        "candidates": [c.detach() for c, _ in levels],
+        "grad_depth": depth.grad,
+        "grad_disp": disp.grad,
+        "grad_pose": [p.grad for p in poses],
+    }
