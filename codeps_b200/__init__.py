@@ -1,2 +1,14 @@
-"""codeps_b200 -- B200-native photometric reprojection loss for CoDEPS."""
-from .camera import CameraModel  # noqa: F401
+"""codeps_b200 -- B200-native photometric reprojection loss for CoDEPS.
+
+Drop-in replacements for the reference's hot-path classes (``CameraModel``, ``ImageWarper``,
+``SSIMLoss``, ``ReconstructionLoss``, ``EdgeAwareSmoothnessLoss``) on top of hand-written
+sm_100a CUDA kernels behind a C ABI (include/codeps_photo.h).  See DESIGN.md.
+"""
+from .camera import CameraModel
+from .install import install, uninstall
+from .losses import EdgeAwareSmoothnessLoss, ReconstructionLoss, SSIMLoss
+from .warper import CoordinateWarper, ImageWarper
+
+__all__ = ["CameraModel", "ImageWarper", "CoordinateWarper", "SSIMLoss", "ReconstructionLoss",
+           "EdgeAwareSmoothnessLoss", "install", "uninstall"]
+__version__ = "0.1.0"

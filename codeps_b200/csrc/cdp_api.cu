@@ -1,0 +1,539 @@
+// cdp_api.cu -- sm_100a kernels and the C ABI of libcodeps_photo.so (see include/codeps_photo.h).
+//
+// Kernel bodies live in cdp_kernels.h / cdp_math.h; this file adds the __global__ wrappers
+// (shared-memory staging, block barriers, fixed-order block reductions) and the host-side entry
+// points (argument checks, launch planning, error reporting).  There is no CPU code path here:
+// every entry point enqueues CUDA kernels on the caller's stream or fails.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "cdp_plan.h"
+
+// ------------------------------------------------------------------------------------------
+// error reporting
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int cdp_fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CDP_REQUIRE(cond, ...) \
+  do { if (!(cond)) return cdp_fail(CDP_ERR_INVALID, __VA_ARGS__); } while (0)
+
+#define CDP_CUDA(expr) \
+  do { cudaError_t e_ = (expr); \
+       if (e_ != cudaSuccess) return cdp_fail(CDP_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } while (0)
+
+#define CDP_LAUNCH_CHECK(name) \
+  do { cudaError_t e_ = cudaGetLastError(); \
+       if (e_ != cudaSuccess) return cdp_fail(CDP_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); } while (0)
+
+extern "C" int cdp_version(void) { return CDP_ABI_VERSION; }
+extern "C" const char* cdp_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int cdp_device_check(void) {
+  int dev = 0, major = 0;
+  CDP_CUDA(cudaGetDevice(&dev));
+  CDP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return cdp_fail(CDP_ERR_UNSUPPORTED, "device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+  return CDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// optional per-kernel timing (cdp_profile_*): CUDA events recorded on the launch stream around
+// each kernel while enabled.  Off by default; must not be enabled during stream capture.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct ProfRecord { int id; cudaEvent_t start, stop; };
+std::mutex g_prof_mutex;
+std::vector<ProfRecord> g_prof_records;
+bool g_prof_enabled = false;
+
+struct ProfScope {
+  bool on;
+  ProfRecord rec;
+  cudaStream_t stream;
+  ProfScope(int id, cudaStream_t s) : on(g_prof_enabled), stream(s) {
+    if (!on) return;
+    rec.id = id;
+    if (cudaEventCreate(&rec.start) != cudaSuccess || cudaEventCreate(&rec.stop) != cudaSuccess) { on = false; return; }
+    cudaEventRecord(rec.start, stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(rec.stop, stream);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof_records.push_back(rec);
+  }
+};
+}  // namespace
+
+extern "C" int cdp_profile_enable(int32_t enable) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  for (auto& r : g_prof_records) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+  g_prof_records.clear();
+  g_prof_enabled = enable != 0;
+  return CDP_OK;
+}
+
+extern "C" int cdp_profile_read(int32_t kernel_id, double* total_ms, int32_t* launches) {
+  CDP_REQUIRE(total_ms && launches, "null pointer");
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  double tot = 0.0;
+  int n = 0;
+  for (auto& r : g_prof_records) {
+    if (r.id != kernel_id) continue;
+    CDP_CUDA(cudaEventSynchronize(r.stop));
+    float ms = 0.f;
+    CDP_CUDA(cudaEventElapsedTime(&ms, r.start, r.stop));
+    tot += ms;
+    ++n;
+  }
+  *total_ms = tot;
+  *launches = n;
+  return CDP_OK;
+}
+
+// cudaFuncSetAttribute once per device (and never during stream capture after the first call)
+template <typename K>
+static cudaError_t cdp_allow_smem(K kernel, size_t bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && (*done_mask >> dev) & 1ull) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev < 64) *done_mask |= 1ull << dev;
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+// Sum N per-thread values over the block in a fixed order (shuffle tree inside a warp, then
+// warps in index order) and let thread j < N write total j to out[j].  red: >= nwarps*N floats.
+template <int N>
+__device__ __forceinline__ void cdp_block_reduce_store(float (&v)[N], float* red, float* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], off);
+    if (lane == 0) red[warp * N + i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float acc = 0.f;
+    for (int w = 0; w < nwarps; ++w) acc += red[w * N + threadIdx.x];
+    out[threadIdx.x] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cdp_pyramid_fwd_kernel(const __grid_constant__ CdpPyrParams p) {
+  cdp_pyramid_fwd_item(p, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+template <bool G>
+__global__ void __launch_bounds__(CDP_PHOTO_THREADS, 2)
+cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const CdpTileCtx c = cdp_tile_ctx(p, blockIdx.x, blockIdx.y);
+  cdp_photo_phase_a<G>(p, c, threadIdx.x, blockDim.x, sm);
+  __syncthreads();
+  cdp_photo_phase_b1<G>(p, c, threadIdx.x, blockDim.x, sm);
+  __syncthreads();
+  float v[G ? 33 : 1];
+#pragma unroll
+  for (int i = 0; i < (G ? 33 : 1); ++i) v[i] = 0.f;
+  cdp_photo_phase_b2<G>(p, c, threadIdx.x, blockDim.x, sm, v[0]);
+  if constexpr (G) {
+    __syncthreads();
+    cdp_photo_phase_c(p, c, threadIdx.x, blockDim.x, sm, &v[1]);
+  }
+  v[0] *= p.lv[c.lvl].weight;
+  __syncthreads();  // tile planes are dead: reuse shared memory for the reduction
+  float* rec = p.partials + ((size_t)c.b * p.blocks_per_image + blockIdx.x) * CDP_PARTIAL_STRIDE;
+  cdp_block_reduce_store(v, sm, rec);
+  if (!G && threadIdx.x >= 1 && threadIdx.x < 33) rec[threadIdx.x] = 0.f;
+}
+
+__global__ void __launch_bounds__(CDP_FINALIZE_THREADS) cdp_finalize_kernel(const CdpFinalizeParams p) {
+  __shared__ double sm[32 * 33];
+  double loss_acc = 0.0;
+  for (int b = 0; b < p.B; ++b) {
+    cdp_finalize_phase_a(p, b, threadIdx.x, sm);
+    __syncthreads();
+    cdp_finalize_phase_b(p, b, threadIdx.x, sm, &loss_acc);
+    __syncthreads();
+  }
+  if (threadIdx.x == 32) p.loss[0] = (float)loss_acc;
+}
+
+__global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_constant__ CdpDepthGradParams p) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < p.H * p.W) cdp_depth_grad_pixel(p, blockIdx.y, pix);
+  if (blockIdx.x == 0 && blockIdx.y == 0)
+    for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
+}
+
+__global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_sum_kernel(const CdpSmoothParams p) {
+  __shared__ float red[CDP_SMOOTH_THREADS / 32];
+  float v[1] = {cdp_smooth_sum_thread(p, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x)};
+  cdp_block_reduce_store(v, red, p.part_sum + blockIdx.y * CDP_SMOOTH_BLOCKS + blockIdx.x);
+}
+
+__global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_main_kernel(const CdpSmoothParams p) {
+  __shared__ float red[3 * CDP_SMOOTH_THREADS / 32];
+  __shared__ float mean_s;
+  if (threadIdx.x == 0) mean_s = cdp_smooth_mean(p, blockIdx.y);
+  __syncthreads();
+  float v[3] = {0.f, 0.f, 0.f};
+  cdp_smooth_main_thread(p, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, mean_s, v);
+  cdp_block_reduce_store(v, red, p.part_main + ((size_t)blockIdx.y * CDP_SMOOTH_BLOCKS + blockIdx.x) * 4);
+}
+
+__global__ void cdp_smooth_finalize_kernel(const CdpSmoothParams p) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) cdp_smooth_finalize(p);
+}
+
+__global__ void __launch_bounds__(256)
+cdp_smooth_bwd_kernel(const float* g, const float* scal, const float* grad_loss, int plane, float* grad_disp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < plane) cdp_smooth_bwd_pixel(g, scal, grad_loss, blockIdx.y, (size_t)plane, i, grad_disp);
+}
+
+__global__ void __launch_bounds__(256) cdp_warp_grid_kernel(const __grid_constant__ CdpWarpParams p) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < p.H * p.W) cdp_warp_grid_pixel(p, blockIdx.y, pix);
+}
+
+__global__ void __launch_bounds__(256) cdp_warp_image_kernel(const __grid_constant__ CdpWarpParams p) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < p.H * p.W) cdp_warp_image_pixel(p, blockIdx.y, pix);
+}
+
+__global__ void __launch_bounds__(256) cdp_warp_bwd_kernel(const __grid_constant__ CdpWarpParams p) {
+  __shared__ float red[16 * 8];
+  float dT[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dT[i] = 0.f;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < p.H * p.W) cdp_warp_bwd_pixel(p, blockIdx.y, pix, dT);
+  const int b = p.batch_begin + blockIdx.y;
+  cdp_block_reduce_store(dT, red, p.partials + ((size_t)b * gridDim.x + blockIdx.x) * 16);
+}
+
+// sum [B][blocks][16] partials over blocks: one block per image, 16 columns x 16 strided rows
+__global__ void __launch_bounds__(256)
+cdp_pose_partials_kernel(const float* partials, int blocks, float* grad_pose) {
+  __shared__ double sm[16 * 16];
+  const int r = threadIdx.x >> 4, j = threadIdx.x & 15, b = blockIdx.x;
+  double acc = 0.0;
+  for (int i = r; i < blocks; i += 16) acc += (double)partials[((size_t)b * blocks + i) * 16 + j];
+  sm[r * 16 + j] = acc;
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double tot = 0.0;
+    for (int i = 0; i < 16; ++i) tot += sm[i * 16 + threadIdx.x];
+    grad_pose[b * 16 + threadIdx.x] = (float)tot;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cdp_ssim_fwd_kernel(const float* x, const float* y, int W, int H, float* out) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < W * H) cdp_ssim_fwd_pixel(x, y, W, H, blockIdx.y, pix, out);
+}
+
+__global__ void __launch_bounds__(256)
+cdp_ssim_bwd_coef_kernel(const float* go, const float* x, const float* y, int W, int H, float* scratch, size_t total) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < W * H) cdp_ssim_bwd_coef_pixel(go, x, y, W, H, blockIdx.y, pix, scratch, total);
+}
+
+__global__ void __launch_bounds__(256)
+cdp_ssim_bwd_gather_kernel(const float* x, const float* y, int W, int H, const float* scratch, size_t total,
+                           float* gx, float* gy) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < W * H) cdp_ssim_bwd_gather_pixel(x, y, W, H, blockIdx.y, pix, scratch, total, gx, gy);
+}
+
+// ------------------------------------------------------------------------------------------
+// resize tables
+// ------------------------------------------------------------------------------------------
+extern "C" size_t cdp_resize_tables_bytes(int32_t height, int32_t width, int32_t num_levels) {
+  CdpPlan plan;
+  if (!cdp_make_plan(1, height, width, num_levels, &plan)) return 0;
+  return (plan.tab_records > 0 ? plan.tab_records : 1) * sizeof(CdpResizeTap);
+}
+
+extern "C" int cdp_resize_tables_build(int32_t height, int32_t width, int32_t num_levels, void* host_out,
+                                       size_t host_bytes) {
+  CdpPlan plan;
+  CDP_REQUIRE(cdp_make_plan(1, height, width, num_levels, &plan), "invalid pyramid %dx%d, %d levels", width, height, num_levels);
+  CDP_REQUIRE(host_out != nullptr, "host_out is null");
+  if (host_bytes < cdp_resize_tables_bytes(height, width, num_levels))
+    return cdp_fail(CDP_ERR_WORKSPACE, "resize table buffer too small");
+  static_assert(sizeof(CdpResizeTap) == 16 && sizeof(CdpResizeInv) == 16, "table records are 16 bytes");
+  int bad = 0;
+  if (!cdp_build_resize_tables(plan, host_out, &bad))
+    return cdp_fail(CDP_ERR_UNSUPPORTED, "resize adjoint needs more than two taps per pixel at level %d", bad);
+  return CDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// photometric loss
+// ------------------------------------------------------------------------------------------
+extern "C" size_t cdp_photo_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels) {
+  CdpPlan plan;
+  if (!cdp_make_plan(batch, height, width, num_levels, &plan)) return 0;
+  return plan.scratch_floats * sizeof(float);
+}
+
+extern "C" size_t cdp_photo_saved_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels) {
+  CdpPlan plan;
+  if (!cdp_make_plan(batch, height, width, num_levels, &plan)) return 0;
+  return plan.saved_floats * sizeof(float);
+}
+
+static int cdp_batch_chunks(int32_t batch) { return (batch + CDP_MAX_BATCH_PER_LAUNCH - 1) / CDP_MAX_BATCH_PER_LAUNCH; }
+
+extern "C" int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels) {
+  return (num_levels > 1 ? 1 : 0) + cdp_batch_chunks(batch) + 1;
+}
+extern "C" int cdp_photo_bwd_launches(int32_t, int32_t) { return 1; }
+
+extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
+  CDP_REQUIRE(a != nullptr, "args is null");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CdpPlan plan;
+  CDP_REQUIRE(cdp_make_plan(a->batch, a->height, a->width, a->num_levels, &plan),
+              "invalid shape: batch %d, %dx%d, %d levels (every level needs >= 2x2 pixels, at most %d levels)",
+              a->batch, a->width, a->height, a->num_levels, CDP_MAX_LEVELS);
+  CDP_REQUIRE(a->intrinsics_host && a->target && a->source0 && a->source1 && a->depth && a->pose0 && a->pose1 && a->loss,
+              "null tensor pointer");
+  CDP_REQUIRE(a->scratch != nullptr, "scratch is null");
+  if (a->scratch_bytes < plan.scratch_floats * sizeof(float))
+    return cdp_fail(CDP_ERR_WORKSPACE, "scratch too small: %zu < %zu", a->scratch_bytes, plan.scratch_floats * sizeof(float));
+  const bool G = a->with_grad != 0;
+  if (G) {
+    CDP_REQUIRE(a->saved != nullptr, "with_grad needs a saved buffer");
+    if (a->saved_bytes < plan.saved_floats * sizeof(float))
+      return cdp_fail(CDP_ERR_WORKSPACE, "saved too small: %zu < %zu", a->saved_bytes, plan.saved_floats * sizeof(float));
+  }
+  CDP_REQUIRE(plan.L == 1 || a->resize_tables != nullptr, "resize_tables is null");
+  bool any_noise = false, all_noise = true;
+  for (int s = 0; s < plan.L; ++s) { any_noise |= a->noise[s] != nullptr; all_noise &= a->noise[s] != nullptr; }
+  CDP_REQUIRE(!any_noise || all_noise, "noise must be given for every level or for none");
+
+  // 1. pyramid
+  if (plan.L > 1) {
+    CdpPyrParams pp;
+    cdp_fill_pyr_params(plan, a, &pp);
+    dim3 grid((plan.pyr_begin[plan.L] + 255) / 256, plan.B);
+    { ProfScope prof_(CDP_KERNEL_PYRAMID, stream); cdp_pyramid_fwd_kernel<<<grid, 256, 0, stream>>>(pp); }
+    CDP_LAUNCH_CHECK("cdp_pyramid_fwd_kernel");
+  }
+
+  // 2. fused tile kernel, all levels per launch, <= CDP_MAX_BATCH_PER_LAUNCH samples per launch
+  const size_t smem = G ? CdpTileGeom<true>::SMEM_BYTES : CdpTileGeom<false>::SMEM_BYTES;
+  static unsigned long long smem_done[2] = {0ull, 0ull};
+  if (G) CDP_CUDA(cdp_allow_smem(cdp_photo_kernel<true>, smem, &smem_done[1]));
+  else CDP_CUDA(cdp_allow_smem(cdp_photo_kernel<false>, smem, &smem_done[0]));
+  for (int b0 = 0; b0 < plan.B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+    const int nb = cdp_chunk_size(plan.B, b0);
+    CdpPhotoParams kp;
+    cdp_fill_photo_params(plan, a, b0, nb, &kp);
+    dim3 grid(plan.blocks_per_image, nb);
+    {
+      ProfScope prof_(CDP_KERNEL_PHOTO, stream);
+      if (G) cdp_photo_kernel<true><<<grid, CDP_PHOTO_THREADS, smem, stream>>>(kp);
+      else cdp_photo_kernel<false><<<grid, CDP_PHOTO_THREADS, smem, stream>>>(kp);
+    }
+    CDP_LAUNCH_CHECK("cdp_photo_kernel");
+  }
+
+  // 3. fixed-order reduction of the per-CTA records
+  CdpFinalizeParams fp;
+  cdp_fill_finalize_params(plan, a, &fp);
+  { ProfScope prof_(CDP_KERNEL_FINALIZE, stream); cdp_finalize_kernel<<<1, CDP_FINALIZE_THREADS, 0, stream>>>(fp); }
+  CDP_LAUNCH_CHECK("cdp_finalize_kernel");
+  return CDP_OK;
+}
+
+extern "C" int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32_t num_levels, const void* saved_,
+                             size_t saved_bytes, const void* resize_tables, const float* grad_loss,
+                             float* grad_depth, float* grad_pose0, float* grad_pose1, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CdpPlan plan;
+  CDP_REQUIRE(cdp_make_plan(batch, height, width, num_levels, &plan), "invalid shape");
+  CDP_REQUIRE(saved_ && grad_loss && grad_depth && grad_pose0 && grad_pose1, "null pointer");
+  CDP_REQUIRE(plan.L == 1 || resize_tables != nullptr, "resize_tables is null");
+  if (saved_bytes < plan.saved_floats * sizeof(float)) return cdp_fail(CDP_ERR_WORKSPACE, "saved too small");
+  CdpDepthGradParams p;
+  cdp_fill_depth_grad_params(plan, saved_, resize_tables, grad_loss, grad_depth, grad_pose0, grad_pose1, &p);
+  dim3 grid((plan.H * plan.W + 255) / 256, plan.B);
+  { ProfScope prof_(CDP_KERNEL_DEPTH_GRAD, stream); cdp_depth_grad_kernel<<<grid, 256, 0, stream>>>(p); }
+  CDP_LAUNCH_CHECK("cdp_depth_grad_kernel");
+  return CDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// smoothness
+// ------------------------------------------------------------------------------------------
+extern "C" size_t cdp_smooth_saved_bytes(int32_t batch, int32_t height, int32_t width) {
+  if (batch <= 0 || height < 2 || width < 2) return 0;
+  return cdp_smooth_layout(batch, height, width).total * sizeof(float);
+}
+
+extern "C" int cdp_smooth_fwd(const float* image, const float* disp, int32_t batch, int32_t height, int32_t width,
+                              int32_t with_grad, float* loss, void* saved_, size_t saved_bytes, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(batch > 0 && height >= 2 && width >= 2, "invalid shape: batch %d, %dx%d (needs >= 2x2)", batch, width, height);
+  CDP_REQUIRE(image && disp && loss && saved_, "null pointer");
+  const CdpSmoothLayout l = cdp_smooth_layout(batch, height, width);
+  if (saved_bytes < l.total * sizeof(float)) return cdp_fail(CDP_ERR_WORKSPACE, "saved too small: %zu < %zu", saved_bytes, l.total * sizeof(float));
+  float* saved = static_cast<float*>(saved_);
+  CdpSmoothParams p;
+  cdp_fill_smooth_params(image, disp, batch, height, width, with_grad, loss, saved, &p);
+  dim3 grid(CDP_SMOOTH_BLOCKS, batch);
+  { ProfScope prof_(CDP_KERNEL_SMOOTH_SUM, stream); cdp_smooth_sum_kernel<<<grid, CDP_SMOOTH_THREADS, 0, stream>>>(p); }
+  CDP_LAUNCH_CHECK("cdp_smooth_sum_kernel");
+  { ProfScope prof_(CDP_KERNEL_SMOOTH_MAIN, stream); cdp_smooth_main_kernel<<<grid, CDP_SMOOTH_THREADS, 0, stream>>>(p); }
+  CDP_LAUNCH_CHECK("cdp_smooth_main_kernel");
+  { ProfScope prof_(CDP_KERNEL_SMOOTH_FINALIZE, stream); cdp_smooth_finalize_kernel<<<1, 32, 0, stream>>>(p); }
+  CDP_LAUNCH_CHECK("cdp_smooth_finalize_kernel");
+  return CDP_OK;
+}
+
+extern "C" int cdp_smooth_bwd(const void* saved_, size_t saved_bytes, const float* grad_loss, int32_t batch,
+                              int32_t height, int32_t width, float* grad_disp, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(batch > 0 && height >= 2 && width >= 2, "invalid shape");
+  CDP_REQUIRE(saved_ && grad_loss && grad_disp, "null pointer");
+  const CdpSmoothLayout l = cdp_smooth_layout(batch, height, width);
+  if (saved_bytes < l.total * sizeof(float)) return cdp_fail(CDP_ERR_WORKSPACE, "saved too small");
+  const float* saved = static_cast<const float*>(saved_);
+  const int plane = height * width;
+  dim3 grid((plane + 255) / 256, batch);
+  { ProfScope prof_(CDP_KERNEL_SMOOTH_BWD, stream); cdp_smooth_bwd_kernel<<<grid, 256, 0, stream>>>(saved + l.g, saved + l.scal, grad_loss, plane, grad_disp); }
+  CDP_LAUNCH_CHECK("cdp_smooth_bwd_kernel");
+  return CDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone operators
+// ------------------------------------------------------------------------------------------
+extern "C" int cdp_warp_grid_fwd(const float* depth, const float* pose, const float* motion, const float* K,
+                                 int32_t batch, int32_t height, int32_t width, float* grid_out, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(batch > 0 && height >= 2 && width >= 2, "invalid shape");
+  CDP_REQUIRE(depth && pose && K && grid_out, "null pointer");
+  for (int b0 = 0; b0 < batch; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+    const int nb = cdp_chunk_size(batch, b0);
+    CdpWarpParams p;
+    cdp_fill_warp_params(&p, nullptr, 0, depth, pose, motion, K, b0, nb, height, width);
+    p.out = grid_out;
+    dim3 grid((height * width + 255) / 256, nb);
+    cdp_warp_grid_kernel<<<grid, 256, 0, stream>>>(p);
+    CDP_LAUNCH_CHECK("cdp_warp_grid_kernel");
+  }
+  return CDP_OK;
+}
+
+extern "C" int cdp_warp_image_fwd(const float* src, int32_t channels, const float* depth, const float* pose,
+                                  const float* motion, const float* K, int32_t batch, int32_t height, int32_t width,
+                                  int32_t mode, float* out, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(batch > 0 && height >= 2 && width >= 2 && channels > 0, "invalid shape");
+  CDP_REQUIRE(src && depth && pose && K && out, "null pointer");
+  CDP_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (bilinear) or 1 (nearest)");
+  for (int b0 = 0; b0 < batch; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+    const int nb = cdp_chunk_size(batch, b0);
+    CdpWarpParams p;
+    cdp_fill_warp_params(&p, src, channels, depth, pose, motion, K, b0, nb, height, width);
+    p.out = out; p.mode = mode;
+    dim3 grid((height * width + 255) / 256, nb);
+    cdp_warp_image_kernel<<<grid, 256, 0, stream>>>(p);
+    CDP_LAUNCH_CHECK("cdp_warp_image_kernel");
+  }
+  return CDP_OK;
+}
+
+extern "C" size_t cdp_warp_bwd_scratch_bytes(int32_t batch, int32_t height, int32_t width) {
+  if (batch <= 0 || height <= 0 || width <= 0) return 0;
+  return (size_t)batch * ((height * width + 255) / 256) * 16 * sizeof(float);
+}
+
+extern "C" int cdp_warp_image_bwd(const float* grad_out, const float* src, int32_t channels, const float* depth,
+                                  const float* pose, const float* motion, const float* K, int32_t batch,
+                                  int32_t height, int32_t width, float* grad_depth, float* grad_pose,
+                                  float* grad_motion, void* scratch, size_t scratch_bytes, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(batch > 0 && height >= 2 && width >= 2 && channels > 0, "invalid shape");
+  CDP_REQUIRE(grad_out && src && depth && pose && K && grad_depth && grad_pose && scratch, "null pointer");
+  CDP_REQUIRE(!(grad_motion != nullptr && motion == nullptr), "grad_motion without motion");
+  if (scratch_bytes < cdp_warp_bwd_scratch_bytes(batch, height, width)) return cdp_fail(CDP_ERR_WORKSPACE, "scratch too small");
+  const int blocks = (height * width + 255) / 256;
+  for (int b0 = 0; b0 < batch; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+    const int nb = cdp_chunk_size(batch, b0);
+    CdpWarpParams p;
+    cdp_fill_warp_params(&p, src, channels, depth, pose, motion, K, b0, nb, height, width);
+    p.grad_out = grad_out; p.grad_depth = grad_depth; p.grad_motion = grad_motion;
+    p.partials = static_cast<float*>(scratch);
+    dim3 grid(blocks, nb);
+    cdp_warp_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+    CDP_LAUNCH_CHECK("cdp_warp_bwd_kernel");
+  }
+  cdp_pose_partials_kernel<<<batch, 256, 0, stream>>>(static_cast<const float*>(scratch), blocks, grad_pose);
+  CDP_LAUNCH_CHECK("cdp_pose_partials_kernel");
+  return CDP_OK;
+}
+
+extern "C" int cdp_ssim_fwd(const float* x, const float* y, int32_t planes, int32_t height, int32_t width, float* out,
+                            cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(planes > 0 && height >= 2 && width >= 2, "invalid shape (reflection padding needs >= 2x2)");
+  CDP_REQUIRE(x && y && out, "null pointer");
+  CDP_REQUIRE(planes <= 65535, "too many planes");
+  dim3 grid((height * width + 255) / 256, planes);
+  cdp_ssim_fwd_kernel<<<grid, 256, 0, stream>>>(x, y, width, height, out);
+  CDP_LAUNCH_CHECK("cdp_ssim_fwd_kernel");
+  return CDP_OK;
+}
+
+extern "C" size_t cdp_ssim_bwd_scratch_bytes(int32_t planes, int32_t height, int32_t width) {
+  if (planes <= 0 || height <= 0 || width <= 0) return 0;
+  return (size_t)4 * planes * height * width * sizeof(float);
+}
+
+extern "C" int cdp_ssim_bwd(const float* grad_out, const float* x, const float* y, int32_t planes, int32_t height,
+                            int32_t width, float* grad_x, float* grad_y, void* scratch, size_t scratch_bytes,
+                            cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(planes > 0 && height >= 2 && width >= 2, "invalid shape");
+  CDP_REQUIRE(grad_out && x && y && scratch, "null pointer");
+  CDP_REQUIRE(planes <= 65535, "too many planes");
+  if (scratch_bytes < cdp_ssim_bwd_scratch_bytes(planes, height, width)) return cdp_fail(CDP_ERR_WORKSPACE, "scratch too small");
+  const size_t total = (size_t)planes * height * width;
+  dim3 grid((height * width + 255) / 256, planes);
+  cdp_ssim_bwd_coef_kernel<<<grid, 256, 0, stream>>>(grad_out, x, y, width, height, static_cast<float*>(scratch), total);
+  CDP_LAUNCH_CHECK("cdp_ssim_bwd_coef_kernel");
+  cdp_ssim_bwd_gather_kernel<<<grid, 256, 0, stream>>>(x, y, width, height, static_cast<const float*>(scratch), total, grad_x, grad_y);
+  CDP_LAUNCH_CHECK("cdp_ssim_bwd_gather_kernel");
+  return CDP_OK;
+}

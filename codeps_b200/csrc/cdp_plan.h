@@ -1,0 +1,124 @@
+// cdp_plan.h -- host-side construction of the kernel parameter blocks from the C-ABI arguments.
+// Shared by cdp_api.cu (which launches the kernels) and tests/emu (which loops over them on the
+// CPU), so that the launch planning itself is covered by the CPU-side tests.
+#pragma once
+
+#include "cdp_kernels.h"
+
+static inline int cdp_chunk_size(int B, int b0) {
+  return B - b0 < CDP_MAX_BATCH_PER_LAUNCH ? B - b0 : CDP_MAX_BATCH_PER_LAUNCH;
+}
+
+static inline void cdp_fill_pyr_params(const CdpPlan& plan, const cdp_photo_args* a, CdpPyrParams* pp) {
+  memset(pp, 0, sizeof(*pp));
+  float* scratch = static_cast<float*>(a->scratch);
+  pp->in[0] = a->target; pp->in[1] = a->source0; pp->in[2] = a->source1; pp->in[3] = a->depth;
+  const CdpResizeTap* tab = static_cast<const CdpResizeTap*>(a->resize_tables);
+  for (int s = 1; s < plan.L; ++s) {
+    pp->out[0][s] = scratch + plan.off_tgt[s]; pp->out[1][s] = scratch + plan.off_src0[s];
+    pp->out[2][s] = scratch + plan.off_src1[s]; pp->out[3][s] = scratch + plan.off_depth[s];
+    pp->tab_x[s] = tab + plan.tab_fwd_x[s]; pp->tab_y[s] = tab + plan.tab_fwd_y[s];
+  }
+  for (int s = 0; s < plan.L; ++s) { pp->Ws[s] = plan.Ws[s]; pp->Hs[s] = plan.Hs[s]; }
+  for (int s = 0; s <= plan.L; ++s) pp->begin[s] = plan.pyr_begin[s];
+  pp->W = plan.W; pp->H = plan.H; pp->L = plan.L;
+}
+
+static inline void cdp_fill_photo_params(const CdpPlan& plan, const cdp_photo_args* a, int b0, int nb,
+                                         CdpPhotoParams* kp) {
+  memset(kp, 0, sizeof(*kp));
+  float* scratch = static_cast<float*>(a->scratch);
+  float* saved = static_cast<float*>(a->saved);
+  const bool G = a->with_grad != 0;
+  for (int s = 0; s < plan.L; ++s) {
+    CdpLevel& lv = kp->lv[s];
+    lv.tgt = s == 0 ? a->target : scratch + plan.off_tgt[s];
+    lv.src0 = s == 0 ? a->source0 : scratch + plan.off_src0[s];
+    lv.src1 = s == 0 ? a->source1 : scratch + plan.off_src1[s];
+    lv.depth = s == 0 ? a->depth : scratch + plan.off_depth[s];
+    lv.noise = a->noise[s];
+    lv.gdepth = G ? saved + plan.off_gdepth[s] : nullptr;
+    lv.argmin = a->argmin[s];
+    lv.W = plan.Ws[s]; lv.H = plan.Hs[s];
+    lv.tiles_x = plan.tiles_x[s]; lv.tiles_y = plan.tiles_y[s];
+    lv.block_begin = plan.block_begin[s];
+    // mean over B*H_s*W_s, / 2^s, / num_levels (algos/depth.py:325-326)
+    lv.weight = (float)(1.0 / ((double)plan.B * plan.Hs[s] * plan.Ws[s] * (double)(1 << s) * plan.L));
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j < 4; ++j) kp->K[s][i][j] = a->intrinsics_host[((size_t)s * plan.B + b0 + i) * 4 + j];
+  }
+  kp->pose0 = a->pose0; kp->pose1 = a->pose1;
+  kp->partials = scratch + plan.off_partials;
+  kp->seed = a->noise_seed;
+  kp->num_levels = plan.L; kp->batch_begin = b0; kp->blocks_per_image = plan.blocks_per_image;
+  kp->alpha = a->alpha;
+}
+
+static inline void cdp_fill_finalize_params(const CdpPlan& plan, const cdp_photo_args* a, CdpFinalizeParams* fp) {
+  float* scratch = static_cast<float*>(a->scratch);
+  float* saved = static_cast<float*>(a->saved);
+  fp->partials = scratch + plan.off_partials;
+  fp->loss = a->loss;
+  fp->pose_unit = a->with_grad ? saved + plan.off_pose_unit : nullptr;
+  fp->B = plan.B; fp->blocks_per_image = plan.blocks_per_image;
+}
+
+static inline void cdp_fill_depth_grad_params(const CdpPlan& plan, const void* saved_, const void* resize_tables,
+                                              const float* grad_loss, float* grad_depth, float* grad_pose0,
+                                              float* grad_pose1, CdpDepthGradParams* p) {
+  memset(p, 0, sizeof(*p));
+  const float* saved = static_cast<const float*>(saved_);
+  const CdpResizeInv* tab = static_cast<const CdpResizeInv*>(resize_tables);
+  for (int s = 0; s < plan.L; ++s) {
+    p->gdepth[s] = saved + plan.off_gdepth[s];
+    p->Ws[s] = plan.Ws[s]; p->Hs[s] = plan.Hs[s];
+    if (s > 0) { p->inv_x[s] = tab + plan.tab_inv_x[s]; p->inv_y[s] = tab + plan.tab_inv_y[s]; }
+  }
+  p->grad_loss = grad_loss;
+  p->pose_unit = saved + plan.off_pose_unit;
+  p->grad_depth = grad_depth;
+  p->grad_pose[0] = grad_pose0; p->grad_pose[1] = grad_pose1;
+  p->B = plan.B; p->H = plan.H; p->W = plan.W; p->L = plan.L;
+}
+
+static inline bool cdp_build_resize_tables(const CdpPlan& plan, void* host_out, int* bad_level) {
+  char* base = static_cast<char*>(host_out);
+  for (int s = 1; s < plan.L; ++s) {
+    bool ok = cdp_resize_axis(plan.W, plan.Ws[s], reinterpret_cast<CdpResizeTap*>(base) + plan.tab_fwd_x[s],
+                              reinterpret_cast<CdpResizeInv*>(base) + plan.tab_inv_x[s]);
+    ok = cdp_resize_axis(plan.H, plan.Hs[s], reinterpret_cast<CdpResizeTap*>(base) + plan.tab_fwd_y[s],
+                         reinterpret_cast<CdpResizeInv*>(base) + plan.tab_inv_y[s]) && ok;
+    if (!ok) { *bad_level = s; return false; }
+  }
+  return true;
+}
+
+struct CdpSmoothLayout { size_t g, part_sum, part_main, scal, total; };
+static inline CdpSmoothLayout cdp_smooth_layout(int32_t B, int32_t H, int32_t W) {
+  CdpSmoothLayout l;
+  size_t o = 0;
+  l.g = o; o += cdp_align_floats((size_t)B * H * W);
+  l.part_sum = o; o += cdp_align_floats((size_t)B * CDP_SMOOTH_BLOCKS);
+  l.part_main = o; o += cdp_align_floats((size_t)B * CDP_SMOOTH_BLOCKS * 4);
+  l.scal = o; o += cdp_align_floats((size_t)B * 2);
+  l.total = o;
+  return l;
+}
+
+static inline void cdp_fill_smooth_params(const float* image, const float* disp, int B, int H, int W, int with_grad,
+                                          float* loss, float* saved, CdpSmoothParams* p) {
+  const CdpSmoothLayout l = cdp_smooth_layout(B, H, W);
+  p->image = image; p->disp = disp; p->g = saved + l.g; p->part_sum = saved + l.part_sum;
+  p->part_main = saved + l.part_main; p->scal = saved + l.scal; p->loss = loss;
+  p->B = B; p->H = H; p->W = W; p->with_grad = with_grad;
+}
+
+static inline void cdp_fill_warp_params(CdpWarpParams* p, const float* src, int C, const float* depth,
+                                        const float* pose, const float* motion, const float* K, int b0, int nb,
+                                        int H, int W) {
+  memset(p, 0, sizeof(*p));
+  p->src = src; p->depth = depth; p->pose = pose; p->motion = motion;
+  p->batch_begin = b0; p->C = C; p->H = H; p->W = W;
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j < 4; ++j) p->K[i][j] = K[(size_t)(b0 + i) * 4 + j];
+}

@@ -1,0 +1,131 @@
+"""Drop-in loss classes of the self-supervised depth path, backed by the fused CUDA kernels.
+
+Names, constructor arguments and call signatures follow /root/reference/algos/depth.py:58-326
+(``EdgeAwareSmoothnessLoss``, ``SSIMLoss``, ``ReconstructionLoss``) so that
+``codeps.model_setup.gen_models`` (/root/reference/codeps/model_setup.py:63-85) and ``DepthAlgo``
+(/root/reference/algos/depth.py:474-481) use them unchanged.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import ops
+from .camera import CameraModel
+from .warper import ImageWarper
+
+
+class EdgeAwareSmoothnessLoss:
+    """Edge-aware smoothness of the mean-normalised disparity
+    (/root/reference/algos/depth.py:58-107): two reduction kernels forward, one kernel backward."""
+
+    def __init__(self):
+        pass
+
+    def __call__(self, target_image: Tensor, disparity_map: Tensor) -> Tensor:
+        return ops.smoothness_loss(target_image, disparity_map)
+
+
+class SSIMLoss:
+    """3x3 SSIM loss map, clamp((1 - SSIM) / 2, 0, 1) (/root/reference/algos/depth.py:110-155)."""
+
+    def __init__(self, window_size: int = 3):
+        if window_size != 3:
+            raise NotImplementedError("only the 3x3 window the reference uses is implemented")
+        self.window_size = window_size
+        self.c1 = .01**2
+        self.c2 = .03**2
+
+    def __call__(self, src_img: Tensor, target_img: Tensor) -> Tensor:
+        return ops.ssim_loss_map(src_img, target_img)
+
+
+class ReconstructionLoss:
+    """Multi-scale photometric reprojection loss with min-reprojection and identity auto-mask
+    (/root/reference/algos/depth.py:176-326).
+
+    One pyramid kernel, one fused tile kernel covering every level (warp of both source frames,
+    SSIM + L1 for the two reprojections and the two identity candidates, tie-break noise, min /
+    argmin, and -- when a gradient is required -- the complete backward to per-level depth and to
+    both poses), and one fixed-order reduction kernel.  ``loss.backward()`` then costs a single
+    kernel that assembles dL/d depth from the per-level gradients.
+
+    Additive surface (not in the reference, which discards the argmin at depth.py:323):
+    ``last_argmin`` -- per level a uint8 [B,H_s,W_s] map, 0/1 = reprojection from t-1/t+1 won,
+    2/3 = an identity candidate won, i.e. the pixel is auto-masked.
+
+    ``noise``: "torch" (default) draws ``torch.randn(B,2,H_s,W_s)`` per level exactly like the
+    reference (depth.py:317), so a seeded run consumes the same random stream; "fused" uses the
+    kernel's counter-based generator (no extra launches or traffic; different random numbers).
+    """
+
+    def __init__(self, ref_img_width, ref_img_height, ssim: SSIMLoss, num_scales: int, device: torch.device,
+                 alpha: float = .85, noise: str = "torch", seed: int = 0):
+        if noise not in ("torch", "fused"):
+            raise ValueError("noise must be 'torch' or 'fused'")
+        self.ssim = ssim
+        self.device = device
+        self.num_scales = num_scales
+        self.alpha = alpha
+        self.noise = noise
+        self.seed = seed
+        self._calls = 0
+        self.image_warpers = {}
+        self.scaled_width = {}
+        self.scaled_height = {}
+        for i in range(self.num_scales):
+            self.scaled_width[i] = ref_img_width // 2**i
+            self.scaled_height[i] = ref_img_height // 2**i
+            self.image_warpers[i] = ImageWarper(self.scaled_width[i], self.scaled_height[i], device)
+        self.last_argmin: List[Tensor] = []
+        self._k_cache = {}
+
+    def _level_intrinsics(self, camera_models: List[CameraModel]) -> np.ndarray:
+        """[num_scales, B, 4]: CameraModel.get_scaled_model_image_size per level, as at
+        depth.py:273-276 (cached per distinct camera)."""
+        out = np.empty((self.num_scales, len(camera_models), 4), dtype=np.float32)
+        for b, cam in enumerate(camera_models):
+            key = (cam.image_size["width"], cam.image_size["height"]) + tuple(cam.intrinsics.values())
+            rows = self._k_cache.get(key)
+            if rows is None:
+                rows = np.empty((self.num_scales, 4), dtype=np.float32)
+                for s in range(self.num_scales):
+                    scaled = cam.get_scaled_model_image_size(self.scaled_width[s], self.scaled_height[s])
+                    rows[s] = [np.float32(v) for v in scaled.intrinsics.values()]
+                if len(self._k_cache) < 4096:
+                    self._k_cache[key] = rows
+            out[:, b] = rows
+        return out
+
+    def __call__(self, camera_models: List[CameraModel], images: Tuple[Tensor, Tensor, Tensor],
+                 depth_map: Tensor, poses: Tuple[Tensor, Tensor],
+                 object_motion_maps: Optional[Tuple[Tensor, Tensor]] = None,
+                 semantic_mask: Optional[Tuple[Tensor, Tensor, Tensor]] = None) -> Tensor:
+        assert len(camera_models) == images[0].shape[0], "Batch size of camera model does not match"
+        if semantic_mask is not None:
+            raise NotImplementedError("the semantic_mask branch (depth.py:284-292) is not taken by any "
+                                      "caller in the reference and is not implemented")
+        if object_motion_maps is not None:
+            raise NotImplementedError("object_motion_maps (make_sflow) is not part of the fused loss yet; "
+                                      "every shipped config sets make_sflow: False")
+        h, w = images[0].shape[2], images[0].shape[3]
+        if (w, h) != (self.scaled_width[0], self.scaled_height[0]):
+            raise ValueError(f"images are {w}x{h} but this loss was built for "
+                             f"{self.scaled_width[0]}x{self.scaled_height[0]}")
+        b = images[0].shape[0]
+        noise = None
+        if self.noise == "torch":
+            noise = [torch.randn((b, 2, self.scaled_height[s], self.scaled_width[s]), device=depth_map.device)
+                     for s in range(self.num_scales)]
+        self._calls += 1
+        loss, self.last_argmin = ops.photometric_loss(
+            self._level_intrinsics(camera_models), images, depth_map, poses, noise, self.num_scales,
+            self.alpha, seed=self.seed + self._calls)
+        return loss
+
+    def auto_mask(self, level: int = 0) -> Tensor:
+        """Boolean [B,H_s,W_s]: True where the last call auto-masked the pixel (identity won)."""
+        return self.last_argmin[level] >= 2

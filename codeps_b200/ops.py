@@ -1,0 +1,358 @@
+"""torch.autograd glue over the C ABI of libcodeps_photo.so.
+
+Only plumbing lives here: argument checks, buffer allocation through torch's caching allocator,
+raw pointers + the current CUDA stream handed to the library, and explicit forward/backward
+``autograd.Function``s.  There is deliberately no CPU or eager-PyTorch implementation: tensors
+that are not fp32 CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import PhotoArgs, check
+
+_LAUNCHES = {"count": 0}  # kernels launched through this module (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _LAUNCHES["count"]
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str, shape: Optional[Sequence[Optional[int]]] = None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}; codeps_b200 runs on CUDA only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype} (the reference path is fp32 only)")
+    if shape is not None:
+        if t.dim() != len(shape) or any(s is not None and s != d for s, d in zip(shape, t.shape)):
+            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    return t.contiguous()
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(None)
+
+
+def _bytes(n: int, device) -> torch.Tensor:
+    return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
+
+
+_device_checked = set()
+
+
+def _lib_for(device):
+    lib = _native.load()
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _device_checked:
+        with torch.cuda.device(idx):
+            check(lib.cdp_device_check(), "cdp_device_check")
+        _device_checked.add(idx)
+    return lib
+
+
+_table_cache = {}
+
+
+def resize_tables(height: int, width: int, num_levels: int, device) -> torch.Tensor:
+    """Device copy of the bilinear-resize tap tables for this pyramid (cached per device)."""
+    key = (height, width, num_levels, str(torch.device(device)))
+    tab = _table_cache.get(key)
+    if tab is None:
+        lib = _native.load()
+        n = lib.cdp_resize_tables_bytes(height, width, num_levels)
+        if n == 0:
+            raise ValueError(f"unsupported pyramid: {width}x{height} with {num_levels} levels "
+                             f"(at most {_native.MAX_LEVELS} levels, every level at least 2x2)")
+        host = torch.empty(n, dtype=torch.uint8)
+        check(lib.cdp_resize_tables_build(height, width, num_levels, _ptr(host), n),
+              "cdp_resize_tables_build")
+        tab = host.to(device)
+        _table_cache[key] = tab
+    return tab
+
+
+class PhotoState:
+    """Side outputs of one reconstruction-loss call."""
+    __slots__ = ("argmin",)
+
+    def __init__(self):
+        self.argmin: List[torch.Tensor] = []
+
+
+class _PhotometricLoss(torch.autograd.Function):
+    """cdp_photo_fwd / cdp_photo_bwd."""
+
+    @staticmethod
+    def forward(ctx, depth, pose0, pose1, target, source0, source1, intrinsics, noise, seed,
+                num_levels, alpha, state):
+        b, _, h, w = target.shape
+        device = target.device
+        lib = _lib_for(device)
+        need_grad = any(ctx.needs_input_grad[:3])
+        tables = resize_tables(h, w, num_levels, device)
+        scratch = _bytes(lib.cdp_photo_scratch_bytes(b, h, w, num_levels), device)
+        saved = _bytes(lib.cdp_photo_saved_bytes(b, h, w, num_levels), device) if need_grad else None
+        loss = torch.empty(1, dtype=torch.float32, device=device)
+        argmin = [torch.empty(b, h >> s, w >> s, dtype=torch.uint8, device=device)
+                  for s in range(num_levels)]
+        a = PhotoArgs()
+        a.batch, a.height, a.width, a.num_levels = b, h, w, num_levels
+        a.alpha, a.with_grad = float(alpha), int(need_grad)
+        a.intrinsics_host = intrinsics.ctypes.data
+        a.target, a.source0, a.source1 = target.data_ptr(), source0.data_ptr(), source1.data_ptr()
+        a.depth, a.pose0, a.pose1 = depth.data_ptr(), pose0.data_ptr(), pose1.data_ptr()
+        for s in range(num_levels):
+            a.noise[s] = noise[s].data_ptr() if noise is not None else None
+            a.argmin[s] = argmin[s].data_ptr()
+        a.noise_seed = int(seed)
+        a.resize_tables = tables.data_ptr()
+        a.loss = loss.data_ptr()
+        a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
+        if need_grad:
+            a.saved, a.saved_bytes = saved.data_ptr(), saved.numel()
+        with torch.cuda.device(device):
+            check(lib.cdp_photo_fwd(ctypes.byref(a), _stream(device)), "cdp_photo_fwd")
+        _LAUNCHES["count"] += lib.cdp_photo_fwd_launches(b, num_levels)
+        state.argmin = argmin
+        ctx.shape = (b, h, w, num_levels)
+        ctx.saved_buf = saved
+        ctx.tables = tables
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        b, h, w, num_levels = ctx.shape
+        saved = ctx.saved_buf
+        if saved is None:
+            raise RuntimeError("photometric loss: backward called but no input required grad")
+        device = saved.device
+        lib = _lib_for(device)
+        go = _require_cuda_f32(grad_loss.reshape(1), "grad_loss")
+        grad_depth = torch.empty(b, 1, h, w, dtype=torch.float32, device=device)
+        grad_pose0 = torch.empty(b, 4, 4, dtype=torch.float32, device=device)
+        grad_pose1 = torch.empty(b, 4, 4, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            check(lib.cdp_photo_bwd(b, h, w, num_levels, _ptr(saved), saved.numel(), _ptr(ctx.tables),
+                                    _ptr(go), _ptr(grad_depth), _ptr(grad_pose0), _ptr(grad_pose1),
+                                    _stream(device)), "cdp_photo_bwd")
+        _LAUNCHES["count"] += lib.cdp_photo_bwd_launches(b, num_levels)
+        return (grad_depth, grad_pose0, grad_pose1) + (None,) * 9
+
+
+def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], depth: torch.Tensor,
+                     poses: Sequence[torch.Tensor], noise: Optional[Sequence[torch.Tensor]],
+                     num_levels: int, alpha: float = 0.85, seed: int = 0
+                     ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    """Multi-scale min-reprojection loss with identity auto-mask.
+
+    intrinsics: float32 array [num_levels, B, 4] (fx, fy, cx, cy per level and sample).
+    noise: per level [B,2,H_s,W_s] standard-normal tie-break draws, or None to use the kernel's
+    counter-based generator with ``seed``.  Returns (loss, per-level argmin maps)."""
+    target = _require_cuda_f32(images[0], "images[0]", (None, 3, None, None))
+    b, _, h, w = target.shape
+    source0 = _require_cuda_f32(images[1], "images[1]", (b, 3, h, w))
+    source1 = _require_cuda_f32(images[2], "images[2]", (b, 3, h, w))
+    depth = _require_cuda_f32(depth, "depth_map", (b, 1, h, w))
+    pose0 = _require_cuda_f32(poses[0], "poses[0]", (b, 4, 4))
+    pose1 = _require_cuda_f32(poses[1], "poses[1]", (b, 4, 4))
+    for name, t in (("images[1]", source0), ("images[2]", source1), ("depth_map", depth),
+                    ("poses[0]", pose0), ("poses[1]", pose1)):
+        if t.device != target.device:
+            raise RuntimeError(f"{name} is on {t.device}, images[0] on {target.device}")
+    intrinsics = np.ascontiguousarray(intrinsics, dtype=np.float32)
+    if intrinsics.shape != (num_levels, b, 4):
+        raise ValueError(f"intrinsics has shape {intrinsics.shape}, expected {(num_levels, b, 4)}")
+    if not 1 <= num_levels <= _native.MAX_LEVELS:
+        raise ValueError(f"num_levels must be in [1, {_native.MAX_LEVELS}], got {num_levels}")
+    if noise is not None:
+        if len(noise) != num_levels:
+            raise ValueError(f"noise has {len(noise)} levels, expected {num_levels}")
+        noise = [_require_cuda_f32(n, f"noise[{s}]", (b, 2, h >> s, w >> s))
+                 for s, n in enumerate(noise)]
+    state = PhotoState()
+    loss = _PhotometricLoss.apply(depth, pose0, pose1, target, source0, source1, intrinsics, noise,
+                                  seed, num_levels, alpha, state)
+    return loss, state.argmin
+
+
+class _Smoothness(torch.autograd.Function):
+    """cdp_smooth_fwd / cdp_smooth_bwd."""
+
+    @staticmethod
+    def forward(ctx, disp, image):
+        b, _, h, w = disp.shape
+        device = disp.device
+        lib = _lib_for(device)
+        need_grad = ctx.needs_input_grad[0]
+        saved = _bytes(lib.cdp_smooth_saved_bytes(b, h, w), device)
+        loss = torch.empty(1, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            check(lib.cdp_smooth_fwd(_ptr(image), _ptr(disp), b, h, w, int(need_grad), _ptr(loss),
+                                     _ptr(saved), saved.numel(), _stream(device)), "cdp_smooth_fwd")
+        _LAUNCHES["count"] += 3
+        ctx.saved_buf = saved if need_grad else None
+        ctx.shape = (b, h, w)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        b, h, w = ctx.shape
+        saved = ctx.saved_buf
+        device = saved.device
+        lib = _lib_for(device)
+        go = _require_cuda_f32(grad_loss.reshape(1), "grad_loss")
+        grad_disp = torch.empty(b, 1, h, w, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            check(lib.cdp_smooth_bwd(_ptr(saved), saved.numel(), _ptr(go), b, h, w, _ptr(grad_disp),
+                                     _stream(device)), "cdp_smooth_bwd")
+        _LAUNCHES["count"] += 1
+        return grad_disp, None
+
+
+def smoothness_loss(target_image: torch.Tensor, disparity: torch.Tensor) -> torch.Tensor:
+    image = _require_cuda_f32(target_image, "target_image", (None, 3, None, None))
+    b, _, h, w = image.shape
+    disp = _require_cuda_f32(disparity, "disparity_map", (b, 1, h, w))
+    if h < 2 or w < 2:
+        raise ValueError("edge-aware smoothness needs at least 2x2 pixels")
+    return _Smoothness.apply(disp, image)
+
+
+class _WarpImage(torch.autograd.Function):
+    """cdp_warp_image_fwd / cdp_warp_image_bwd."""
+
+    @staticmethod
+    def forward(ctx, src, depth, pose, motion, intrinsics, mode):
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("ImageWarper: gradients w.r.t. the source image are not supported "
+                               "(the loss never needs them); detach the source image")
+        b, c, h, w = src.shape
+        device = src.device
+        lib = _lib_for(device)
+        out = torch.empty_like(src)
+        with torch.cuda.device(device):
+            check(lib.cdp_warp_image_fwd(_ptr(src), c, _ptr(depth), _ptr(pose), _ptr(motion),
+                                         ctypes.c_void_p(intrinsics.ctypes.data), b, h, w, mode, _ptr(out),
+                                         _stream(device)), "cdp_warp_image_fwd")
+        _LAUNCHES["count"] += (b + _native.MAX_BATCH_PER_LAUNCH - 1) // _native.MAX_BATCH_PER_LAUNCH
+        ctx.save_for_backward(src, depth, pose, motion if motion is not None else torch.empty(0))
+        ctx.intrinsics = intrinsics
+        ctx.mode = mode
+        ctx.has_motion = motion is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        src, depth, pose, motion = ctx.saved_tensors
+        motion = motion if ctx.has_motion else None
+        if ctx.mode != 0:
+            raise RuntimeError("ImageWarper: nearest-neighbour warping has no coordinate gradient")
+        b, c, h, w = src.shape
+        device = src.device
+        lib = _lib_for(device)
+        grad_out = _require_cuda_f32(grad_out, "grad_output", (b, c, h, w))
+        grad_depth = torch.empty_like(depth)
+        grad_pose = torch.empty_like(pose)
+        grad_motion = torch.empty_like(motion) if motion is not None else None
+        scratch = _bytes(lib.cdp_warp_bwd_scratch_bytes(b, h, w), device)
+        with torch.cuda.device(device):
+            check(lib.cdp_warp_image_bwd(_ptr(grad_out), _ptr(src), c, _ptr(depth), _ptr(pose), _ptr(motion),
+                                         ctypes.c_void_p(ctx.intrinsics.ctypes.data), b, h, w,
+                                         _ptr(grad_depth), _ptr(grad_pose), _ptr(grad_motion), _ptr(scratch),
+                                         scratch.numel(), _stream(device)), "cdp_warp_image_bwd")
+        _LAUNCHES["count"] += 1 + (b + _native.MAX_BATCH_PER_LAUNCH - 1) // _native.MAX_BATCH_PER_LAUNCH
+        return None, grad_depth, grad_pose, grad_motion, None, None
+
+
+def _check_warp_inputs(depth, pose, motion, intrinsics):
+    depth = _require_cuda_f32(depth, "batch_depth_map", (None, 1, None, None))
+    b, _, h, w = depth.shape
+    pose = _require_cuda_f32(pose, "T", (b, 4, 4))
+    if motion is not None:
+        motion = _require_cuda_f32(motion, "object_motion_map", (b, 3, h, w))
+    intrinsics = np.ascontiguousarray(intrinsics, dtype=np.float32)
+    if intrinsics.shape != (b, 4):
+        raise ValueError(f"intrinsics has shape {intrinsics.shape}, expected {(b, 4)}")
+    if h < 2 or w < 2:
+        raise ValueError("warping needs at least 2x2 pixels")
+    return depth, pose, motion, intrinsics
+
+
+def warp_image(src, depth, pose, intrinsics, mode: str = "bilinear", motion=None) -> torch.Tensor:
+    if mode not in ("bilinear", "nearest"):
+        raise ValueError(f"interp_mode must be 'bilinear' or 'nearest', got {mode!r}")
+    depth, pose, motion, intrinsics = _check_warp_inputs(depth, pose, motion, intrinsics)
+    b, _, h, w = depth.shape
+    src = _require_cuda_f32(src, "batch_src_img", (b, None, h, w))
+    return _WarpImage.apply(src, depth, pose, motion, intrinsics, 0 if mode == "bilinear" else 1)
+
+
+def warp_grid(depth, pose, intrinsics, motion=None) -> torch.Tensor:
+    """Normalised sampling grid [B,H,W,2] (forward only)."""
+    depth, pose, motion, intrinsics = _check_warp_inputs(depth, pose, motion, intrinsics)
+    if any(t is not None and t.requires_grad for t in (depth, pose, motion)) and torch.is_grad_enabled():
+        raise RuntimeError("CoordinateWarper: the stand-alone grid output is forward-only; use "
+                           "ImageWarper / ReconstructionLoss for differentiable warping")
+    b, _, h, w = depth.shape
+    device = depth.device
+    lib = _lib_for(device)
+    grid = torch.empty(b, h, w, 2, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(lib.cdp_warp_grid_fwd(_ptr(depth), _ptr(pose), _ptr(motion),
+                                    ctypes.c_void_p(intrinsics.ctypes.data), b, h, w, _ptr(grid),
+                                    _stream(device)), "cdp_warp_grid_fwd")
+    _LAUNCHES["count"] += (b + _native.MAX_BATCH_PER_LAUNCH - 1) // _native.MAX_BATCH_PER_LAUNCH
+    return grid
+
+
+class _Ssim(torch.autograd.Function):
+    """cdp_ssim_fwd / cdp_ssim_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        b, c, h, w = x.shape
+        device = x.device
+        lib = _lib_for(device)
+        out = torch.empty_like(x)
+        with torch.cuda.device(device):
+            check(lib.cdp_ssim_fwd(_ptr(x), _ptr(y), b * c, h, w, _ptr(out), _stream(device)), "cdp_ssim_fwd")
+        _LAUNCHES["count"] += 1
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, y = ctx.saved_tensors
+        b, c, h, w = x.shape
+        device = x.device
+        lib = _lib_for(device)
+        grad_out = _require_cuda_f32(grad_out, "grad_output", (b, c, h, w))
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        scratch = _bytes(lib.cdp_ssim_bwd_scratch_bytes(b * c, h, w), device)
+        with torch.cuda.device(device):
+            check(lib.cdp_ssim_bwd(_ptr(grad_out), _ptr(x), _ptr(y), b * c, h, w, _ptr(gx), _ptr(gy),
+                                   _ptr(scratch), scratch.numel(), _stream(device)), "cdp_ssim_bwd")
+        _LAUNCHES["count"] += 2
+        return gx, gy
+
+
+def ssim_loss_map(src_img: torch.Tensor, target_img: torch.Tensor) -> torch.Tensor:
+    x = _require_cuda_f32(src_img, "src_img", (None, None, None, None))
+    y = _require_cuda_f32(target_img, "target_img", tuple(x.shape))
+    if x.shape[2] < 2 or x.shape[3] < 2:
+        raise ValueError("SSIM with reflection padding needs at least 2x2 pixels")
+    return _Ssim.apply(x, y)

@@ -1,0 +1,168 @@
+/*
+ * codeps_photo.h -- C ABI of libcodeps_photo.so: the CoDEPS photometric reprojection loss hot
+ * path as hand-written CUDA for sm_100a (B200).
+ *
+ * The reference (robot-learning-freiburg/CoDEPS) is pure Python/PyTorch and has no FFI; each
+ * entry point below replaces a Python class on the hot path and cites it (paths relative to the
+ * reference root).  A maintainer binds these with ctypes (INTEGRATION.md shows the stub);
+ * codeps_b200/_native.py is exactly that binding.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch types.  All tensors fp32, NCHW, contiguous, on the
+ *     current CUDA device, unless a parameter says HOST.
+ *   - The caller owns every buffer, including outputs, scratch and saved-for-backward state,
+ *     sized with the *_bytes() helpers.  The library never allocates or frees device memory and
+ *     keeps no pointer after a call returns.
+ *   - Work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation.
+ *   - Every function returns CDP_OK (0) or a negative cdp_status; cdp_last_error() returns a
+ *     thread-local message for the most recent failure on the calling thread.
+ *   - Reductions are fixed-order (no atomics): results are bit-identical run to run.
+ *   - There is no CPU implementation behind this ABI.
+ */
+#ifndef CODEPS_PHOTO_H_
+#define CODEPS_PHOTO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDP_ABI_VERSION 1
+#define CDP_MAX_LEVELS 6           /* pyramid levels per call (reference uses 5) */
+#define CDP_MAX_BATCH_PER_LAUNCH 32 /* intrinsics travel in kernel-parameter (constant) space */
+
+typedef enum cdp_status {
+  CDP_OK = 0,
+  CDP_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, ...) */
+  CDP_ERR_UNSUPPORTED = -2, /* valid request the library does not implement */
+  CDP_ERR_CUDA = -3,        /* a CUDA runtime call or launch failed */
+  CDP_ERR_WORKSPACE = -4    /* caller-provided buffer too small */
+} cdp_status;
+
+typedef void* cdp_stream_t; /* cudaStream_t */
+
+int cdp_version(void);
+const char* cdp_last_error(void);
+/* CDP_OK when the current device can run the sm_100a kernels. */
+int cdp_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optional per-kernel timing for benchmarks: while enabled, every kernel of the fused loss is
+ * bracketed by CUDA events on its launch stream.  cdp_profile_read synchronises on the recorded
+ * events and returns the summed duration and launch count of one kernel since the last
+ * cdp_profile_enable().  Do not enable during CUDA-graph capture.
+ * ------------------------------------------------------------------------------------------- */
+enum cdp_kernel_id {
+  CDP_KERNEL_PYRAMID = 0, CDP_KERNEL_PHOTO = 1, CDP_KERNEL_FINALIZE = 2, CDP_KERNEL_DEPTH_GRAD = 3,
+  CDP_KERNEL_SMOOTH_SUM = 4, CDP_KERNEL_SMOOTH_MAIN = 5, CDP_KERNEL_SMOOTH_FINALIZE = 6,
+  CDP_KERNEL_SMOOTH_BWD = 7, CDP_KERNEL_COUNT = 8
+};
+int cdp_profile_enable(int32_t enable);
+int cdp_profile_read(int32_t kernel_id, double* total_ms, int32_t* launches);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bilinear resize tables (Interpolate / F.interpolate(mode="bilinear", align_corners=False),
+ * algos/depth.py:158-173, always from full resolution: algos/depth.py:280-281,295,313).
+ * Built once per (H, W, num_levels) on the HOST, uploaded by the caller, shared by forward and
+ * backward so that both use identical taps and weights.
+ * ------------------------------------------------------------------------------------------- */
+size_t cdp_resize_tables_bytes(int32_t height, int32_t width, int32_t num_levels);
+int cdp_resize_tables_build(int32_t height, int32_t width, int32_t num_levels, void* host_out,
+                            size_t host_bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * ReconstructionLoss.__call__ (algos/depth.py:239-326) on top of ImageWarper.forward
+ * (misc/image_warper.py:153-184), CameraModel (misc/camera_model.py:36-71), SSIMLoss
+ * (algos/depth.py:128-155) and _compute_loss (algos/depth.py:221-237): multi-scale
+ * min-reprojection with identity auto-mask.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cdp_photo_args {
+  int32_t batch, height, width; /* full resolution */
+  int32_t num_levels;           /* level s has size (height >> s, width >> s) */
+  float alpha;                  /* SSIM weight, reference default 0.85 */
+  int32_t with_grad;            /* also produce the state cdp_photo_bwd needs */
+  /* HOST [num_levels][batch][4] = fx,fy,cx,cy already rescaled to each level
+   * (CameraModel.get_scaled_model_image_size, misc/camera_model.py:36-41). */
+  const float* intrinsics_host;
+  const float* target;  /* [B,3,H,W] frame t   */
+  const float* source0; /* [B,3,H,W] frame t-1 */
+  const float* source1; /* [B,3,H,W] frame t+1 */
+  const float* depth;   /* [B,1,H,W] */
+  const float* pose0;   /* [B,4,4] t -> t-1 */
+  const float* pose1;   /* [B,4,4] t -> t+1 */
+  /* Tie-break noise (algos/depth.py:316-318).  noise[s] = [B,2,H_s,W_s] standard normal draws
+   * (the library multiplies by 1e-5), or all NULL to use the built-in counter-based generator
+   * seeded with noise_seed. */
+  const float* noise[CDP_MAX_LEVELS];
+  uint64_t noise_seed;
+  const void* resize_tables; /* device copy of cdp_resize_tables_build output */
+  /* outputs */
+  float* loss;                      /* [1] */
+  uint8_t* argmin[CDP_MAX_LEVELS];  /* [B,H_s,W_s]: 0/1 reprojection from t-1/t+1, 2/3 identity
+                                       (pixel auto-masked); may be NULL per level */
+  void* scratch; size_t scratch_bytes; /* pyramid levels; dead after the call */
+  void* saved;   size_t saved_bytes;   /* with_grad: state for cdp_photo_bwd */
+} cdp_photo_args;
+
+size_t cdp_photo_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels);
+size_t cdp_photo_saved_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels);
+int cdp_photo_fwd(const cdp_photo_args* args, cdp_stream_t stream);
+/* Backward of the above: grad_loss is a DEVICE scalar (dL/d loss).  Writes dL/d depth [B,1,H,W]
+ * and dL/dT for both poses [B,4,4] each (autograd of torch.bmm, misc/image_warper.py:129). */
+int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32_t num_levels,
+                  const void* saved, size_t saved_bytes, const void* resize_tables,
+                  const float* grad_loss, float* grad_depth, float* grad_pose0, float* grad_pose1,
+                  cdp_stream_t stream);
+/* Number of kernels one cdp_photo_fwd / cdp_photo_bwd call launches (for launch accounting). */
+int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels);
+int cdp_photo_bwd_launches(int32_t batch, int32_t num_levels);
+
+/* ---------------------------------------------------------------------------------------------
+ * EdgeAwareSmoothnessLoss.__call__ (algos/depth.py:58-107).
+ * ------------------------------------------------------------------------------------------- */
+size_t cdp_smooth_saved_bytes(int32_t batch, int32_t height, int32_t width);
+int cdp_smooth_fwd(const float* image /*[B,3,H,W]*/, const float* disp /*[B,1,H,W]*/,
+                   int32_t batch, int32_t height, int32_t width, int32_t with_grad,
+                   float* loss /*[1]*/, void* saved, size_t saved_bytes, cdp_stream_t stream);
+int cdp_smooth_bwd(const void* saved, size_t saved_bytes, const float* grad_loss /*device [1]*/,
+                   int32_t batch, int32_t height, int32_t width, float* grad_disp /*[B,1,H,W]*/,
+                   cdp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stand-alone operators (same classes used outside the fused loss).
+ * intrinsics_host: HOST [batch][4] for this image size.
+ * ------------------------------------------------------------------------------------------- */
+/* CoordinateWarper.forward (misc/image_warper.py:100-144): normalised grid [B,H,W,2]. */
+int cdp_warp_grid_fwd(const float* depth, const float* pose, const float* motion /*nullable*/,
+                      const float* intrinsics_host, int32_t batch, int32_t height, int32_t width,
+                      float* grid, cdp_stream_t stream);
+/* ImageWarper.forward (misc/image_warper.py:153-184); mode 0 = bilinear, 1 = nearest. */
+int cdp_warp_image_fwd(const float* src /*[B,C,H,W]*/, int32_t channels, const float* depth,
+                       const float* pose, const float* motion /*nullable [B,3,H,W]*/,
+                       const float* intrinsics_host, int32_t batch, int32_t height, int32_t width,
+                       int32_t mode, float* out /*[B,C,H,W]*/, cdp_stream_t stream);
+/* Backward of the bilinear warp w.r.t. depth, pose (and motion when given).
+ * partials: device scratch of cdp_warp_bwd_scratch_bytes(). */
+size_t cdp_warp_bwd_scratch_bytes(int32_t batch, int32_t height, int32_t width);
+int cdp_warp_image_bwd(const float* grad_out /*[B,C,H,W]*/, const float* src, int32_t channels,
+                       const float* depth, const float* pose, const float* motion,
+                       const float* intrinsics_host, int32_t batch, int32_t height, int32_t width,
+                       float* grad_depth /*[B,1,H,W]*/, float* grad_pose /*[B,4,4]*/,
+                       float* grad_motion /*nullable [B,3,H,W]*/, void* scratch,
+                       size_t scratch_bytes, cdp_stream_t stream);
+/* SSIMLoss.__call__ (algos/depth.py:128-155) on `planes` = B*C images of H x W. */
+int cdp_ssim_fwd(const float* x, const float* y, int32_t planes, int32_t height, int32_t width,
+                 float* out, cdp_stream_t stream);
+/* scratch: 4 * planes*H*W floats. */
+size_t cdp_ssim_bwd_scratch_bytes(int32_t planes, int32_t height, int32_t width);
+int cdp_ssim_bwd(const float* grad_out, const float* x, const float* y, int32_t planes,
+                 int32_t height, int32_t width, float* grad_x /*nullable*/,
+                 float* grad_y /*nullable*/, void* scratch, size_t scratch_bytes,
+                 cdp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CODEPS_PHOTO_H_ */

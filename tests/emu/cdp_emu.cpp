@@ -1,0 +1,203 @@
+// cdp_emu.cpp -- CPU emulator of the CUDA kernels.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the same kernel bodies (codeps_b200/csrc/cdp_kernels.h, cdp_math.h) and the same
+// launch planning (cdp_plan.h) with g++ and runs every (block, thread) sequentially, one phase
+// at a time where the CUDA kernel has a __syncthreads().  It lets the tile / halo / reflection
+// adjoint / pyramid-table logic be checked against the oracle in the build container, which has
+// no GPU.  It is built and loaded only by tests/; the codeps_b200 package never touches it, and
+// it is never timed.  Entry points mirror include/codeps_photo.h with an emu_ prefix and HOST
+// pointers everywhere.
+#include <vector>
+
+#include "cdp_plan.h"
+
+#define EMU_API extern "C" __attribute__((visibility("default")))
+
+EMU_API size_t emu_resize_tables_bytes(int32_t h, int32_t w, int32_t l) {
+  CdpPlan plan;
+  if (!cdp_make_plan(1, h, w, l, &plan)) return 0;
+  return (plan.tab_records > 0 ? plan.tab_records : 1) * sizeof(CdpResizeTap);
+}
+EMU_API int emu_resize_tables_build(int32_t h, int32_t w, int32_t l, void* out) {
+  CdpPlan plan;
+  if (!cdp_make_plan(1, h, w, l, &plan)) return CDP_ERR_INVALID;
+  int bad = 0;
+  return cdp_build_resize_tables(plan, out, &bad) ? CDP_OK : CDP_ERR_UNSUPPORTED;
+}
+EMU_API size_t emu_photo_scratch_bytes(int32_t b, int32_t h, int32_t w, int32_t l) {
+  CdpPlan plan;
+  return cdp_make_plan(b, h, w, l, &plan) ? plan.scratch_floats * sizeof(float) : 0;
+}
+EMU_API size_t emu_photo_saved_bytes(int32_t b, int32_t h, int32_t w, int32_t l) {
+  CdpPlan plan;
+  return cdp_make_plan(b, h, w, l, &plan) ? plan.saved_floats * sizeof(float) : 0;
+}
+
+template <bool G>
+static void emu_photo_block(const CdpPhotoParams& kp, int bx, int by) {
+  typedef CdpTileGeom<G> Geo;
+  const int nt = CDP_PHOTO_THREADS;
+  std::vector<float> sm(Geo::SMEM_BYTES / sizeof(float) + 4, 0.f);
+  const CdpTileCtx c = cdp_tile_ctx(kp, bx, by);
+  for (int t = 0; t < nt; ++t) cdp_photo_phase_a<G>(kp, c, t, nt, sm.data());
+  for (int t = 0; t < nt; ++t) cdp_photo_phase_b1<G>(kp, c, t, nt, sm.data());
+  std::vector<float> v((size_t)nt * 33, 0.f);
+  for (int t = 0; t < nt; ++t) cdp_photo_phase_b2<G>(kp, c, t, nt, sm.data(), v[(size_t)t * 33]);
+  if (G)
+    for (int t = 0; t < nt; ++t) cdp_photo_phase_c(kp, c, t, nt, sm.data(), &v[(size_t)t * 33 + 1]);
+  float* rec = kp.partials + ((size_t)c.b * kp.blocks_per_image + bx) * CDP_PARTIAL_STRIDE;
+  for (int j = 0; j < 33; ++j) {
+    float acc = 0.f;
+    for (int t = 0; t < nt; ++t) acc += (j == 0 ? v[(size_t)t * 33] * kp.lv[c.lvl].weight : v[(size_t)t * 33 + j]);
+    rec[j] = acc;
+  }
+}
+
+EMU_API int emu_photo_fwd(const cdp_photo_args* a) {
+  CdpPlan plan;
+  if (!cdp_make_plan(a->batch, a->height, a->width, a->num_levels, &plan)) return CDP_ERR_INVALID;
+  if (plan.L > 1) {
+    CdpPyrParams pp;
+    cdp_fill_pyr_params(plan, a, &pp);
+    for (int b = 0; b < plan.B; ++b)
+      for (int i = 0; i < plan.pyr_begin[plan.L]; ++i) cdp_pyramid_fwd_item(pp, b, i);
+  }
+  for (int b0 = 0; b0 < plan.B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+    const int nb = cdp_chunk_size(plan.B, b0);
+    CdpPhotoParams kp;
+    cdp_fill_photo_params(plan, a, b0, nb, &kp);
+    for (int by = 0; by < nb; ++by)
+      for (int bx = 0; bx < plan.blocks_per_image; ++bx) {
+        if (a->with_grad) emu_photo_block<true>(kp, bx, by);
+        else emu_photo_block<false>(kp, bx, by);
+      }
+  }
+  CdpFinalizeParams fp;
+  cdp_fill_finalize_params(plan, a, &fp);
+  std::vector<double> sm(32 * 33);
+  double loss_acc = 0.0;
+  for (int b = 0; b < fp.B; ++b) {
+    for (int t = 0; t < CDP_FINALIZE_THREADS; ++t) cdp_finalize_phase_a(fp, b, t, sm.data());
+    for (int t = 0; t < CDP_FINALIZE_THREADS; ++t) cdp_finalize_phase_b(fp, b, t, sm.data(), &loss_acc);
+  }
+  fp.loss[0] = (float)loss_acc;
+  return CDP_OK;
+}
+
+EMU_API int emu_photo_bwd(int32_t b, int32_t h, int32_t w, int32_t l, const void* saved, const void* tables,
+                          const float* grad_loss, float* grad_depth, float* gp0, float* gp1) {
+  CdpPlan plan;
+  if (!cdp_make_plan(b, h, w, l, &plan)) return CDP_ERR_INVALID;
+  CdpDepthGradParams p;
+  cdp_fill_depth_grad_params(plan, saved, tables, grad_loss, grad_depth, gp0, gp1, &p);
+  for (int i = 0; i < plan.B; ++i)
+    for (int pix = 0; pix < h * w; ++pix) cdp_depth_grad_pixel(p, i, pix);
+  for (int i = 0; i < 2 * plan.B * 16; ++i) cdp_pose_grad_scale(p, i);
+  return CDP_OK;
+}
+
+EMU_API size_t emu_smooth_saved_bytes(int32_t b, int32_t h, int32_t w) {
+  return cdp_smooth_layout(b, h, w).total * sizeof(float);
+}
+
+EMU_API int emu_smooth_fwd(const float* image, const float* disp, int32_t B, int32_t H, int32_t W, int32_t with_grad,
+                           float* loss, void* saved) {
+  CdpSmoothParams p;
+  cdp_fill_smooth_params(image, disp, B, H, W, with_grad, loss, static_cast<float*>(saved), &p);
+  const int nt = CDP_SMOOTH_THREADS;
+  for (int b = 0; b < B; ++b)
+    for (int blk = 0; blk < CDP_SMOOTH_BLOCKS; ++blk) {
+      float acc = 0.f;
+      for (int t = 0; t < nt; ++t) acc += cdp_smooth_sum_thread(p, b, blk, t, nt);
+      p.part_sum[b * CDP_SMOOTH_BLOCKS + blk] = acc;
+    }
+  for (int b = 0; b < B; ++b) {
+    const float mean = cdp_smooth_mean(p, b);
+    for (int blk = 0; blk < CDP_SMOOTH_BLOCKS; ++blk) {
+      float tot[3] = {0.f, 0.f, 0.f};
+      for (int t = 0; t < nt; ++t) {
+        float v[3] = {0.f, 0.f, 0.f};
+        cdp_smooth_main_thread(p, b, blk, t, nt, mean, v);
+        for (int j = 0; j < 3; ++j) tot[j] += v[j];
+      }
+      for (int j = 0; j < 3; ++j) p.part_main[((size_t)b * CDP_SMOOTH_BLOCKS + blk) * 4 + j] = tot[j];
+    }
+  }
+  cdp_smooth_finalize(p);
+  return CDP_OK;
+}
+
+EMU_API int emu_smooth_bwd(const void* saved_, const float* grad_loss, int32_t B, int32_t H, int32_t W,
+                           float* grad_disp) {
+  const CdpSmoothLayout l = cdp_smooth_layout(B, H, W);
+  const float* saved = static_cast<const float*>(saved_);
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < H * W; ++i)
+      cdp_smooth_bwd_pixel(saved + l.g, saved + l.scal, grad_loss, b, (size_t)H * W, i, grad_disp);
+  return CDP_OK;
+}
+
+EMU_API int emu_warp_grid_fwd(const float* depth, const float* pose, const float* motion, const float* K, int32_t B,
+                              int32_t H, int32_t W, float* grid) {
+  for (int b0 = 0; b0 < B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+    const int nb = cdp_chunk_size(B, b0);
+    CdpWarpParams p;
+    cdp_fill_warp_params(&p, nullptr, 0, depth, pose, motion, K, b0, nb, H, W);
+    p.out = grid;
+    for (int i = 0; i < nb; ++i)
+      for (int pix = 0; pix < H * W; ++pix) cdp_warp_grid_pixel(p, i, pix);
+  }
+  return CDP_OK;
+}
+
+EMU_API int emu_warp_image_fwd(const float* src, int32_t C, const float* depth, const float* pose,
+                               const float* motion, const float* K, int32_t B, int32_t H, int32_t W, int32_t mode,
+                               float* out) {
+  for (int b0 = 0; b0 < B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+    const int nb = cdp_chunk_size(B, b0);
+    CdpWarpParams p;
+    cdp_fill_warp_params(&p, src, C, depth, pose, motion, K, b0, nb, H, W);
+    p.out = out; p.mode = mode;
+    for (int i = 0; i < nb; ++i)
+      for (int pix = 0; pix < H * W; ++pix) cdp_warp_image_pixel(p, i, pix);
+  }
+  return CDP_OK;
+}
+
+EMU_API int emu_warp_image_bwd(const float* grad_out, const float* src, int32_t C, const float* depth,
+                               const float* pose, const float* motion, const float* K, int32_t B, int32_t H,
+                               int32_t W, float* grad_depth, float* grad_pose, float* grad_motion) {
+  for (int b0 = 0; b0 < B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+    const int nb = cdp_chunk_size(B, b0);
+    CdpWarpParams p;
+    cdp_fill_warp_params(&p, src, C, depth, pose, motion, K, b0, nb, H, W);
+    p.grad_out = grad_out; p.grad_depth = grad_depth; p.grad_motion = grad_motion;
+    for (int i = 0; i < nb; ++i) {
+      double tot[16] = {0};
+      for (int pix = 0; pix < H * W; ++pix) {
+        float dT[16] = {0};
+        cdp_warp_bwd_pixel(p, i, pix, dT);
+        for (int j = 0; j < 16; ++j) tot[j] += dT[j];
+      }
+      for (int j = 0; j < 16; ++j) grad_pose[(size_t)(b0 + i) * 16 + j] = (float)tot[j];
+    }
+  }
+  return CDP_OK;
+}
+
+EMU_API int emu_ssim_fwd(const float* x, const float* y, int32_t planes, int32_t H, int32_t W, float* out) {
+  for (int pl = 0; pl < planes; ++pl)
+    for (int pix = 0; pix < H * W; ++pix) cdp_ssim_fwd_pixel(x, y, W, H, pl, pix, out);
+  return CDP_OK;
+}
+
+EMU_API int emu_ssim_bwd(const float* go, const float* x, const float* y, int32_t planes, int32_t H, int32_t W,
+                         float* gx, float* gy) {
+  const size_t total = (size_t)planes * H * W;
+  std::vector<float> scratch(4 * total);
+  for (int pl = 0; pl < planes; ++pl)
+    for (int pix = 0; pix < H * W; ++pix) cdp_ssim_bwd_coef_pixel(go, x, y, W, H, pl, pix, scratch.data(), total);
+  for (int pl = 0; pl < planes; ++pl)
+    for (int pix = 0; pix < H * W; ++pix) cdp_ssim_bwd_gather_pixel(x, y, W, H, pl, pix, scratch.data(), total, gx, gy);
+  return CDP_OK;
+}

@@ -1,0 +1,180 @@
+"""ctypes access to the CPU emulator of the CUDA kernels (tests/emu/cdp_emu.cpp).
+
+Test infrastructure: lets the CPU-only test tier run the kernel bodies and launch planning of
+codeps_b200/csrc on host memory.  Never imported by the codeps_b200 package.
+"""
+import ctypes
+import os
+import subprocess
+from ctypes import c_float, c_int32, c_size_t, c_void_p
+
+import numpy as np
+import torch
+
+from codeps_b200._native import MAX_LEVELS, PhotoArgs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "emu", "cdp_emu.cpp")
+LIB = os.path.join(HERE, "emu", "libcdp_emu.so")
+DEPS = [SRC] + [os.path.join(REPO, "codeps_b200", "csrc", n)
+                for n in ("cdp_common.h", "cdp_math.h", "cdp_kernels.h", "cdp_plan.h")]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+               "-I", os.path.join(REPO, "include"), "-I", os.path.join(REPO, "codeps_b200", "csrc"),
+               "-o", LIB, SRC]
+        subprocess.run(cmd, check=True)
+    lib = ctypes.CDLL(LIB)
+    lib.emu_resize_tables_bytes.restype = c_size_t
+    lib.emu_photo_scratch_bytes.restype = c_size_t
+    lib.emu_photo_saved_bytes.restype = c_size_t
+    lib.emu_smooth_saved_bytes.restype = c_size_t
+    for name in ("emu_resize_tables_bytes",):
+        getattr(lib, name).argtypes = [c_int32] * 3
+    for name in ("emu_photo_scratch_bytes", "emu_photo_saved_bytes"):
+        getattr(lib, name).argtypes = [c_int32] * 4
+    lib.emu_smooth_saved_bytes.argtypes = [c_int32] * 3
+    _lib = lib
+    return lib
+
+
+def _p(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(None)
+
+
+def _f32(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def resize_tables(h, w, levels):
+    lib = load()
+    n = lib.emu_resize_tables_bytes(h, w, levels)
+    buf = torch.zeros(n, dtype=torch.uint8)
+    assert lib.emu_resize_tables_build(c_int32(h), c_int32(w), c_int32(levels), _p(buf)) == 0
+    return buf
+
+
+def photo(level_intrinsics, images, depth, poses, noise, num_scales, alpha=0.85, with_grad=True,
+          grad_loss=1.0, seed=0):
+    """Run emu_photo_fwd (+ emu_photo_bwd).  level_intrinsics: [L,B,4] float32."""
+    lib = load()
+    b, _, h, w = depth.shape
+    tgt, s0, s1 = (_f32(i) for i in images)
+    depth, p0, p1 = _f32(depth), _f32(poses[0]), _f32(poses[1])
+    k = np.ascontiguousarray(level_intrinsics, dtype=np.float32)
+    assert k.shape == (num_scales, b, 4)
+    tables = resize_tables(h, w, num_scales)
+    scratch = torch.zeros(lib.emu_photo_scratch_bytes(b, h, w, num_scales), dtype=torch.uint8)
+    saved = torch.zeros(lib.emu_photo_saved_bytes(b, h, w, num_scales), dtype=torch.uint8)
+    loss = torch.zeros(1)
+    argmin = [torch.full((b, h >> s, w >> s), 77, dtype=torch.uint8) for s in range(num_scales)]
+    noise = [_f32(n) for n in noise] if noise is not None else None
+    a = PhotoArgs()
+    a.batch, a.height, a.width, a.num_levels = b, h, w, num_scales
+    a.alpha, a.with_grad = alpha, int(with_grad)
+    a.intrinsics_host = k.ctypes.data
+    a.target, a.source0, a.source1, a.depth = tgt.data_ptr(), s0.data_ptr(), s1.data_ptr(), depth.data_ptr()
+    a.pose0, a.pose1 = p0.data_ptr(), p1.data_ptr()
+    for s in range(num_scales):
+        a.noise[s] = noise[s].data_ptr() if noise is not None else None
+        a.argmin[s] = argmin[s].data_ptr()
+    a.noise_seed = seed
+    a.resize_tables = tables.data_ptr()
+    a.loss = loss.data_ptr()
+    a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
+    a.saved, a.saved_bytes = saved.data_ptr(), saved.numel()
+    assert lib.emu_photo_fwd(ctypes.byref(a)) == 0
+    out = {"recon": loss[0].clone(), "argmin": argmin}
+    if with_grad:
+        go = torch.tensor([grad_loss], dtype=torch.float32)
+        gd = torch.zeros_like(depth)
+        g0, g1 = torch.zeros(b, 4, 4), torch.zeros(b, 4, 4)
+        assert lib.emu_photo_bwd(c_int32(b), c_int32(h), c_int32(w), c_int32(num_scales), _p(saved), _p(tables),
+                                 _p(go), _p(gd), _p(g0), _p(g1)) == 0
+        out.update(grad_depth=gd, grad_pose=[g0, g1])
+    return out
+
+
+def smooth(image, disp, with_grad=True, grad_loss=1.0):
+    lib = load()
+    b, _, h, w = disp.shape
+    image, disp = _f32(image), _f32(disp)
+    saved = torch.zeros(lib.emu_smooth_saved_bytes(b, h, w), dtype=torch.uint8)
+    loss = torch.zeros(1)
+    assert lib.emu_smooth_fwd(_p(image), _p(disp), c_int32(b), c_int32(h), c_int32(w), c_int32(int(with_grad)),
+                              _p(loss), _p(saved)) == 0
+    out = {"smooth": loss[0].clone()}
+    if with_grad:
+        go = torch.tensor([grad_loss], dtype=torch.float32)
+        gd = torch.zeros_like(disp)
+        assert lib.emu_smooth_bwd(_p(saved), _p(go), c_int32(b), c_int32(h), c_int32(w), _p(gd)) == 0
+        out["grad_disp"] = gd
+    return out
+
+
+def warp_grid(depth, pose, k, motion=None):
+    lib = load()
+    b, _, h, w = depth.shape
+    depth, pose = _f32(depth), _f32(pose)
+    motion = _f32(motion) if motion is not None else None
+    k = np.ascontiguousarray(k, dtype=np.float32)
+    grid = torch.zeros(b, h, w, 2)
+    assert lib.emu_warp_grid_fwd(_p(depth), _p(pose), _p(motion), c_void_p(k.ctypes.data), c_int32(b), c_int32(h),
+                                 c_int32(w), _p(grid)) == 0
+    return grid
+
+
+def warp_image(src, depth, pose, k, mode=0, motion=None):
+    lib = load()
+    b, c, h, w = src.shape
+    src, depth, pose = _f32(src), _f32(depth), _f32(pose)
+    motion = _f32(motion) if motion is not None else None
+    k = np.ascontiguousarray(k, dtype=np.float32)
+    out = torch.zeros_like(src)
+    assert lib.emu_warp_image_fwd(_p(src), c_int32(c), _p(depth), _p(pose), _p(motion), c_void_p(k.ctypes.data),
+                                  c_int32(b), c_int32(h), c_int32(w), c_int32(mode), _p(out)) == 0
+    return out
+
+
+def warp_image_bwd(grad_out, src, depth, pose, k, motion=None):
+    lib = load()
+    b, c, h, w = src.shape
+    grad_out, src, depth, pose = _f32(grad_out), _f32(src), _f32(depth), _f32(pose)
+    motion = _f32(motion) if motion is not None else None
+    k = np.ascontiguousarray(k, dtype=np.float32)
+    gd = torch.zeros_like(depth)
+    gp = torch.zeros(b, 4, 4)
+    gm = torch.zeros_like(motion) if motion is not None else None
+    assert lib.emu_warp_image_bwd(_p(grad_out), _p(src), c_int32(c), _p(depth), _p(pose), _p(motion),
+                                  c_void_p(k.ctypes.data), c_int32(b), c_int32(h), c_int32(w), _p(gd), _p(gp),
+                                  _p(gm)) == 0
+    return gd, gp, gm
+
+
+def ssim(x, y):
+    lib = load()
+    b, c, h, w = x.shape
+    x, y = _f32(x), _f32(y)
+    out = torch.zeros_like(x)
+    assert lib.emu_ssim_fwd(_p(x), _p(y), c_int32(b * c), c_int32(h), c_int32(w), _p(out)) == 0
+    return out
+
+
+def ssim_bwd(grad_out, x, y):
+    lib = load()
+    b, c, h, w = x.shape
+    grad_out, x, y = _f32(grad_out), _f32(x), _f32(y)
+    gx, gy = torch.zeros_like(x), torch.zeros_like(y)
+    assert lib.emu_ssim_bwd(_p(grad_out), _p(x), _p(y), c_int32(b * c), c_int32(h), c_int32(w), _p(gx), _p(gy)) == 0
+    return gx, gy
+
+
+_ = (MAX_LEVELS, c_float)

@@ -1,0 +1,259 @@
+"""Parity of the CUDA path (through the drop-in classes and the C ABI) against the reference's
+golden outputs and against the CPU oracle.  Needs a B200: run with -m gpu.
+
+Tolerances are BASELINE.json's: loss rel 1e-5, gradients rel 1e-4 (normalised by the
+reference gradient's max-abs), argmin bit-exact wherever the fp64 reference's top-2 gap
+exceeds 1e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+import codeps_b200
+from codeps_b200 import ops
+from codeps_b200.synthetic import make_batch, make_preset_batch
+from helpers import (GOLDEN_CASES, Golden, assert_argmin_matches, assert_grad_close,
+                     assert_loss_close, rel_err)
+from oracle import photo_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def cams_from(k, w, h):
+    return [codeps_b200.CameraModel.from_tensor(w, h, torch.from_numpy(np.asarray(row))) for row in k]
+
+
+def run_cuda(g_or_inputs, w, h, num_scales, dev, noise, recon_weight=1.0):
+    """Forward + backward through ReconstructionLoss / EdgeAwareSmoothnessLoss on the GPU."""
+    inp = g_or_inputs
+    images = tuple(i.to(dev) for i in inp["images"])
+    depth = inp["depth"].to(dev).requires_grad_(True)
+    disp = inp["disp"].to(dev).requires_grad_(True)
+    poses = [p.to(dev).requires_grad_(True) for p in inp["poses"]]
+    loss_fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), num_scales, dev)
+    k_levels = loss_fn._level_intrinsics(cams_from(inp["intrinsics"], w, h))
+    recon, argmin = ops.photometric_loss(k_levels, images, depth, poses, [n.to(dev) for n in noise],
+                                         num_scales, 0.85)
+    smooth = codeps_b200.EdgeAwareSmoothnessLoss()(images[0], disp)
+    (recon_weight * recon + smooth).backward()
+    torch.cuda.synchronize()
+    return dict(recon=recon.detach().cpu(), smooth=smooth.detach().cpu(), argmin=[a.cpu() for a in argmin],
+                grad_depth=depth.grad.cpu(), grad_disp=disp.grad.cpu(),
+                grad_pose=[p.grad.cpu() for p in poses])
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_fixture_parity(name, cuda_device):
+    g = Golden(name)
+    inp = g.inputs()
+    out = run_cuda(inp, g.width, g.height, g.num_scales, cuda_device, inp["noise"])
+    assert_loss_close(out["recon"], g.z["ref64_recon"], "recon vs reference fp64")
+    assert_loss_close(out["recon"], g.z["ref32_recon"], "recon vs reference fp32")
+    assert_loss_close(out["smooth"], g.z["ref64_smooth"], "smooth")
+    for s in range(g.num_scales):
+        assert_argmin_matches(out["argmin"][s], g, s, "cuda")
+    assert_grad_close(out["grad_depth"], g.z["ref64_grad_depth"], "dL/d depth")
+    assert_grad_close(out["grad_disp"], g.z["ref64_grad_disp"], "dL/d disp")
+    assert_grad_close(out["grad_pose"][0], g.z["ref64_grad_pose0"], "dL/dT0")
+    assert_grad_close(out["grad_pose"][1], g.z["ref64_grad_pose1"], "dL/dT1")
+
+
+def test_golden_standalone_operators(cuda_device):
+    g = Golden("city_near")
+    inp = g.inputs(cuda_device)
+    cams = cams_from(inp["intrinsics"], g.width, g.height)
+    warper = codeps_b200.ImageWarper(g.width, g.height, cuda_device)
+    depth = inp["depth"].clone().requires_grad_(True)
+    pose = inp["poses"][1].clone().requires_grad_(True)
+    grid = warper.coordinate_warper(cams, depth.detach(), pose.detach())
+    np.testing.assert_allclose(grid.cpu().numpy(), g.z["op_grid"], rtol=0, atol=2e-6)
+    warped = warper(cams, inp["images"][2], depth, pose)
+    np.testing.assert_allclose(warped.detach().cpu().numpy(), g.z["op_warped"], rtol=0, atol=1e-4)
+    nearest = warper(cams, inp["images"][2], depth.detach(), pose.detach(), interp_mode="nearest")
+    assert (nearest.cpu().numpy() != g.z["op_nearest"]).mean() < 1e-3
+    up = g.t("op_upstream", cuda_device)
+    (warped * up).sum().backward()
+    assert_grad_close(depth.grad, g.z["op_warp_grad_depth"], "warp dL/d depth")
+    assert_grad_close(pose.grad, g.z["op_warp_grad_pose"], "warp dL/dT")
+    x = inp["images"][1].clone().requires_grad_(True)
+    y = inp["images"][0].clone().requires_grad_(True)
+    ssim = codeps_b200.SSIMLoss()(x, y)
+    np.testing.assert_allclose(ssim.detach().cpu().numpy(), g.z["op_ssim"], rtol=0, atol=2e-6)
+    (ssim * up).sum().backward()
+    assert_grad_close(x.grad, g.z["op_ssim_grad_x"], "ssim dL/dx")
+    assert_grad_close(y.grad, g.z["op_ssim_grad_y"], "ssim dL/dy")
+
+
+def test_object_motion_warp(cuda_device):
+    g = Golden("city_near")
+    inp = g.inputs()
+    k = inp["intrinsics"]
+    gen = torch.Generator().manual_seed(5)
+    motion = 0.01 * torch.randn(inp["depth"].shape[0], 3, g.height, g.width, generator=gen)
+    d_ref = inp["depth"].clone().requires_grad_(True)
+    p_ref = inp["poses"][0].clone().requires_grad_(True)
+    m_ref = motion.clone().requires_grad_(True)
+    want = po.warp_image(inp["images"][1], d_ref, p_ref, k, motion=m_ref)
+    up = torch.randn(want.shape, generator=gen)
+    (want * up).sum().backward()
+    d = inp["depth"].to(cuda_device).requires_grad_(True)
+    p = inp["poses"][0].to(cuda_device).requires_grad_(True)
+    m = motion.to(cuda_device).requires_grad_(True)
+    warper = codeps_b200.ImageWarper(g.width, g.height, cuda_device)
+    got = warper(cams_from(k, g.width, g.height), inp["images"][1].to(cuda_device), d, p, object_motion_map=m)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=0, atol=1e-4)
+    (got * up.to(cuda_device)).sum().backward()
+    assert_grad_close(d.grad, d_ref.grad, "dL/d depth")
+    assert_grad_close(p.grad, p_ref.grad, "dL/dT")
+    assert_grad_close(m.grad, m_ref.grad, "dL/d motion")
+
+
+@pytest.mark.parametrize("preset,batch", [("cityscapes", 1), ("kitti360", 1), ("semkitti", 2)])
+def test_full_size_against_oracle(preset, batch, cuda_device):
+    """BASELINE shapes (1024x512, 1408x376 with non-integer pyramid ratios, 1280x384) against the
+    CPU oracle in fp32 for values and fp64 for the argmin arbiter."""
+    tb = make_preset_batch(preset, batch, seed=21, flip_every_other=(batch > 1))
+    w, h, scales = tb.width, tb.height, 5
+    noise = po.draw_noise(batch, w, h, scales, seed=4321)
+    inp = dict(images=tb.images, depth=tb.depth, disp=tb.disp, poses=tb.poses, intrinsics=tb.intrinsics.numpy())
+    out = run_cuda(inp, w, h, scales, cuda_device, noise, recon_weight=10.0)
+    cams = cams_from(inp["intrinsics"], w, h)
+    k_levels = codeps_b200.ReconstructionLoss(w, h, None, scales, "cpu")._level_intrinsics(cams)
+    ref = po.loss_and_grads(inp["intrinsics"], tb.images, tb.depth, tb.disp, tb.poses, noise, scales,
+                            dtype=torch.float64, recon_weight=10.0, level_intrinsics=list(k_levels))
+    assert_loss_close(out["recon"], ref["recon"], "recon")
+    assert_loss_close(out["smooth"], ref["smooth"], "smooth")
+    assert_grad_close(out["grad_depth"], ref["grad_depth"], "dL/d depth")
+    assert_grad_close(out["grad_disp"], ref["grad_disp"], "dL/d disp")
+    assert_grad_close(out["grad_pose"][0], ref["grad_pose"][0], "dL/dT0")
+    assert_grad_close(out["grad_pose"][1], ref["grad_pose"][1], "dL/dT1")
+    flips = 0
+    for s in range(scales):
+        cand = ref["candidates"][s]
+        top2 = torch.sort(cand, dim=1).values[:, :2]
+        decided = (top2[:, 1] - top2[:, 0]) > 1e-6
+        bad = (out["argmin"][s] != ref["argmin"][s]) & decided
+        assert not bad.any(), f"level {s}: {int(bad.sum())} argmin mismatches away from ties"
+        flips += int((out["argmin"][s] != ref["argmin"][s]).sum())
+    hist = torch.bincount(out["argmin"][0].flatten().long(), minlength=4)
+    assert (hist > 0).all(), hist  # both reprojection and auto-mask winners present
+    print(f"{preset}: near-tie argmin differences vs fp64 oracle: {flips}; level-0 histogram {hist.tolist()}")
+
+
+def test_seeded_torch_noise_matches_reference_stream(cuda_device):
+    """Default mode draws torch.randn(B,2,H_s,W_s) per level like algos/depth.py:317, so a seeded
+    call consumes exactly the stream the reference would on the same device."""
+    tb = make_batch(2, 160, 96, (150.0, 151.0, 80.0, 47.0), seed=3)
+    scales = 4
+    dev = cuda_device
+    loss_fn = codeps_b200.ReconstructionLoss(tb.width, tb.height, codeps_b200.SSIMLoss(), scales, dev)
+    gpu = tb.to(dev)
+    torch.manual_seed(77)
+    recon = loss_fn(gpu.camera_models(), gpu.images, gpu.depth, gpu.poses)
+    after = torch.randn(3, device=dev)
+    torch.manual_seed(77)
+    noise = [torch.randn((2, 2, tb.height >> s, tb.width >> s), device=dev) for s in range(scales)]
+    assert torch.equal(after, torch.randn(3, device=dev)), "random stream position differs"
+    want = po.reconstruction_loss(tb.intrinsics.numpy(), tb.images, tb.depth, tb.poses,
+                                  [n.cpu() for n in noise], scales)
+    assert_loss_close(recon.cpu(), want, "recon with torch-drawn noise")
+    assert len(loss_fn.last_argmin) == scales and loss_fn.last_argmin[0].dtype == torch.uint8
+    assert loss_fn.auto_mask(0).shape == (2, tb.height, tb.width)
+
+
+def test_run_to_run_determinism(cuda_device):
+    tb = make_preset_batch("cityscapes", 2, seed=5)
+    noise = po.draw_noise(2, tb.width, tb.height, 5, seed=1)
+    inp = dict(images=tb.images, depth=tb.depth, disp=tb.disp, poses=tb.poses, intrinsics=tb.intrinsics.numpy())
+    a = run_cuda(inp, tb.width, tb.height, 5, cuda_device, noise)
+    b = run_cuda(inp, tb.width, tb.height, 5, cuda_device, noise)
+    assert torch.equal(a["recon"], b["recon"]) and torch.equal(a["smooth"], b["smooth"])
+    assert torch.equal(a["grad_depth"], b["grad_depth"]) and torch.equal(a["grad_disp"], b["grad_disp"])
+    assert all(torch.equal(x, y) for x, y in zip(a["grad_pose"], b["grad_pose"]))
+    assert all(torch.equal(x, y) for x, y in zip(a["argmin"], b["argmin"]))
+
+
+def test_full_size_properties(cuda_device):
+    """Size-independent properties at BASELINE size (Cityscapes, batch 8)."""
+    dev = cuda_device
+    tb = make_preset_batch("cityscapes", 8, seed=9)
+    w, h, scales = tb.width, tb.height, 5
+    noise = po.draw_noise(8, w, h, scales, seed=2)
+    inp = dict(images=tb.images, depth=tb.depth, disp=tb.disp, poses=tb.poses, intrinsics=tb.intrinsics.numpy())
+    full = run_cuda(inp, w, h, scales, dev, noise)
+    # (1) linearity of backward in the upstream gradient
+    scaled = run_cuda(inp, w, h, scales, dev, noise, recon_weight=10.0)
+    assert rel_err(scaled["grad_depth"], 10.0 * full["grad_depth"]) < 1e-6
+    assert rel_err(scaled["grad_pose"][1], 10.0 * full["grad_pose"][1]) < 1e-6
+    # (2) samples are independent: the batch loss is the mean of per-sample losses, and batch
+    #     gradients are per-sample gradients / B
+    recon_sum, smooth_sum = 0.0, 0.0
+    for i in (0, 5):
+        one = dict(images=tuple(t[i:i + 1] for t in tb.images), depth=tb.depth[i:i + 1], disp=tb.disp[i:i + 1],
+                   poses=tuple(p[i:i + 1] for p in tb.poses), intrinsics=inp["intrinsics"][i:i + 1])
+        single = run_cuda(one, w, h, scales, dev, [n[i:i + 1] for n in noise])
+        assert torch.equal(single["argmin"][0][0], full["argmin"][0][i])
+        assert rel_err(single["grad_depth"][0] / 8, full["grad_depth"][i]) < 1e-5
+        assert rel_err(single["grad_pose"][0][0] / 8, full["grad_pose"][0][i]) < 1e-5
+        recon_sum += float(single["recon"])
+        smooth_sum += float(single["smooth"])
+    # (3) a frame compared with itself under the identity pose costs nothing
+    eye = torch.eye(4).repeat(2, 1, 1)
+    same = dict(images=(tb.images[0][:2],) * 3, depth=tb.depth[:2], disp=tb.disp[:2], poses=(eye, eye),
+                intrinsics=inp["intrinsics"][:2])
+    zero_noise = [torch.zeros_like(n[:2]) for n in noise]
+    ident = run_cuda(same, w, h, scales, dev, zero_noise)
+    assert float(ident["recon"]) < 1e-5
+    # (4) auto-mask histogram is mixed
+    hist = torch.bincount(full["argmin"][0].flatten().long(), minlength=4)
+    assert (hist > 0).all()
+    del recon_sum, smooth_sum
+
+
+def test_batch_chunking_over_32_samples(cuda_device):
+    """More than CDP_MAX_BATCH_PER_LAUNCH samples go through several launches."""
+    dev = cuda_device
+    tb = make_batch(35, 64, 32, (70.0, 70.0, 32.0, 16.0), seed=8, flip_every_other=True)
+    scales = 3
+    noise = po.draw_noise(35, 64, 32, scales, seed=6)
+    inp = dict(images=tb.images, depth=tb.depth, disp=tb.disp, poses=tb.poses, intrinsics=tb.intrinsics.numpy())
+    out = run_cuda(inp, 64, 32, scales, dev, noise)
+    ref = po.loss_and_grads(inp["intrinsics"], tb.images, tb.depth, tb.disp, tb.poses, noise, scales,
+                            dtype=torch.float64)
+    assert_loss_close(out["recon"], ref["recon"], "recon")
+    assert_grad_close(out["grad_depth"], ref["grad_depth"], "dL/d depth")
+    assert_grad_close(out["grad_pose"][0], ref["grad_pose"][0], "dL/dT0")
+    assert_grad_close(out["grad_disp"], ref["grad_disp"], "dL/d disp")
+
+
+def test_fused_noise_mode_and_no_grad(cuda_device):
+    dev = cuda_device
+    tb = make_preset_batch("cityscapes", 2, seed=15).to(dev)
+    fused = codeps_b200.ReconstructionLoss(tb.width, tb.height, codeps_b200.SSIMLoss(), 5, dev, noise="fused")
+    default = codeps_b200.ReconstructionLoss(tb.width, tb.height, codeps_b200.SSIMLoss(), 5, dev)
+    with torch.no_grad():
+        a = fused(tb.camera_models(), tb.images, tb.depth, tb.poses)
+        b = default(tb.camera_models(), tb.images, tb.depth, tb.poses)
+    assert abs(float(a) - float(b)) <= 1e-4 * abs(float(b))  # only the tie-break draws differ
+    depth = tb.depth.clone().requires_grad_(True)
+    c = default(tb.camera_models(), tb.images, depth, tb.poses)
+    c.backward()
+    assert depth.grad is not None and torch.isfinite(depth.grad).all()
+    assert abs(float(c) - float(b)) <= 1e-4 * abs(float(b))
+
+
+def test_error_behaviour(cuda_device):
+    tb = make_batch(1, 64, 32, (70.0, 70.0, 32.0, 16.0), seed=1)
+    loss_fn = codeps_b200.ReconstructionLoss(64, 32, codeps_b200.SSIMLoss(), 3, cuda_device)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        loss_fn(tb.camera_models(), tb.images, tb.depth, tb.poses)  # CPU tensors: no fallback
+    gpu = tb.to(cuda_device)
+    with pytest.raises(TypeError):
+        loss_fn(gpu.camera_models(), tuple(i.double() for i in gpu.images), gpu.depth, gpu.poses)
+    with pytest.raises(AssertionError):
+        loss_fn([], gpu.images, gpu.depth, gpu.poses)  # same assert as algos/depth.py:268
+    with pytest.raises(ValueError):
+        codeps_b200.ReconstructionLoss(128, 64, codeps_b200.SSIMLoss(), 3, cuda_device)(
+            gpu.camera_models(), gpu.images, gpu.depth, gpu.poses)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        codeps_b200.EdgeAwareSmoothnessLoss()(tb.images[0], tb.disp)
