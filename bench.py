@@ -210,14 +210,12 @@ def main():
     w_recon = torch.tensor(RECON_WEIGHT, device=dev)
     w_smooth = torch.tensor(SMOOTH_WEIGHT, device=dev)
 
-    leaves = []
-    for ds in dev_sets:
-        leaves.append((ds.depth.clone().requires_grad_(True), ds.disp.clone().requires_grad_(True),
-                       ds.poses[0].clone().requires_grad_(True), ds.poses[1].clone().requires_grad_(True)))
-
     def step(i):
         """fwd + bwd on resident input set i; returns (recon, smooth, grads)."""
-        ds, (depth, disp, p0, p1) = dev_sets[i], leaves[i]
+        ds = dev_sets[i]
+        # fresh autograd leaves every step (views, no copies), created on the launching stream
+        depth, disp = ds.depth.detach().requires_grad_(True), ds.disp.detach().requires_grad_(True)
+        p0, p1 = ds.poses[0].detach().requires_grad_(True), ds.poses[1].detach().requires_grad_(True)
         recon = recon_fn(cams[i], ds.images, depth, (p0, p1))
         smooth = smooth_fn(ds.images[0], disp)
         # the caller's  loss = 10*recon + 0.001*smooth; loss.backward()  (train_codeps.py:102-107)

@@ -178,7 +178,7 @@ CDP_HD void cdp_pair_losses(const float* sm, int xbase, int ridx, float alpha, f
       ssim_sum[k] = CDP_ADD(ssim_sum[k], t.loss);
       const float x = k == 0 ? xs0[0] : xs1[0];
       l1_sum[k] = CDP_ADD(l1_sum[k], fabsf(CDP_SUB(x, ys[0])));
-      if (WANT_COEF) cdp_ssim_coeffs(st.mx[k], st.my, t, coef[k][ch * 3], coef[k][ch * 3 + 1], coef[k][ch * 3 + 2]);
+      if (WANT_COEF) cdp_ssim_coeffs(st.mx[k], st.my, x, ys[0], t, coef[k][ch * 3], coef[k][ch * 3 + 1], coef[k][ch * 3 + 2]);
     }
   }
   const float one_minus_alpha = (float)(1.0 - (double)alpha);
@@ -282,7 +282,7 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
     bool have_pt = false;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      float sa[3] = {0.f, 0.f, 0.f}, sb[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f};
+      float acc[3] = {0.f, 0.f, 0.f};  // sum over the window of m * (A0 + 2 (x_p - x_q) B + (y_p - y_q) C)
       bool any = kown == k;
 #pragma unroll
       for (int dy = -1; dy <= 1; ++dy) {
@@ -295,9 +295,11 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
           any = true;
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
-            sa[ch] += m * sm[Geo::coef_plane(ch * 3 + 0) * Geo::RN + n];
-            sb[ch] += m * sm[Geo::coef_plane(ch * 3 + 1) * Geo::RN + n];
-            sc[ch] += m * sm[Geo::coef_plane(ch * 3 + 2) * Geo::RN + n];
+            const float dxv = sm[(Geo::P_WARP + k * 3 + ch) * Geo::RN + ridx] - sm[(Geo::P_WARP + k * 3 + ch) * Geo::RN + n];
+            const float dyv = sm[(Geo::P_TGT + ch) * Geo::RN + ridx] - sm[(Geo::P_TGT + ch) * Geo::RN + n];
+            acc[ch] += m * (sm[Geo::coef_plane(ch * 3 + 0) * Geo::RN + n] +
+                            2.f * dxv * sm[Geo::coef_plane(ch * 3 + 1) * Geo::RN + n] +
+                            dyv * sm[Geo::coef_plane(ch * 3 + 2) * Geo::RN + n]);
           }
         }
       }
@@ -315,7 +317,7 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
       for (int ch = 0; ch < 3; ++ch) {
         const float x = sm[(Geo::P_WARP + k * 3 + ch) * Geo::RN + ridx];
         const float y = sm[(Geo::P_TGT + ch) * Geo::RN + ridx];
-        float gw = w_ssim * (sa[ch] + 2.f * x * sb[ch] + y * sc[ch]);
+        float gw = w_ssim * acc[ch];
         if (kown == k) gw += w_l1 * (x > y ? 1.f : (x < y ? -1.f : 0.f));
         gw *= lv.weight;
         float dix, diy;
@@ -636,7 +638,7 @@ CDP_HD void cdp_ssim_fwd_pixel(const float* x, const float* y, int W, int H, int
 }
 
 // backward pass 1: coefficient fields scaled by the upstream gradient -> scratch[4][planes*H*W]
-// (A_x, A_y, B, C)
+// (A0_x, A0_y, B, C in the centred form of cdp_ssim_coeffs)
 CDP_HD void cdp_ssim_bwd_coef_pixel(const float* grad_out, const float* x, const float* y, int W,
                                     int H, int plane_idx, int pix, float* scratch, size_t total) {
   const size_t base = (size_t)plane_idx * W * H;
@@ -644,10 +646,10 @@ CDP_HD void cdp_ssim_bwd_coef_pixel(const float* grad_out, const float* x, const
   cdp_ssim_stats_global(x + base, y + base, W, H, pix % W, pix / W, mx, my, exx, eyy, exy);
   CdpSsimTerms t;
   cdp_ssim_terms(mx, my, exx, eyy, exy, t);
+  const float xq = CDP_LDG(x + base + pix), yq = CDP_LDG(y + base + pix);
   float Ax, Bx, C, Ay, By;
-  cdp_ssim_coeffs(mx, my, t, Ax, Bx, C);
-  CdpSsimTerms ts = t;  // SSIM is symmetric in (x, y): swap the means for d/dy
-  cdp_ssim_coeffs(my, mx, ts, Ay, By, C);
+  cdp_ssim_coeffs(mx, my, xq, yq, t, Ax, Bx, C);
+  cdp_ssim_coeffs(my, mx, yq, xq, t, Ay, By, C);  // SSIM is symmetric in (x, y)
   const float go = CDP_LDG(grad_out + base + pix);
   scratch[0 * total + base + pix] = go * Ax;
   scratch[1 * total + base + pix] = go * Ay;
@@ -661,18 +663,18 @@ CDP_HD void cdp_ssim_bwd_gather_pixel(const float* x, const float* y, int W, int
                                       float* grad_y) {
   const size_t base = (size_t)plane_idx * W * H;
   const int py = pix / W, px = pix - py * W;
-  float sax = 0.f, say = 0.f, sb = 0.f, sc = 0.f;
+  const float xv = CDP_LDG(x + base + pix), yv = CDP_LDG(y + base + pix);
+  float gx = 0.f, gy = 0.f;
   for (int dy = -1; dy <= 1; ++dy)
     for (int dx = -1; dx <= 1; ++dx) {
       const float m = cdp_reflect_mult(py, dy, H) * cdp_reflect_mult(px, dx, W);
       if (m == 0.f) continue;
       const size_t o = base + (size_t)(py + dy) * W + (px + dx);
-      sax += m * scratch[0 * total + o];
-      say += m * scratch[1 * total + o];
-      sb += m * scratch[2 * total + o];
-      sc += m * scratch[3 * total + o];
+      const float ddx = xv - CDP_LDG(x + o), ddy = yv - CDP_LDG(y + o);
+      const float b = scratch[2 * total + o], c = scratch[3 * total + o];
+      gx += m * (scratch[0 * total + o] + 2.f * ddx * b + ddy * c);
+      gy += m * (scratch[1 * total + o] + 2.f * ddy * b + ddx * c);
     }
-  const float xv = CDP_LDG(x + base + pix), yv = CDP_LDG(y + base + pix);
-  if (grad_x) grad_x[base + pix] = (sax + 2.f * xv * sb + yv * sc) / 9.0f;
-  if (grad_y) grad_y[base + pix] = (say + 2.f * yv * sb + xv * sc) / 9.0f;
+  if (grad_x) grad_x[base + pix] = gx / 9.0f;
+  if (grad_y) grad_y[base + pix] = gy / 9.0f;
 }

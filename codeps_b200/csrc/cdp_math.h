@@ -173,15 +173,22 @@ CDP_HD void cdp_ssim_terms(float mx, float my, float exx, float eyy, float exy, 
   o.dl = (raw >= 0.f && raw <= 1.f) ? -0.5f : 0.f;  // clamp gradient is inclusive
 }
 
-// d loss / d (mean_x, E[x^2], E[xy]) -> the A, B, C fields of SURVEY.md section 8a:
-// d loss(q) / d x(p) = m(p,q)/9 * (A(q) + 2 x(p) B(q) + y(p) C(q)).
-CDP_HD void cdp_ssim_coeffs(float mx, float my, const CdpSsimTerms& t, float& A, float& B,
-                            float& C) {
+// SSIM adjoint coefficients.  With A = dl/dmean_x, B = dl/dE[x^2], C = dl/dE[xy] the gradient of
+// the loss at window centre q w.r.t. a window pixel p is
+//     d loss(q) / d x(p) = m(p,q)/9 * (A + 2 x(p) B + y(p) C).
+// A, 2xB and yC are each O(1/d2) and cancel almost completely, so in fp32 that form loses ~3
+// digits.  Substituting A = A1 - 2 mean_x B - mean_y C with
+//     A1 = dl * (2 mean_y n2 / (d1 d2) - 2 mean_x S / d1)          (no large terms)
+// gives the centred, well-conditioned form used by the kernels:
+//     d loss(q) / d x(p) = m/9 * (A0 + 2 (x(p) - x(q)) B + (y(p) - y(q)) C),
+//     A0 = A1 + 2 (x(q) - mean_x) B + (y(q) - mean_y) C            (gradient at the centre itself).
+CDP_HD void cdp_ssim_coeffs(float mx, float my, float xq, float yq, const CdpSsimTerms& t, float& A0,
+                            float& B, float& C) {
   const float inv = 1.0f / (t.d1 * t.d2);
-  const float dS_dm = 2.f * my * (t.n2 - t.n1) * inv - 2.f * mx * t.S / t.d1 + 2.f * mx * t.S / t.d2;
-  A = t.dl * dS_dm;
   B = t.dl * (-t.S / t.d2);
   C = t.dl * (2.f * t.n1 * inv);
+  const float A1 = t.dl * (2.f * my * t.n2 * inv - 2.f * mx * t.S / t.d1);
+  A0 = A1 + 2.f * (xq - mx) * B + (yq - my) * C;
 }
 
 // Reflection padding of one pixel (nn.ReflectionPad2d(1), algos/depth.py:123): -1 -> 1, n -> n-2.

@@ -88,9 +88,10 @@ def warp_image(src: torch.Tensor, depth: torch.Tensor, pose: torch.Tensor, intri
     return F.grid_sample(src, grid, mode=mode, padding_mode="border", align_corners=True)
 
 
-def ssim_loss_map(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+def ssim_loss_map(x: torch.Tensor, y: torch.Tensor, return_raw: bool = False):
     """SSIMLoss.__call__ (algos/depth.py:128-155): 3x3 box statistics on reflect-padded
-    inputs; returns clamp((1-SSIM)/2, 0, 1) per channel."""
+    inputs; returns clamp((1-SSIM)/2, 0, 1) per channel (and, on request, the un-clamped
+    value, whose distance to 0 / 1 tells how close the clamp is to switching)."""
     xp = F.pad(x, (1, 1, 1, 1), mode="reflect")
     yp = F.pad(y, (1, 1, 1, 1), mode="reflect")
     box = lambda t: F.avg_pool2d(t, 3, 1)
@@ -100,7 +101,9 @@ def ssim_loss_map(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     cov = box(xp * yp) - mu_x * mu_y
     num = (2 * mu_x * mu_y + SSIM_C1) * (2 * cov + SSIM_C2)
     den = (mu_x**2 + mu_y**2 + SSIM_C1) * (var_x + var_y + SSIM_C2)
-    return torch.clamp((1 - num / den) / 2, 0, 1)
+    raw = (1 - num / den) / 2
+    out = torch.clamp(raw, 0, 1)
+    return (out, raw) if return_raw else out
 
 
 def photometric_error(pred: torch.Tensor, tgt: torch.Tensor, alpha: float = 0.85) -> torch.Tensor:
@@ -134,16 +137,25 @@ def reconstruction_loss(intrinsics, images: Sequence[torch.Tensor], depth: torch
                         poses: Sequence[torch.Tensor], noise: Sequence[torch.Tensor],
                         num_scales: int = 5, alpha: float = 0.85,
                         motions: Optional[Sequence[torch.Tensor]] = None,
-                        level_intrinsics: Optional[Sequence] = None, details: bool = False):
+                        level_intrinsics: Optional[Sequence] = None, details: bool = False,
+                        forced_argmin: Optional[Sequence[torch.Tensor]] = None):
     """ReconstructionLoss.__call__ (algos/depth.py:239-326), auto-mask branch.
 
     ``noise[s]`` is the [B,2,H_s,W_s] tensor the reference would draw with ``torch.randn`` at
     level s (depth.py:317) -- *unscaled*; it is multiplied by 1e-5 here.  ``level_intrinsics``
     optionally overrides the per-level [B,4] tables (used when the caller has CameraModel
     objects and wants the exact python-side rounding).  With ``details`` also returns, per
-    level, the stacked candidate losses [B,4,H_s,W_s] and the argmin [B,H_s,W_s] (index 0/1 =
+    level, the stacked candidate losses [B,4,H_s,W_s], the argmin [B,H_s,W_s] (index 0/1 =
     reprojection from t-1/t+1, 2/3 = identity, i.e. auto-masked), which the reference
-    computes and discards (depth.py:323).
+    computes and discards (depth.py:323), the two normalised sampling grids, and the smallest
+    |warped - target| over sources and channels (distance of the L1 term to its sign switch).
+
+    ``forced_argmin`` (test aid): per level a [B,H_s,W_s] index map to select instead of the
+    minimum.  Gradients are a smooth function of the inputs only for a *given* selection; at a
+    near-tie, fp32 and fp64 evaluations of the reference itself pick different candidates and
+    their gradients differ at those pixels.  Forcing the selection of the implementation under
+    test lets a gradient comparison ignore exactly that ambiguity (the selection itself is
+    checked separately, bit-exact away from ties).
     """
     _, _, h, w = depth.shape
     total = torch.zeros(1, dtype=depth.dtype, device=depth.device)
@@ -154,19 +166,29 @@ def reconstruction_loss(intrinsics, images: Sequence[torch.Tensor], depth: torch
             intrinsics, (w, h), (ws, hs)))
         tgt_s = resize_bilinear(images[0], hs, ws)
         depth_s = resize_bilinear(depth, hs, ws)
-        cands = []
+        cands, grids, l1_margin, clamp_margin = [], [], None, None
         for i, frame in enumerate(images[1:]):
             src_s = resize_bilinear(frame, hs, ws)
             motion_s = None if motions is None else resize_bilinear(motions[i], hs, ws)
-            warped = warp_image(src_s, depth_s, poses[i], k_s, motion=motion_s)
+            grid = reproject_grid(depth_s, poses[i], k_s, motion_s)
+            grids.append(grid.detach())
+            warped = F.grid_sample(src_s, grid, mode="bilinear", padding_mode="border", align_corners=True)
             cands.append(photometric_error(warped, tgt_s, alpha))
+            margin = (warped.detach() - tgt_s).abs().amin(1)
+            l1_margin = margin if l1_margin is None else torch.minimum(l1_margin, margin)
+            raw = ssim_loss_map(warped.detach(), tgt_s, return_raw=True)[1]
+            margin = torch.minimum(raw.abs(), (1 - raw).abs()).amin(1)
+            clamp_margin = margin if clamp_margin is None else torch.minimum(clamp_margin, margin)
         ident = [photometric_error(resize_bilinear(frame, hs, ws), tgt_s, alpha)
                  for frame in images[1:]]
         ident = torch.cat(ident, 1) + noise[s].to(depth.dtype) * 0.00001
         stacked = torch.cat(cands + [ident], dim=1)
         best, which = torch.min(stacked, dim=1)
+        if forced_argmin is not None:
+            which = forced_argmin[s].to(torch.int64)
+            best = stacked.gather(1, which.unsqueeze(1)).squeeze(1)
         total = total + best.mean() / (2**s)
-        per_level.append((stacked, which))
+        per_level.append((stacked, which, grids, l1_margin, clamp_margin))
     loss = total[0] / num_scales
     return (loss, per_level) if details else loss
 
@@ -193,7 +215,7 @@ def draw_noise(batch: int, width: int, height: int, num_scales: int, seed: int,
 
 def loss_and_grads(intrinsics, images, depth, disp, poses, noise, num_scales=5, alpha=0.85,
                    dtype=torch.float32, recon_weight: float = 1.0, smooth_weight: float = 1.0,
-                   level_intrinsics=None):
+                   level_intrinsics=None, forced_argmin=None):
     """Forward + autograd backward of (recon, smooth) on the CPU.  Returns a dict with the two
     loss values, per-level argmin/candidates and dL/d depth, dL/d disp, dL/dT_0, dL/dT_1 of
     ``recon_weight*recon + smooth_weight*smooth`` (depth and disp are treated as independent
@@ -204,14 +226,18 @@ def loss_and_grads(intrinsics, images, depth, disp, poses, noise, num_scales=5, 
     disp = cast(disp).requires_grad_(True)
     poses = [cast(p).requires_grad_(True) for p in poses]
     recon, levels = reconstruction_loss(intrinsics, images, depth, poses, noise, num_scales,
-                                        alpha, level_intrinsics=level_intrinsics, details=True)
+                                        alpha, level_intrinsics=level_intrinsics, details=True,
+                                        forced_argmin=forced_argmin)
     smooth = smoothness_loss(images[0], disp)
     (recon_weight * recon + smooth_weight * smooth).backward()
     return {
         "recon": recon.detach(),
         "smooth": smooth.detach(),
-        "argmin": [w.to(torch.uint8) for _, w in levels],
-        "candidates": [c.detach() for c, _ in levels],
+        "argmin": [lv[1].to(torch.uint8) for lv in levels],
+        "candidates": [lv[0].detach() for lv in levels],
+        "grids": [lv[2] for lv in levels],  # per level: normalised sampling grids of both sources
+        "l1_margin": [lv[3] for lv in levels],  # per level: min over sources/channels |warped - target|
+        "clamp_margin": [lv[4] for lv in levels],  # per level: distance of (1-SSIM)/2 to the clamp bounds
         "grad_depth": depth.grad,
         "grad_disp": disp.grad,
         "grad_pose": [p.grad for p in poses],

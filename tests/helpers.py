@@ -62,3 +62,156 @@ def assert_argmin_matches(got, golden: Golden, level: int, what=""):
     assert not bad.any(), (f"{what} level {level}: {int(bad.sum())} argmin mismatches away from ties "
                            f"(of {bad.size}; {int((~decided).sum())} near-tie pixels excluded)")
     return int((got != ref64).sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# Elements whose gradient is not a continuous function of the inputs.
+#
+# The loss contains discrete decisions: the min-reprojection argmin, the bilinear tap cell
+# floor(ix) (the sampled VALUE is continuous across cells, its coordinate derivative is not), the
+# border clip, and sign() in the L1 / smoothness terms.  Where such a decision sits within fp32
+# rounding of its switching point, the fp32 reference, its own fp64 run and any other fp32
+# implementation legitimately disagree (oracle/make_golden.py fixtures: the fp32 reference
+# deviates from its fp64 run by up to 8e-4 of max-abs on dL/dT).  The gradient tolerance of
+# 1e-4 is therefore asserted on all other elements, the excluded ones are counted, and their
+# share is bounded.  The decisions themselves are tested separately (argmin bit-exact away from
+# ties).
+# ---------------------------------------------------------------------------------------------
+COORD_EPS = 2e-6  # relative to the image extent: a few fp32 ulps of the pixel coordinate
+
+
+def _spread_to_full_res(masks, height, width, window):
+    """Union over levels of level-s boolean masks [B,H_s,W_s] (grown by the 3x3 SSIM window when
+    ``window``), mapped to the exact set of full-resolution pixels that feed them through the
+    bilinear pyramid (the support of the adjoint of F.interpolate), as a [B,H,W] mask."""
+    import torch.nn.functional as F
+    total = torch.zeros(masks[0].shape[0], height, width, dtype=torch.bool)
+    for m in masks:
+        m = m.float().unsqueeze(1)
+        if window:
+            m = F.max_pool2d(m, 3, 1, 1)
+        if m.shape[2] == height and m.shape[3] == width:
+            total |= m[:, 0] > 0
+            continue
+        x = torch.zeros(m.shape[0], 1, height, width, requires_grad=True)
+        y = F.interpolate(x, (m.shape[2], m.shape[3]), mode="bilinear", align_corners=False)
+        (y * m).sum().backward()
+        total |= x.grad[:, 0] != 0
+    return total
+
+
+def tie_shadow(got_argmin, ref_argmin, height, width):
+    """[B,H,W] mask of the depth pixels that can depend on a pixel whose selection differs."""
+    diff = [torch.as_tensor(a).cpu().long() != torch.as_tensor(b).cpu().long()
+            for a, b in zip(got_argmin, ref_argmin)]
+    return _spread_to_full_res(diff, height, width, window=True)
+
+
+def tap_shadow(grids, height, width, eps=COORD_EPS):
+    """[B,H,W] mask of the depth pixels fed by a level pixel whose (fp64) sample coordinate lies
+    within ``eps`` * image extent of an integer for either source frame (tap cell / border clip
+    switch)."""
+    masks = []
+    for level_grids in grids:
+        unstable = None
+        for g in level_grids:
+            hs, ws = g.shape[1], g.shape[2]
+            ix = (g[..., 0].double() + 1) / 2 * (ws - 1)
+            iy = (g[..., 1].double() + 1) / 2 * (hs - 1)
+            near = ((ix - ix.round()).abs() < eps * ws) | ((iy - iy.round()).abs() < eps * hs)
+            unstable = near if unstable is None else (unstable | near)
+        masks.append(unstable.cpu())
+    return _spread_to_full_res(masks, height, width, window=False)
+
+
+def l1_sign_shadow(l1_margin, height, width, eps=2e-5):
+    """[B,H,W] mask of the depth pixels fed by a level pixel where some warped channel is within
+    ``eps`` of the target value: sign(warped - target) of the L1 term is undecided in fp32."""
+    return _spread_to_full_res([(m < eps).cpu() for m in l1_margin], height, width, window=False)
+
+
+def ssim_clamp_shadow(clamp_margin, height, width, eps=2e-5):
+    """[B,H,W] mask of the depth pixels inside the SSIM window of a level pixel whose un-clamped
+    (1-SSIM)/2 is within ``eps`` of 0 or 1 (clamp gradient switches between -1/2 and 0)."""
+    return _spread_to_full_res([(m < eps).cpu() for m in clamp_margin], height, width, window=True)
+
+
+def unstable_depth_mask(ref, got_argmin, height, width):
+    """Union of the masks above, from an fp64 oracle result ``ref`` (loss_and_grads)."""
+    return (tie_shadow(got_argmin, ref["argmin"], height, width) | tap_shadow(ref["grids"], height, width)
+            | l1_sign_shadow(ref["l1_margin"], height, width)
+            | ssim_clamp_shadow(ref["clamp_margin"], height, width))
+
+
+def smooth_sign_shadow(disp, rel_eps=2e-6):
+    """[B,1,H,W] mask of disparity pixels that touch a neighbour pair whose normalised
+    disparities differ by less than fp32 resolution (sign() of the difference is undecided)."""
+    d = torch.as_tensor(disp, dtype=torch.float64).cpu()
+    d = d / (d.mean((2, 3), keepdim=True) + 1e-7)
+    mask = torch.zeros_like(d, dtype=torch.bool)
+    dx = (d[..., :, :-1] - d[..., :, 1:]).abs() < rel_eps * d[..., :, :-1].abs()
+    dy = (d[..., :-1, :] - d[..., 1:, :]).abs() < rel_eps * d[..., :-1, :].abs()
+    mask[..., :, :-1] |= dx
+    mask[..., :, 1:] |= dx
+    mask[..., :-1, :] |= dy
+    mask[..., 1:, :] |= dy
+    return mask
+
+
+def assert_grad_close_masked(got, want, mask_out, what, rtol=GRAD_RTOL, max_masked_frac=0.25, ref32=None):
+    """Deviation from the fp64 result ``want``, normalised by max|want|, over the elements NOT in
+    ``mask_out`` (discrete switches).
+
+    Without ``ref32``: every element within ``rtol``.
+
+    With ``ref32`` (the reference algorithm evaluated in fp32 on the same inputs): fp32 cannot
+    hold 1e-4 element-wise at BASELINE image sizes -- sample coordinates above 1000 px resolve
+    only ~1e-4 px, which moves warped values by ~5e-5 and, through SSIM variances E[x^2]-mu^2 of
+    order 1e-3, single gradient elements by ~1e-3 of max-abs; the fp32 reference deviates from
+    its own fp64 run by that much (5e-4 on dL/d depth, 8e-4 on dL/dT in the committed
+    fixtures).  So: 99.9 % of the elements within ``rtol``, and the worst element no worse than
+    ``rtol`` + 3x the fp32 reference's own worst deviation."""
+    got = torch.as_tensor(got, dtype=torch.float64).cpu()
+    want = torch.as_tensor(want, dtype=torch.float64).cpu()
+    keep = ~mask_out.reshape(want.shape) if mask_out is not None else torch.ones_like(want, dtype=torch.bool)
+    frac = float((~keep).float().mean())
+    assert frac <= max_masked_frac, f"{what}: {frac:.3%} of the elements are excluded (limit {max_masked_frac:.0%})"
+    scale = want.abs().max().clamp_min(1e-30)
+    dev = ((got - want).abs() / scale)[keep]
+    worst = float(dev.max())
+    excluded = int((~keep).sum())
+    if ref32 is None:
+        assert worst <= rtol, (f"{what}: max-abs-normalised error {worst:.3e} > {rtol} "
+                               f"({excluded} discontinuous elements excluded)")
+        return excluded
+    ref_worst = float((((torch.as_tensor(ref32, dtype=torch.float64).cpu() - want).abs() / scale)[keep]).max())
+    if dev.numel() >= 1000:
+        bulk = float(torch.quantile(dev[torch.randperm(dev.numel())[:4_000_000]], 0.999))
+        assert bulk <= rtol, f"{what}: 99.9% quantile of the normalised error {bulk:.3e} > {rtol}"
+    assert worst <= rtol + 3 * ref_worst, (f"{what}: worst normalised error {worst:.3e} exceeds {rtol} + 3 x the fp32 "
+                                           f"reference's own worst deviation ({ref_worst:.3e})")
+    return excluded
+
+
+def check_photo_grads(out, inputs, num_scales, what, level_intrinsics=None, recon_weight=1.0,
+                      max_masked_frac=0.25):
+    """Gradient parity of one photometric-loss result ``out`` (dict with argmin, grad_depth,
+    grad_pose) against the oracle evaluated with the same min-reprojection selection, in fp64
+    (truth) and fp32 (the reference's own rounding).  Returns a short report string."""
+    from oracle import photo_oracle as po
+    h, w = inputs["depth"].shape[2], inputs["depth"].shape[3]
+    kw = dict(num_scales=num_scales, recon_weight=recon_weight, level_intrinsics=level_intrinsics,
+              forced_argmin=[a.cpu() for a in out["argmin"]])
+    args = (inputs["intrinsics"], inputs["images"], inputs["depth"], inputs["disp"], inputs["poses"], inputs["noise"])
+    r64 = po.loss_and_grads(*args, dtype=torch.float64, **kw)
+    r32 = po.loss_and_grads(*args, dtype=torch.float32, **kw)
+    mask = unstable_depth_mask(r64, out["argmin"], h, w).unsqueeze(1)
+    n = assert_grad_close_masked(out["grad_depth"], r64["grad_depth"], mask, f"{what} dL/d depth",
+                                 max_masked_frac=max_masked_frac, ref32=r32["grad_depth"])
+    for i in range(2):
+        assert_grad_close_masked(out["grad_pose"][i], r64["grad_pose"][i], None, f"{what} dL/dT{i}",
+                                 ref32=r32["grad_pose"][i])
+    raw = rel_err(out["grad_depth"], r64["grad_depth"])
+    raw32 = rel_err(r32["grad_depth"], r64["grad_depth"])
+    return (f"{what}: dL/d depth max-abs-normalised deviation from fp64 {raw:.2e} (fp32 reference algorithm: "
+            f"{raw32:.2e}); {n} of {mask.numel()} pixels at discrete switches excluded")
