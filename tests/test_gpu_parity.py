@@ -134,14 +134,21 @@ def test_full_size_against_oracle(preset, batch, cuda_device):
     inp["noise"] = noise
     print(check_photo_grads(out, inp, scales, preset, level_intrinsics=list(k_levels), recon_weight=10.0,
                             max_masked_frac=0.05))
+    # argmin: bit-exact wherever the fp64 top-2 gap exceeds TIE_GAP_FULL.  At >= 1024 px the fp32
+    # sample coordinate resolves ~1e-4 px, i.e. candidate losses carry ~1e-5 of rounding: the
+    # reference algorithm evaluated in fp32 differs from its own fp64 run on 7-10 pixels per
+    # 0.5 Mpx with gaps up to 1.1e-5 (measured with the oracle on these inputs), so the 1e-6 gap
+    # used for the small golden fixtures is below fp32 resolution here.
+    TIE_GAP_FULL = 2e-5
     flips = 0
     for s in range(scales):
         cand = ref["candidates"][s]
         top2 = torch.sort(cand, dim=1).values[:, :2]
-        decided = (top2[:, 1] - top2[:, 0]) > 1e-6
+        decided = (top2[:, 1] - top2[:, 0]) > TIE_GAP_FULL
         bad = (out["argmin"][s] != ref["argmin"][s]) & decided
         assert not bad.any(), f"level {s}: {int(bad.sum())} argmin mismatches away from ties"
         flips += int((out["argmin"][s] != ref["argmin"][s]).sum())
+    assert flips <= 64 * batch, f"{flips} near-tie differences"
     hist = torch.bincount(out["argmin"][0].flatten().long(), minlength=4)
     assert (hist > 0).all(), hist  # both reprojection and auto-mask winners present
     print(f"{preset}: near-tie argmin differences vs fp64 oracle: {flips}; level-0 histogram {hist.tolist()}")
