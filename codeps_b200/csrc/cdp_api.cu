@@ -152,15 +152,15 @@ __global__ void __launch_bounds__(CDP_PHOTO_THREADS, 2)
 cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p) {
   extern __shared__ __align__(16) float sm[];
   const CdpTileCtx c = cdp_tile_ctx(p, blockIdx.x, blockIdx.y);
-  cdp_photo_phase_a<G>(p, c, threadIdx.x, blockDim.x, sm);
-  __syncthreads();
-  cdp_photo_phase_b1<G>(p, c, threadIdx.x, blockDim.x, sm);
-  __syncthreads();
   float v[G ? 33 : 1];
 #pragma unroll
   for (int i = 0; i < (G ? 33 : 1); ++i) v[i] = 0.f;
-  cdp_photo_phase_b2<G>(p, c, threadIdx.x, blockDim.x, sm, v[0]);
+  cdp_photo_phase_a<G>(p, c, threadIdx.x, blockDim.x, sm);
+  __syncthreads();
+  cdp_photo_phase_b1<G>(p, c, threadIdx.x, blockDim.x, sm, v[0]);
   if constexpr (G) {
+    __syncthreads();
+    cdp_photo_phase_b2(p, c, threadIdx.x, blockDim.x, sm);
     __syncthreads();
     cdp_photo_phase_c(p, c, threadIdx.x, blockDim.x, sm, &v[1]);
   }

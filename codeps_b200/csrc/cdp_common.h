@@ -21,6 +21,12 @@
 #define CDP_HD inline
 #endif
 
+#if !defined(__CUDACC__)
+struct alignas(8) float2 {  // CUDA's vector type, for the host build of the kernel bodies
+  float x, y;
+};
+#endif
+
 // Separately rounded fp32 operations.  The reference evaluates SSIM and the warp chain as
 // individual ATen ops, each rounding to fp32; nvcc would otherwise contract a*b+c into FMA.
 // Where matching that rounding matters for the argmin the kernels use
@@ -52,6 +58,7 @@
 
 struct CdpCam {
   float fx, fy, cx, cy;
+  float ifx, ify;  // 1/fx, 1/fy
 };
 
 // Bilinear-resize taps (forward) and their transpose (adjoint gather), built on the host by

@@ -46,290 +46,9 @@ CDP_HD void cdp_pyramid_fwd_item(const CdpPyrParams& p, int b, int item) {
 }
 
 // ==========================================================================================
-// 2. Fused photometric tile kernel.
+// 2. Fused photometric tile kernel: see cdp_photo_tile.h
 // ==========================================================================================
-template <bool G>
-struct CdpTileGeom {
-  static constexpr int HALO = G ? 2 : 1;  // warped / source / target values staged around the tile
-  static constexpr int RW = CDP_TILE_X + 2 * HALO, RH = CDP_TILE_Y + 2 * HALO, RN = RW * RH;
-  static constexpr int HB = HALO - 1;     // ring on which losses / argmin / coefficients are needed
-  static constexpr int BW = CDP_TILE_X + 2 * HB, BH = CDP_TILE_Y + 2 * HB, BN = BW * BH;
-  // shared-memory planes of RN floats each
-  static constexpr int P_WARP = 0;   // 6: warped source k, channel c at k*3+c
-  static constexpr int P_TGT = 6;    // 3
-  static constexpr int P_SRC = 9;    // 6: un-warped sources (identity candidates)
-  static constexpr int P_ID = 15;    // 2: identity losses per source
-  static constexpr int P_EXTRA = 17; // 1 (with grad)
-  static constexpr int NPLANES = G ? 18 : 17;
-  static constexpr size_t SMEM_BYTES = (size_t)NPLANES * RN * sizeof(float) + ((RN + 15) & ~15);
-  // After the identity pass the source planes are dead: the 9 coefficient fields of the winning
-  // reprojection (A,B,C per channel) reuse P_SRC+0..5, P_ID+0..1 and P_EXTRA.
-  static constexpr CDP_HD int coef_plane(int j) { return j < 6 ? P_SRC + j : (j < 8 ? P_ID + (j - 6) : P_EXTRA); }
-};
-
-struct CdpTileCtx {
-  int lvl, b, b_local, x0, y0;  // level, sample (global / within launch), tile origin
-};
-
-CDP_HD CdpTileCtx cdp_tile_ctx(const CdpPhotoParams& p, int bx, int by) {
-  CdpTileCtx c;
-  int s = p.num_levels - 1;
-  while (s > 0 && bx < p.lv[s].block_begin) --s;
-  c.lvl = s;
-  const int tile = bx - p.lv[s].block_begin;
-  const int ty = tile / p.lv[s].tiles_x;
-  c.x0 = (tile - ty * p.lv[s].tiles_x) * CDP_TILE_X;
-  c.y0 = ty * CDP_TILE_Y;
-  c.b_local = by;
-  c.b = p.batch_begin + by;
-  return c;
-}
-
-CDP_HD CdpCam cdp_tile_cam(const CdpPhotoParams& p, const CdpTileCtx& c) {
-  CdpCam k;
-  k.fx = p.K[c.lvl][c.b_local][0]; k.fy = p.K[c.lvl][c.b_local][1];
-  k.cx = p.K[c.lvl][c.b_local][2]; k.cy = p.K[c.lvl][c.b_local][3];
-  return k;
-}
-
-// Phase A: warp both sources for every staged position (tile + halo, reflected at the image
-// border) and stage target / source values.
-template <bool G>
-CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads,
-                              float* sm) {
-  typedef CdpTileGeom<G> Geo;
-  const CdpLevel& lv = p.lv[c.lvl];
-  const int W = lv.W, H = lv.H;
-  const size_t plane = (size_t)W * H;
-  const CdpCam cam = cdp_tile_cam(p, c);
-  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-  const float* T[2] = {p.pose0 + (size_t)c.b * 16, p.pose1 + (size_t)c.b * 16};
-  const float* src[2] = {lv.src0 + (size_t)c.b * 3 * plane, lv.src1 + (size_t)c.b * 3 * plane};
-  const float* tgt = lv.tgt + (size_t)c.b * 3 * plane;
-  for (int idx = tid; idx < Geo::RN; idx += nthreads) {
-    const int ry = idx / Geo::RW, rx = idx - ry * Geo::RW;
-    const int px = c.x0 - Geo::HALO + rx, py = c.y0 - Geo::HALO + ry;
-    if (px < -1 || px > W || py < -1 || py > H) continue;  // never read
-    const int u = cdp_reflect(px, W), v = cdp_reflect(py, H);
-    const int pix = v * W + u;
-    CdpPoint pt;
-    cdp_backproject((float)u, (float)v, CDP_LDG(lv.depth + (size_t)c.b * plane + pix), cam, pt);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      sm[(Geo::P_TGT + ch) * Geo::RN + idx] = CDP_LDG(tgt + ch * plane + pix);
-      sm[(Geo::P_SRC + ch) * Geo::RN + idx] = CDP_LDG(src[0] + ch * plane + pix);
-      sm[(Geo::P_SRC + 3 + ch) * Geo::RN + idx] = CDP_LDG(src[1] + ch * plane + pix);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      CdpProj pr;
-      cdp_project(pt.P, T[k], nullptr, cam, wm1, hm1, pr);
-      CdpTaps t;
-      cdp_taps(pr.ix, pr.iy, W, H, t);
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch)
-        sm[(Geo::P_WARP + k * 3 + ch) * Geo::RN + idx] = cdp_bilinear(src[k] + ch * plane, t);
-    }
-  }
-}
-
-// 3x3 window sums in the reference's order (avg_pool2d: row-major accumulation, then / 9) for
-// two candidate images sharing one target.  xs0/xs1/ys point at the window centre.
-struct CdpPairStats {
-  float mx[2], exx[2], exy[2], my, eyy;
-};
-
-CDP_HD void cdp_window_stats(const float* xs0, const float* xs1, const float* ys, int pitch,
-                             CdpPairStats& o) {
-  float sx0 = 0.f, sx1 = 0.f, sy = 0.f, sxx0 = 0.f, sxx1 = 0.f, syy = 0.f, sxy0 = 0.f, sxy1 = 0.f;
-#pragma unroll
-  for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int o = dy * pitch + dx;
-      const float y = ys[o], a = xs0[o], b = xs1[o];
-      sy = CDP_ADD(sy, y); syy = CDP_ADD(syy, CDP_MUL(y, y));
-      sx0 = CDP_ADD(sx0, a); sxx0 = CDP_ADD(sxx0, CDP_MUL(a, a)); sxy0 = CDP_ADD(sxy0, CDP_MUL(a, y));
-      sx1 = CDP_ADD(sx1, b); sxx1 = CDP_ADD(sxx1, CDP_MUL(b, b)); sxy1 = CDP_ADD(sxy1, CDP_MUL(b, y));
-    }
-  o.my = sy / 9.0f; o.eyy = syy / 9.0f;
-  o.mx[0] = sx0 / 9.0f; o.exx[0] = sxx0 / 9.0f; o.exy[0] = sxy0 / 9.0f;
-  o.mx[1] = sx1 / 9.0f; o.exx[1] = sxx1 / 9.0f; o.exy[1] = sxy1 / 9.0f;
-}
-
-// ReconstructionLoss._compute_loss (algos/depth.py:234-236) for two candidates at one position.
-// xbase = first plane of candidate 0 (candidate 1 follows 3 planes later).  coef (optional,
-// [2][9]) receives A,B,C per channel for both candidates.
-template <bool WANT_COEF, int RN, int RW, int P_TGT>
-CDP_HD void cdp_pair_losses(const float* sm, int xbase, int ridx, float alpha, float loss[2],
-                            float (*coef)[9]) {
-  float ssim_sum[2] = {0.f, 0.f}, l1_sum[2] = {0.f, 0.f};
-#pragma unroll
-  for (int ch = 0; ch < 3; ++ch) {
-    const float* xs0 = sm + (xbase + ch) * RN + ridx;
-    const float* xs1 = sm + (xbase + 3 + ch) * RN + ridx;
-    const float* ys = sm + (P_TGT + ch) * RN + ridx;
-    CdpPairStats st;
-    cdp_window_stats(xs0, xs1, ys, RW, st);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      CdpSsimTerms t;
-      cdp_ssim_terms(st.mx[k], st.my, st.exx[k], st.eyy, st.exy[k], t);
-      ssim_sum[k] = CDP_ADD(ssim_sum[k], t.loss);
-      const float x = k == 0 ? xs0[0] : xs1[0];
-      l1_sum[k] = CDP_ADD(l1_sum[k], fabsf(CDP_SUB(x, ys[0])));
-      if (WANT_COEF) cdp_ssim_coeffs(st.mx[k], st.my, x, ys[0], t, coef[k][ch * 3], coef[k][ch * 3 + 1], coef[k][ch * 3 + 2]);
-    }
-  }
-  const float one_minus_alpha = (float)(1.0 - (double)alpha);
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-    loss[k] = CDP_ADD(CDP_MUL(alpha, ssim_sum[k] / 3.0f), CDP_MUL(one_minus_alpha, l1_sum[k] / 3.0f));
-}
-
-// Phase B1: identity (un-warped) losses on the statistics ring -> P_ID planes.
-template <bool G>
-CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads,
-                               float* sm) {
-  typedef CdpTileGeom<G> Geo;
-  const CdpLevel& lv = p.lv[c.lvl];
-  for (int idx = tid; idx < Geo::BN; idx += nthreads) {
-    const int by = idx / Geo::BW, bx = idx - by * Geo::BW;
-    const int qx = c.x0 - Geo::HB + bx, qy = c.y0 - Geo::HB + by;
-    if (qx < 0 || qx >= lv.W || qy < 0 || qy >= lv.H) continue;
-    const int ridx = (by + 1) * Geo::RW + bx + 1;
-    float id[2];
-    cdp_pair_losses<false, Geo::RN, Geo::RW, Geo::P_TGT>(sm, Geo::P_SRC, ridx, p.alpha, id, nullptr);
-    sm[(Geo::P_ID + 0) * Geo::RN + ridx] = id[0];
-    sm[(Geo::P_ID + 1) * Geo::RN + ridx] = id[1];
-  }
-}
-
-// Phase B2: reprojection losses, tie-break noise, min / argmin (algos/depth.py:316-323),
-// per-thread loss sum over the tile proper, argmin map, and (with grad) the SSIM adjoint
-// coefficient fields of the winning reprojection.
-template <bool G>
-CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads,
-                               float* sm, float& loss_acc) {
-  typedef CdpTileGeom<G> Geo;
-  const CdpLevel& lv = p.lv[c.lvl];
-  const int W = lv.W, H = lv.H;
-  uint8_t* kplane = reinterpret_cast<uint8_t*>(sm + (size_t)Geo::NPLANES * Geo::RN);
-  for (int idx = tid; idx < Geo::BN; idx += nthreads) {
-    const int by = idx / Geo::BW, bx = idx - by * Geo::BW;
-    const int qx = c.x0 - Geo::HB + bx, qy = c.y0 - Geo::HB + by;
-    const int ridx = (by + 1) * Geo::RW + bx + 1;
-    if (qx < 0 || qx >= W || qy < 0 || qy >= H) {
-      if (G) kplane[ridx] = 255;
-      continue;
-    }
-    float pe[2];
-    float coef[2][9];
-    cdp_pair_losses<G, Geo::RN, Geo::RW, Geo::P_TGT>(sm, Geo::P_WARP, ridx, p.alpha, pe, coef);
-    float n0, n1;
-    if (lv.noise) {
-      const size_t plane = (size_t)W * H;
-      n0 = CDP_LDG(lv.noise + ((size_t)c.b * 2 + 0) * plane + qy * W + qx);
-      n1 = CDP_LDG(lv.noise + ((size_t)c.b * 2 + 1) * plane + qy * W + qx);
-    } else {
-      cdp_noise_pair(p.seed, (uint32_t)(qy * W + qx), (uint32_t)c.lvl, (uint32_t)c.b, n0, n1);
-    }
-    const float id0 = CDP_ADD(sm[(Geo::P_ID + 0) * Geo::RN + ridx], CDP_MUL(n0, CDP_NOISE_SCALE));
-    const float id1 = CDP_ADD(sm[(Geo::P_ID + 1) * Geo::RN + ridx], CDP_MUL(n1, CDP_NOISE_SCALE));
-    float best = pe[0];
-    int kb = 0;
-    if (pe[1] < best) { best = pe[1]; kb = 1; }
-    if (id0 < best) { best = id0; kb = 2; }
-    if (id1 < best) { best = id1; kb = 3; }
-    const bool in_tile = qx >= c.x0 && qx < c.x0 + CDP_TILE_X && qy >= c.y0 && qy < c.y0 + CDP_TILE_Y;
-    if (in_tile) {
-      loss_acc += best;
-      if (lv.argmin) lv.argmin[(size_t)c.b * W * H + qy * W + qx] = (uint8_t)kb;
-    }
-    if (G) {
-      kplane[ridx] = (uint8_t)kb;
-      if (kb < 2) {
-#pragma unroll
-        for (int j = 0; j < 9; ++j) sm[Geo::coef_plane(j) * Geo::RN + ridx] = kb == 0 ? coef[0][j] : coef[1][j];
-      }
-    }
-  }
-}
-
-// Phase C (with grad): gather the SSIM adjoint over the reflected 3x3 neighbourhood, add the L1
-// term, chain through the bilinear sampler and the projection to depth and pose.
-CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads,
-                              const float* sm, float* dT /*[32]*/) {
-  typedef CdpTileGeom<true> Geo;
-  const CdpLevel& lv = p.lv[c.lvl];
-  const int W = lv.W, H = lv.H;
-  const size_t plane = (size_t)W * H;
-  const CdpCam cam = cdp_tile_cam(p, c);
-  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-  const float* T[2] = {p.pose0 + (size_t)c.b * 16, p.pose1 + (size_t)c.b * 16};
-  const float* src[2] = {lv.src0 + (size_t)c.b * 3 * plane, lv.src1 + (size_t)c.b * 3 * plane};
-  const uint8_t* kplane = reinterpret_cast<const uint8_t*>(sm + (size_t)Geo::NPLANES * Geo::RN);
-  const float w_ssim = p.alpha / 27.0f;                       // alpha * (1/3 channels) * (1/9 window)
-  const float w_l1 = (float)(1.0 - (double)p.alpha) / 3.0f;
-  for (int idx = tid; idx < CDP_TILE_X * CDP_TILE_Y; idx += nthreads) {
-    const int ly = idx / CDP_TILE_X, lx = idx - ly * CDP_TILE_X;
-    const int px = c.x0 + lx, py = c.y0 + ly;
-    if (px >= W || py >= H) continue;
-    const int ridx = (ly + Geo::HALO) * Geo::RW + lx + Geo::HALO;
-    const int kown = kplane[ridx];
-    float gd = 0.f;
-    CdpPoint pt;
-    bool have_pt = false;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      float acc[3] = {0.f, 0.f, 0.f};  // sum over the window of m * (A0 + 2 (x_p - x_q) B + (y_p - y_q) C)
-      bool any = kown == k;
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const float my = cdp_reflect_mult(py, dy, H);
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          const float m = my * cdp_reflect_mult(px, dx, W);
-          const int n = ridx + dy * Geo::RW + dx;
-          if (m == 0.f || kplane[n] != k) continue;
-          any = true;
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            const float dxv = sm[(Geo::P_WARP + k * 3 + ch) * Geo::RN + ridx] - sm[(Geo::P_WARP + k * 3 + ch) * Geo::RN + n];
-            const float dyv = sm[(Geo::P_TGT + ch) * Geo::RN + ridx] - sm[(Geo::P_TGT + ch) * Geo::RN + n];
-            acc[ch] += m * (sm[Geo::coef_plane(ch * 3 + 0) * Geo::RN + n] +
-                            2.f * dxv * sm[Geo::coef_plane(ch * 3 + 1) * Geo::RN + n] +
-                            dyv * sm[Geo::coef_plane(ch * 3 + 2) * Geo::RN + n]);
-          }
-        }
-      }
-      if (!any) continue;
-      if (!have_pt) {
-        cdp_backproject((float)px, (float)py, CDP_LDG(lv.depth + (size_t)c.b * plane + py * W + px), cam, pt);
-        have_pt = true;
-      }
-      CdpProj pr;
-      cdp_project(pt.P, T[k], nullptr, cam, wm1, hm1, pr);
-      CdpTaps t;
-      cdp_taps(pr.ix, pr.iy, W, H, t);
-      float gix = 0.f, giy = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const float x = sm[(Geo::P_WARP + k * 3 + ch) * Geo::RN + ridx];
-        const float y = sm[(Geo::P_TGT + ch) * Geo::RN + ridx];
-        float gw = w_ssim * acc[ch];
-        if (kown == k) gw += w_l1 * (x > y ? 1.f : (x < y ? -1.f : 0.f));
-        gw *= lv.weight;
-        float dix, diy;
-        cdp_bilinear_grad(src[k] + ch * plane, t, dix, diy);
-        gix += gw * dix;
-        giy += gw * diy;
-      }
-      cdp_warp_adjoint(gix * t.mx, giy * t.my, pr, pt, T[k], cam, gd, dT + 16 * k, nullptr);
-    }
-    lv.gdepth[(size_t)c.b * plane + py * W + px] = gd;
-  }
-}
+#include "cdp_photo_tile.h"
 
 // ==========================================================================================
 // 3. Fixed-order reduction of the per-CTA partial records (one block).
@@ -453,10 +172,10 @@ CDP_HD float cdp_smooth_mean(const CdpSmoothParams& p, int b) {
 }
 
 CDP_HD float cdp_edge_weight(const float* img, size_t plane, int a, int bidx) {
-  const float s = CDP_ADD(CDP_ADD(fabsf(CDP_LDG(img + a) - CDP_LDG(img + bidx)),
-                                  fabsf(CDP_LDG(img + plane + a) - CDP_LDG(img + plane + bidx))),
-                          fabsf(CDP_LDG(img + 2 * plane + a) - CDP_LDG(img + 2 * plane + bidx)));
-  return expf(-(s / 3.0f));
+  const float s = fabsf(CDP_LDG(img + a) - CDP_LDG(img + bidx)) +
+                  fabsf(CDP_LDG(img + plane + a) - CDP_LDG(img + plane + bidx)) +
+                  fabsf(CDP_LDG(img + 2 * plane + a) - CDP_LDG(img + 2 * plane + bidx));
+  return cdp_exp(-(s * (1.0f / 3.0f)));
 }
 
 CDP_HD float cdp_sign(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
@@ -471,33 +190,33 @@ CDP_HD void cdp_smooth_main_thread(const CdpSmoothParams& p, int b, int blk, int
   const size_t plane = (size_t)H * W;
   const float* d = p.disp + (size_t)b * plane;
   const float* img = p.image + (size_t)b * 3 * plane;
-  const float den = CDP_ADD(mean, 1e-7f);
+  const float iden = 1.0f / (mean + 1e-7f);
   const float cx = 1.0f / ((float)p.B * (float)H * (float)(W - 1));
   const float cy = 1.0f / ((float)p.B * (float)(H - 1) * (float)W);
   for (int i = lo + tid; i < hi; i += nthreads) {
     const int y = i / W, x = i - y * W;
     const float raw = CDP_LDG(d + i);
-    const float dc = raw / den;
+    const float dc = raw * iden;
     float g = 0.f;
     if (x < W - 1) {
-      const float diff = CDP_SUB(dc, CDP_LDG(d + i + 1) / den);
+      const float diff = dc - CDP_LDG(d + i + 1) * iden;
       const float e = cdp_edge_weight(img, plane, i, i + 1);
-      acc[0] += CDP_MUL(fabsf(diff), e);
+      acc[0] += fabsf(diff) * e;
       g += cdp_sign(diff) * e * cx;
     }
     if (y < H - 1) {
-      const float diff = CDP_SUB(dc, CDP_LDG(d + i + W) / den);
+      const float diff = dc - CDP_LDG(d + i + W) * iden;
       const float e = cdp_edge_weight(img, plane, i, i + W);
-      acc[1] += CDP_MUL(fabsf(diff), e);
+      acc[1] += fabsf(diff) * e;
       g += cdp_sign(diff) * e * cy;
     }
     if (p.with_grad) {
       if (x > 0) {
-        const float diff = CDP_SUB(CDP_LDG(d + i - 1) / den, dc);
+        const float diff = CDP_LDG(d + i - 1) * iden - dc;
         g -= cdp_sign(diff) * cdp_edge_weight(img, plane, i - 1, i) * cx;
       }
       if (y > 0) {
-        const float diff = CDP_SUB(CDP_LDG(d + i - W) / den, dc);
+        const float diff = CDP_LDG(d + i - W) * iden - dc;
         g -= cdp_sign(diff) * cdp_edge_weight(img, plane, i - W, i) * cy;
       }
       p.g[(size_t)b * plane + i] = g;
@@ -516,7 +235,7 @@ CDP_HD void cdp_smooth_finalize(const CdpSmoothParams& p) {
       sx += (double)rec[0]; sy += (double)rec[1]; gd += (double)rec[2];
     }
     if (p.with_grad) {
-      const float den = CDP_ADD(cdp_smooth_mean(p, b), 1e-7f);
+      const float den = cdp_smooth_mean(p, b) + 1e-7f;
       const double a = 1.0 / (double)den;
       p.scal[b * 2 + 0] = (float)a;
       p.scal[b * 2 + 1] = (float)(gd * a * a / (double)((size_t)p.H * p.W));
@@ -549,41 +268,40 @@ struct CdpWarpParams {
   int32_t batch_begin, C, H, W, mode;
 };
 
-CDP_HD void cdp_warp_setup(const CdpWarpParams& p, int b_local, int pix, CdpPoint& pt, CdpProj& pr,
-                           CdpCam& cam) {
+CDP_HD void cdp_warp_setup(const CdpWarpParams& p, int b_local, int pix, CdpWarp& w, CdpCam& cam, CdpPose& T) {
   const int b = p.batch_begin + b_local;
   const size_t plane = (size_t)p.H * p.W;
   const int y = pix / p.W, x = pix - y * p.W;
-  cam.fx = p.K[b_local][0]; cam.fy = p.K[b_local][1]; cam.cx = p.K[b_local][2]; cam.cy = p.K[b_local][3];
-  cdp_backproject((float)x, (float)y, CDP_LDG(p.depth + (size_t)b * plane + pix), cam, pt);
+  cam = cdp_make_cam(p.K[b_local][0], p.K[b_local][1], p.K[b_local][2], p.K[b_local][3]);
+  cdp_load_pose(p.pose + (size_t)b * 16, T);
   float mo[3];
   if (p.motion) {
     for (int c = 0; c < 3; ++c) mo[c] = CDP_LDG(p.motion + ((size_t)b * 3 + c) * plane + pix);
   }
-  cdp_project(pt.P, p.pose + (size_t)b * 16, p.motion ? mo : nullptr, cam, (float)(p.W - 1),
-              (float)(p.H - 1), pr);
+  cdp_warp_point((float)x, (float)y, CDP_LDG(p.depth + (size_t)b * plane + pix), cam, T, p.motion ? mo : nullptr, w);
 }
 
 CDP_HD void cdp_warp_grid_pixel(const CdpWarpParams& p, int b_local, int pix) {
-  CdpPoint pt; CdpProj pr; CdpCam cam;
-  cdp_warp_setup(p, b_local, pix, pt, pr, cam);
+  CdpWarp w; CdpCam cam; CdpPose T;
+  cdp_warp_setup(p, b_local, pix, w, cam, T);
   const size_t o = (((size_t)(p.batch_begin + b_local)) * p.H * p.W + pix) * 2;
-  p.out[o] = pr.gx;
-  p.out[o + 1] = pr.gy;
+  // normalisation of _PointcloudToImage (misc/image_warper.py:44-45)
+  p.out[o] = (w.ix / (float)(p.W - 1) - 0.5f) * 2.0f;
+  p.out[o + 1] = (w.iy / (float)(p.H - 1) - 0.5f) * 2.0f;
 }
 
 CDP_HD void cdp_warp_image_pixel(const CdpWarpParams& p, int b_local, int pix) {
-  CdpPoint pt; CdpProj pr; CdpCam cam;
-  cdp_warp_setup(p, b_local, pix, pt, pr, cam);
+  CdpWarp w; CdpCam cam; CdpPose T;
+  cdp_warp_setup(p, b_local, pix, w, cam, T);
   const int b = p.batch_begin + b_local;
   const size_t plane = (size_t)p.H * p.W;
   if (p.mode == 0) {
     CdpTaps t;
-    cdp_taps(pr.ix, pr.iy, p.W, p.H, t);
+    cdp_taps(pix % p.W, pix / p.W, w, p.W, p.H, t);
     for (int c = 0; c < p.C; ++c)
       p.out[((size_t)b * p.C + c) * plane + pix] = cdp_bilinear(p.src + ((size_t)b * p.C + c) * plane, t);
   } else {
-    const int o = cdp_nearest_index(pr.ix, pr.iy, p.W, p.H);
+    const int o = cdp_nearest_index(w.ix, w.iy, p.W, p.H);
     for (int c = 0; c < p.C; ++c)
       p.out[((size_t)b * p.C + c) * plane + pix] = CDP_LDG(p.src + ((size_t)b * p.C + c) * plane + o);
   }
@@ -591,12 +309,12 @@ CDP_HD void cdp_warp_image_pixel(const CdpWarpParams& p, int b_local, int pix) {
 
 // backward of the bilinear warp for one pixel; accumulates this thread's dT[16]
 CDP_HD void cdp_warp_bwd_pixel(const CdpWarpParams& p, int b_local, int pix, float* dT) {
-  CdpPoint pt; CdpProj pr; CdpCam cam;
-  cdp_warp_setup(p, b_local, pix, pt, pr, cam);
+  CdpWarp w; CdpCam cam; CdpPose T;
+  cdp_warp_setup(p, b_local, pix, w, cam, T);
   const int b = p.batch_begin + b_local;
   const size_t plane = (size_t)p.H * p.W;
   CdpTaps t;
-  cdp_taps(pr.ix, pr.iy, p.W, p.H, t);
+  cdp_taps(pix % p.W, pix / p.W, w, p.W, p.H, t);
   float gix = 0.f, giy = 0.f;
   for (int c = 0; c < p.C; ++c) {
     float dix, diy;
@@ -606,34 +324,35 @@ CDP_HD void cdp_warp_bwd_pixel(const CdpWarpParams& p, int b_local, int pix, flo
     giy += go * diy;
   }
   float gd = 0.f, gm[3];
-  cdp_warp_adjoint(gix * t.mx, giy * t.my, pr, pt, p.pose + (size_t)b * 16, cam, gd, dT,
-                   p.grad_motion ? gm : nullptr);
+  cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dT, p.grad_motion ? gm : nullptr);
   p.grad_depth[(size_t)b * plane + pix] = gd;
   if (p.grad_motion)
     for (int c = 0; c < 3; ++c) p.grad_motion[((size_t)b * 3 + c) * plane + pix] = gm[c];
 }
 
-// SSIM map for one pixel of one plane (reflect-padded 3x3 statistics straight from global memory)
+// SSIM statistics for one pixel of one plane straight from global memory: reflect-padded 3x3
+// window, values centred on the target value at the window centre (returned in c).
 CDP_HD void cdp_ssim_stats_global(const float* x, const float* y, int W, int H, int px, int py,
-                                  float& mx, float& my, float& exx, float& eyy, float& exy) {
+                                  float& mxc, float& myc, float& exx, float& eyy, float& exy, float& c) {
+  c = CDP_LDG(y + py * W + px);
   float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
   for (int dy = -1; dy <= 1; ++dy)
     for (int dx = -1; dx <= 1; ++dx) {
       const int o = cdp_reflect(py + dy, H) * W + cdp_reflect(px + dx, W);
-      const float a = CDP_LDG(x + o), b = CDP_LDG(y + o);
-      sx = CDP_ADD(sx, a); sy = CDP_ADD(sy, b);
-      sxx = CDP_ADD(sxx, CDP_MUL(a, a)); syy = CDP_ADD(syy, CDP_MUL(b, b)); sxy = CDP_ADD(sxy, CDP_MUL(a, b));
+      const float a = CDP_LDG(x + o) - c, b = CDP_LDG(y + o) - c;
+      sx += a; sy += b; sxx += a * a; syy += b * b; sxy += a * b;
     }
-  mx = sx / 9.0f; my = sy / 9.0f; exx = sxx / 9.0f; eyy = syy / 9.0f; exy = sxy / 9.0f;
+  const float ninth = 1.0f / 9.0f;
+  mxc = sx * ninth; myc = sy * ninth; exx = sxx * ninth; eyy = syy * ninth; exy = sxy * ninth;
 }
 
 CDP_HD void cdp_ssim_fwd_pixel(const float* x, const float* y, int W, int H, int plane_idx, int pix,
                                float* out) {
   const size_t base = (size_t)plane_idx * W * H;
-  float mx, my, exx, eyy, exy;
-  cdp_ssim_stats_global(x + base, y + base, W, H, pix % W, pix / W, mx, my, exx, eyy, exy);
+  float mxc, myc, exx, eyy, exy, c;
+  cdp_ssim_stats_global(x + base, y + base, W, H, pix % W, pix / W, mxc, myc, exx, eyy, exy, c);
   CdpSsimTerms t;
-  cdp_ssim_terms(mx, my, exx, eyy, exy, t);
+  cdp_ssim_terms(mxc, myc, exx, eyy, exy, c, t);
   out[base + pix] = t.loss;
 }
 
@@ -642,14 +361,16 @@ CDP_HD void cdp_ssim_fwd_pixel(const float* x, const float* y, int W, int H, int
 CDP_HD void cdp_ssim_bwd_coef_pixel(const float* grad_out, const float* x, const float* y, int W,
                                     int H, int plane_idx, int pix, float* scratch, size_t total) {
   const size_t base = (size_t)plane_idx * W * H;
-  float mx, my, exx, eyy, exy;
-  cdp_ssim_stats_global(x + base, y + base, W, H, pix % W, pix / W, mx, my, exx, eyy, exy);
+  float mxc, myc, exx, eyy, exy, c;
+  cdp_ssim_stats_global(x + base, y + base, W, H, pix % W, pix / W, mxc, myc, exx, eyy, exy, c);
   CdpSsimTerms t;
-  cdp_ssim_terms(mx, my, exx, eyy, exy, t);
-  const float xq = CDP_LDG(x + base + pix), yq = CDP_LDG(y + base + pix);
+  cdp_ssim_terms(mxc, myc, exx, eyy, exy, c, t);
+  const float dxq = (CDP_LDG(x + base + pix) - c) - mxc, dyq = (CDP_LDG(y + base + pix) - c) - myc;
   float Ax, Bx, C, Ay, By;
-  cdp_ssim_coeffs(mx, my, xq, yq, t, Ax, Bx, C);
-  cdp_ssim_coeffs(my, mx, yq, xq, t, Ay, By, C);  // SSIM is symmetric in (x, y)
+  cdp_ssim_coeffs(t, dxq, dyq, Ax, Bx, C);
+  CdpSsimTerms ts = t;  // SSIM is symmetric in (x, y): swap the roles for d/dy
+  ts.mx = t.my; ts.my = t.mx;
+  cdp_ssim_coeffs(ts, dyq, dxq, Ay, By, C);
   const float go = CDP_LDG(grad_out + base + pix);
   scratch[0 * total + base + pix] = go * Ax;
   scratch[1 * total + base + pix] = go * Ay;
@@ -675,6 +396,6 @@ CDP_HD void cdp_ssim_bwd_gather_pixel(const float* x, const float* y, int W, int
       gx += m * (scratch[0 * total + o] + 2.f * ddx * b + ddy * c);
       gy += m * (scratch[1 * total + o] + 2.f * ddy * b + ddx * c);
     }
-  if (grad_x) grad_x[base + pix] = gx / 9.0f;
-  if (grad_y) grad_y[base + pix] = gy / 9.0f;
+  if (grad_x) grad_x[base + pix] = gx * (1.0f / 9.0f);
+  if (grad_y) grad_y[base + pix] = gy * (1.0f / 9.0f);
 }

@@ -8,60 +8,129 @@
 #include "cdp_common.h"
 
 // ------------------------------------------------------------------------------------------
-// Back-projection: CameraModel.get_viewing_ray (misc/camera_model.py:52-71) followed by
-// _ImageToPointcloud.forward (misc/image_warper.py:83-85).
+// Fast scalar helpers.  The kernels do not try to reproduce the reference's fp32 rounding
+// operation by operation (two fp32 evaluations of this loss differ by ~1e-4 of max-abs in the
+// gradients anyway, see tests/helpers.py); instead every quantity is computed in the
+// best-conditioned form available, so that results sit closer to the fp64 evaluation of the
+// reference than the reference's own fp32 run does.
 // ------------------------------------------------------------------------------------------
-struct CdpPoint {
-  float P[3];     // 3-D point
-  float dPdD[3];  // dP / d depth  (= unit ray / |ray_z|)
-};
+CDP_HD float cdp_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
+CDP_HD float cdp_fdiv(float a, float b) {  // a / b to ~2 ulp
+#if defined(__CUDA_ARCH__)
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+CDP_HD float cdp_exp(float x) {
+#if defined(__CUDA_ARCH__)
+  return __expf(x);
+#else
+  return expf(x);
+#endif
+}
 
-CDP_HD void cdp_backproject(float u, float v, float depth, const CdpCam& k, CdpPoint& o) {
-  const float rx = (u - k.cx) / k.fx;
-  const float ry = (v - k.cy) / k.fy;
-  const float nrm = sqrtf(CDP_ADD(CDP_ADD(CDP_MUL(rx, rx), CDP_MUL(ry, ry)), 1.0f));
-  const float hx = rx / nrm, hy = ry / nrm, hz = 1.0f / nrm;
-  const float az = fabsf(hz);
-  const float a = depth / az;
-  o.P[0] = CDP_MUL(a, hx);
-  o.P[1] = CDP_MUL(a, hy);
-  o.P[2] = CDP_MUL(a, hz);
-  o.dPdD[0] = hx / az;
-  o.dPdD[1] = hy / az;
-  o.dPdD[2] = hz / az;
+// Packed fp32 pairs: on sm_100a these are single FADD2 / FMUL2 / FFMA2 instructions working on
+// an aligned register pair (two pixels' or two candidates' worth of math per issue slot).
+CDP_HD float2 cdp_set2(float v) { float2 r; r.x = v; r.y = v; return r; }
+CDP_HD float2 cdp_add2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd2_rn(a, b);
+#else
+  float2 r; r.x = a.x + b.x; r.y = a.y + b.y; return r;
+#endif
+}
+CDP_HD float2 cdp_mul2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul2_rn(a, b);
+#else
+  float2 r; r.x = a.x * b.x; r.y = a.y * b.y; return r;
+#endif
+}
+CDP_HD float2 cdp_fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+  return __ffma2_rn(a, b, c);
+#else
+  float2 r; r.x = a.x * b.x + c.x; r.y = a.y * b.y + c.y; return r;
+#endif
+}
+
+CDP_HD CdpCam cdp_make_cam(float fx, float fy, float cx, float cy) {
+  CdpCam k;
+  k.fx = fx; k.fy = fy; k.cx = cx; k.cy = cy;
+  k.ifx = 1.0f / fx; k.ify = 1.0f / fy;
+  return k;
+}
+
+// Pose in the form the warp uses: row-major 4x4 with the identity removed from the rotation
+// diagonal (D = T - diag(1,1,1,0)), so that small motions keep full relative precision.
+struct CdpPose {
+  float d[16];
+};
+CDP_HD void cdp_load_pose(const float* T, CdpPose& o) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o.d[i] = CDP_LDG(T + i);
+  o.d[0] -= 1.0f; o.d[5] -= 1.0f; o.d[10] -= 1.0f;
 }
 
 // ------------------------------------------------------------------------------------------
-// CoordinateWarper.forward after the point cloud (misc/image_warper.py:125-144) and
-// _PointcloudToImage / CameraModel.get_image_point (misc/image_warper.py:29-45,
-// misc/camera_model.py:43-50), then grid_sample's un-normalisation (align_corners=True).
+// Warp of one pixel: CameraModel.get_viewing_ray + _ImageToPointcloud (misc/camera_model.py:52-71,
+// misc/image_warper.py:68-87), CoordinateWarper (misc/image_warper.py:100-144),
+// _PointcloudToImage / get_image_point (misc/image_warper.py:20-51, misc/camera_model.py:43-50)
+// and grid_sample's un-normalisation.
+//
+// The reference normalises the viewing ray and rescales it by depth/|ray_z|, which is D*(rx,ry,1)
+// with rx = (u-cx)/fx; it then forms absolute pixel coordinates u' = fx*E_x/z + cx and pushes them
+// through normalise / un-normalise, all in fp32, which leaves ~1e-4 px of rounding at u ~ 1000.
+// Here the sample position is computed as a displacement from the pixel itself:
+//     Q = P + a,  a = (T - I) P + t (+ motion),     u' - u = fx * (a_x - rx * a_z) / Q_z
+// (Q_w cancels whenever the depth clamp max(E_z, 1e-5) is inactive), which is exact to ~1e-7 of
+// the displacement.  The clamped / degenerate case falls back to the literal formula.
 // ------------------------------------------------------------------------------------------
-struct CdpProj {
-  float Q[4];    // T * [P;1] (+ motion on xyz)
-  float E[3];    // Q_xyz / Q_w
-  float zt;      // max(E_z, 1e-5)
-  float gx, gy;  // normalised grid coordinates (what CoordinateWarper returns)
-  float ix, iy;  // un-normalised, un-clipped sample position in source pixels
+struct CdpWarp {
+  float rx, ry;        // viewing ray (x/z, y/z)
+  float P[3];          // back-projected point
+  float Q[4];          // transformed homogeneous point
+  float iz;            // 1 / Q_z (regular) or 1 / zt (clamped)
+  float ix, iy;        // absolute sample position in source pixels (un-clipped)
+  float dx, dy;        // ix - u, iy - v at full relative precision (regular case)
+  bool regular;        // depth clamp inactive and Q_w != 0
 };
 
-CDP_HD void cdp_project(const float P[3], const float* T, const float* motion3, const CdpCam& k,
-                        float wm1, float hm1, CdpProj& o) {
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-    o.Q[r] = T[4 * r + 0] * P[0] + T[4 * r + 1] * P[1] + T[4 * r + 2] * P[2] + T[4 * r + 3];
-  if (motion3) {
-    o.Q[0] += motion3[0]; o.Q[1] += motion3[1]; o.Q[2] += motion3[2];
+CDP_HD void cdp_warp_point(float u, float v, float depth, const CdpCam& k, const CdpPose& T,
+                           const float* motion3, CdpWarp& o) {
+  o.rx = (u - k.cx) * k.ifx;
+  o.ry = (v - k.cy) * k.ify;
+  o.P[0] = depth * o.rx; o.P[1] = depth * o.ry; o.P[2] = depth;
+  float ax = T.d[0] * o.P[0] + T.d[1] * o.P[1] + T.d[2] * o.P[2] + T.d[3];
+  float ay = T.d[4] * o.P[0] + T.d[5] * o.P[1] + T.d[6] * o.P[2] + T.d[7];
+  float az = T.d[8] * o.P[0] + T.d[9] * o.P[1] + T.d[10] * o.P[2] + T.d[11];
+  if (motion3) { ax += motion3[0]; ay += motion3[1]; az += motion3[2]; }
+  o.Q[3] = T.d[12] * o.P[0] + T.d[13] * o.P[1] + T.d[14] * o.P[2] + T.d[15];
+  o.Q[0] = o.P[0] + ax; o.Q[1] = o.P[1] + ay; o.Q[2] = o.P[2] + az;
+  // E_z = Q_z / Q_w >= 1e-5 without dividing
+  o.regular = o.Q[3] > 0.f ? (o.Q[2] >= CDP_Z_MIN * o.Q[3]) : (o.Q[3] < 0.f && o.Q[2] <= CDP_Z_MIN * o.Q[3]);
+  if (o.regular) {
+    o.iz = cdp_rcp(o.Q[2]);
+    o.dx = k.fx * (ax - o.rx * az) * o.iz;
+    o.dy = k.fy * (ay - o.ry * az) * o.iz;
+    o.ix = u + o.dx;
+    o.iy = v + o.dy;
+  } else {  // literal reference formula: E = Q_xyz / Q_w, z = max(E_z, 1e-5)
+    const float ex = o.Q[0] / o.Q[3], ey = o.Q[1] / o.Q[3], ez = o.Q[2] / o.Q[3];
+    const float zt = fmaxf(ez, CDP_Z_MIN);
+    o.iz = 1.0f / zt;
+    o.ix = ex * o.iz * k.fx + k.cx;
+    o.iy = ey * o.iz * k.fy + k.cy;
+    o.dx = o.ix - u;
+    o.dy = o.iy - v;
   }
-  o.E[0] = o.Q[0] / o.Q[3];
-  o.E[1] = o.Q[1] / o.Q[3];
-  o.E[2] = o.Q[2] / o.Q[3];
-  o.zt = fmaxf(o.E[2], CDP_Z_MIN);
-  const float u2 = CDP_ADD(CDP_MUL(o.E[0] / o.zt, k.fx), k.cx);
-  const float v2 = CDP_ADD(CDP_MUL(o.E[1] / o.zt, k.fy), k.cy);
-  o.gx = CDP_MUL(CDP_SUB(u2 / wm1, 0.5f), 2.0f);
-  o.gy = CDP_MUL(CDP_SUB(v2 / hm1, 0.5f), 2.0f);
-  o.ix = CDP_MUL(CDP_MUL(CDP_ADD(o.gx, 1.0f), 0.5f), wm1);
-  o.iy = CDP_MUL(CDP_MUL(CDP_ADD(o.gy, 1.0f), 0.5f), hm1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -74,39 +143,43 @@ struct CdpTaps {
   float mx, my;                // 1 where the coordinate gradient passes the border clip
 };
 
-CDP_HD void cdp_taps(float ix, float iy, int W, int H, CdpTaps& t) {
-  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-  t.mx = (ix > 0.f && ix < wm1) ? 1.f : 0.f;  // clip_coordinates_set_grad
-  t.my = (iy > 0.f && iy < hm1) ? 1.f : 0.f;
-  const float cx = fminf(fmaxf(ix, 0.f), wm1);
-  const float cy = fminf(fmaxf(iy, 0.f), hm1);
-  const float fx0 = floorf(cx), fy0 = floorf(cy);
-  t.wx1 = cx - fx0; t.wx0 = (fx0 + 1.f) - cx;
-  t.wy1 = cy - fy0; t.wy0 = (fy0 + 1.f) - cy;
-  int x0 = (int)fx0, y0 = (int)fy0;
-  // NaN / garbage coordinates must never index out of the plane
-  x0 = x0 < 0 ? 0 : (x0 > W - 1 ? W - 1 : x0);
-  y0 = y0 < 0 ? 0 : (y0 > H - 1 ? H - 1 : y0);
-  // a tap one past the border has weight exactly 0: clamp its index instead of branching
-  const int x1 = x0 + 1 > W - 1 ? W - 1 : x0 + 1;
-  const int y1 = y0 + 1 > H - 1 ? H - 1 : y0 + 1;
+// one axis: integer pixel index p, displacement d (= i - p), absolute position i, extent n
+CDP_HD void cdp_tap_axis(int p, float d, float i, int n, int& i0, int& i1, float& w0, float& w1, float& m) {
+  const float nm1 = (float)(n - 1);
+  float frac;
+  if (!(i > 0.f)) { i0 = 0; frac = 0.f; m = 0.f; }            // clip_coordinates_set_grad; NaN lands here
+  else if (i >= nm1) { i0 = n - 1; frac = 0.f; m = 0.f; }
+  else {
+    const float fl = floorf(d);
+    i0 = p + (int)fl; frac = d - fl; m = 1.f;
+  }
+  i0 = i0 < 0 ? 0 : (i0 > n - 1 ? n - 1 : i0);
+  i1 = i0 + 1 > n - 1 ? n - 1 : i0 + 1;  // a tap one past the border has weight exactly 0
+  w1 = frac; w0 = 1.0f - frac;
+}
+
+CDP_HD void cdp_taps(int u, int v, const CdpWarp& w, int W, int H, CdpTaps& t) {
+  int x0, x1, y0, y1;
+  cdp_tap_axis(u, w.dx, w.ix, W, x0, x1, t.wx0, t.wx1, t.mx);
+  cdp_tap_axis(v, w.dy, w.iy, H, y0, y1, t.wy0, t.wy1, t.my);
   t.o00 = y0 * W + x0; t.o01 = y0 * W + x1; t.o10 = y1 * W + x0; t.o11 = y1 * W + x1;
 }
 
 CDP_HD float cdp_bilinear(const float* plane, const CdpTaps& t) {
   const float nw = CDP_LDG(plane + t.o00), ne = CDP_LDG(plane + t.o01);
   const float sw = CDP_LDG(plane + t.o10), se = CDP_LDG(plane + t.o11);
-  return CDP_ADD(CDP_ADD(CDP_ADD(CDP_MUL(nw, CDP_MUL(t.wx0, t.wy0)), CDP_MUL(ne, CDP_MUL(t.wx1, t.wy0))),
-                         CDP_MUL(sw, CDP_MUL(t.wx0, t.wy1))),
-                 CDP_MUL(se, CDP_MUL(t.wx1, t.wy1)));
+  const float top = nw + t.wx1 * (ne - nw), bot = sw + t.wx1 * (se - sw);
+  return top + t.wy1 * (bot - top);
 }
 
-// d(sample)/d(ix), d(sample)/d(iy) for one channel (grid_sampler_2d_backward w.r.t. the grid).
-CDP_HD void cdp_bilinear_grad(const float* plane, const CdpTaps& t, float& dix, float& diy) {
+// value and d(sample)/d(ix), d(sample)/d(iy) for one channel
+CDP_HD float cdp_bilinear_grad(const float* plane, const CdpTaps& t, float& dix, float& diy) {
   const float nw = CDP_LDG(plane + t.o00), ne = CDP_LDG(plane + t.o01);
   const float sw = CDP_LDG(plane + t.o10), se = CDP_LDG(plane + t.o11);
   dix = (ne - nw) * t.wy0 + (se - sw) * t.wy1;
   diy = (sw - nw) * t.wx0 + (se - ne) * t.wx1;
+  const float top = nw + t.wx1 * (ne - nw), bot = sw + t.wx1 * (se - sw);
+  return top + t.wy1 * (bot - top);
 }
 
 CDP_HD int cdp_nearest_index(float ix, float iy, int W, int H) {
@@ -119,56 +192,67 @@ CDP_HD int cdp_nearest_index(float ix, float iy, int W, int H) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Chain dL/d(ix,iy) back to depth, pose (and motion): adjoint of cdp_project / cdp_backproject.
-// gu, gv already include the border-clip mask.
+// Chain dL/d(ix,iy) back to depth, pose (and motion).  gu, gv already include the clip mask.
+// T here is the TRUE pose matrix minus diag(1,1,1,0) (CdpPose).
 // ------------------------------------------------------------------------------------------
-CDP_HD void cdp_warp_adjoint(float gu, float gv, const CdpProj& pr, const CdpPoint& pt,
-                             const float* T, const CdpCam& k, float& g_depth, float* dT,
-                             float* g_motion3) {
-  const float izt = 1.0f / pr.zt;
-  const float ax = gu * k.fx, ay = gv * k.fy;
-  const float gEx = ax * izt, gEy = ay * izt;
-  const float gzt = -(ax * pr.E[0] + ay * pr.E[1]) * izt * izt;
-  const float gEz = (pr.E[2] >= CDP_Z_MIN) ? gzt : 0.f;  // clamp(min=) passes gradient on >=
-  const float iw = 1.0f / pr.Q[3];
+CDP_HD void cdp_warp_adjoint(float gu, float gv, const CdpWarp& w, const CdpCam& k, const CdpPose& T,
+                             float& g_depth, float* dT, float* g_motion3) {
   float gQ[4];
-  gQ[0] = gEx * iw; gQ[1] = gEy * iw; gQ[2] = gEz * iw;
-  gQ[3] = -(gEx * pr.Q[0] + gEy * pr.Q[1] + gEz * pr.Q[2]) * iw * iw;
+  const float ax = gu * k.fx, ay = gv * k.fy;
+  if (w.regular) {  // u' = fx Q_x / Q_z + cx: Q_w drops out
+    gQ[0] = ax * w.iz;
+    gQ[1] = ay * w.iz;
+    gQ[2] = -(gQ[0] * w.Q[0] + gQ[1] * w.Q[1]) * w.iz;
+    gQ[3] = 0.f;
+  } else {  // E = Q/Q_w, zt = max(E_z, eps) = eps or E_z
+    const float iw = 1.0f / w.Q[3];
+    const float ex = w.Q[0] * iw, ey = w.Q[1] * iw, ez = w.Q[2] * iw;
+    const float gEx = ax * w.iz, gEy = ay * w.iz;
+    const float gzt = -(ax * ex + ay * ey) * w.iz * w.iz;
+    const float gEz = (ez >= CDP_Z_MIN) ? gzt : 0.f;  // clamp(min=) passes gradient on >=
+    gQ[0] = gEx * iw; gQ[1] = gEy * iw; gQ[2] = gEz * iw;
+    gQ[3] = -(gEx * w.Q[0] + gEy * w.Q[1] + gEz * w.Q[2]) * iw * iw;
+  }
   if (g_motion3) { g_motion3[0] = gQ[0]; g_motion3[1] = gQ[1]; g_motion3[2] = gQ[2]; }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    dT[4 * r + 0] += gQ[r] * pt.P[0];
-    dT[4 * r + 1] += gQ[r] * pt.P[1];
-    dT[4 * r + 2] += gQ[r] * pt.P[2];
+    dT[4 * r + 0] += gQ[r] * w.P[0];
+    dT[4 * r + 1] += gQ[r] * w.P[1];
+    dT[4 * r + 2] += gQ[r] * w.P[2];
     dT[4 * r + 3] += gQ[r];
   }
-  float gd = 0.f;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float gP = T[c] * gQ[0] + T[4 + c] * gQ[1] + T[8 + c] * gQ[2] + T[12 + c] * gQ[3];
-    gd += gP * pt.dPdD[c];
-  }
-  g_depth += gd;
+  // gP = T^T gQ with T = D + diag(1,1,1,0);  dP/d depth = (rx, ry, 1)
+  const float gPx = gQ[0] + T.d[0] * gQ[0] + T.d[4] * gQ[1] + T.d[8] * gQ[2] + T.d[12] * gQ[3];
+  const float gPy = gQ[1] + T.d[1] * gQ[0] + T.d[5] * gQ[1] + T.d[9] * gQ[2] + T.d[13] * gQ[3];
+  const float gPz = gQ[2] + T.d[2] * gQ[0] + T.d[6] * gQ[1] + T.d[10] * gQ[2] + T.d[14] * gQ[3];
+  g_depth += gPx * w.rx + gPy * w.ry + gPz;
 }
 
 // ------------------------------------------------------------------------------------------
-// SSIMLoss (algos/depth.py:141-153) from the five window means.
+// SSIMLoss (algos/depth.py:141-153) from window statistics of values CENTRED on a constant c
+// (variances and the covariance are shift invariant; only the means need c added back).
+// Centring removes most of the cancellation in E[x^2] - mean^2 that costs the fp32 reference
+// about three digits in smooth image regions.
 // ------------------------------------------------------------------------------------------
 struct CdpSsimTerms {
-  float n1, n2, d1, d2, S;
+  float mx, my;  // true means
+  float n1, n2, id1, id2, S;
   float loss;  // clamp((1 - S) / 2, 0, 1)
   float dl;    // d loss / d S: -0.5 inside the clamp, else 0
 };
 
-CDP_HD void cdp_ssim_terms(float mx, float my, float exx, float eyy, float exy, CdpSsimTerms& o) {
-  const float mxy = CDP_MUL(mx, my), mxx = CDP_MUL(mx, mx), myy = CDP_MUL(my, my);
-  const float vx = CDP_SUB(exx, mxx), vy = CDP_SUB(eyy, myy), cov = CDP_SUB(exy, mxy);
-  o.n1 = CDP_ADD(CDP_MUL(2.0f, mxy), CDP_SSIM_C1);
-  o.n2 = CDP_ADD(CDP_MUL(2.0f, cov), CDP_SSIM_C2);
-  o.d1 = CDP_ADD(CDP_ADD(mxx, myy), CDP_SSIM_C1);
-  o.d2 = CDP_ADD(CDP_ADD(vx, vy), CDP_SSIM_C2);
-  o.S = CDP_MUL(o.n1, o.n2) / CDP_MUL(o.d1, o.d2);
-  const float raw = CDP_MUL(CDP_SUB(1.0f, o.S), 0.5f);
+// mxc, myc: means of the centred values; exx, eyy, exy: second moments of the centred values
+CDP_HD void cdp_ssim_terms(float mxc, float myc, float exx, float eyy, float exy, float c, CdpSsimTerms& o) {
+  o.mx = mxc + c; o.my = myc + c;
+  const float vx = exx - mxc * mxc, vy = eyy - myc * myc, cov = exy - mxc * myc;
+  o.n1 = 2.0f * o.mx * o.my + CDP_SSIM_C1;
+  o.n2 = 2.0f * cov + CDP_SSIM_C2;
+  const float d1 = o.mx * o.mx + o.my * o.my + CDP_SSIM_C1;
+  const float d2 = vx + vy + CDP_SSIM_C2;
+  o.id1 = cdp_rcp(d1);
+  o.id2 = cdp_rcp(d2);
+  o.S = (o.n1 * o.id1) * (o.n2 * o.id2);
+  const float raw = (1.0f - o.S) * 0.5f;
   o.loss = fminf(fmaxf(raw, 0.f), 1.f);
   o.dl = (raw >= 0.f && raw <= 1.f) ? -0.5f : 0.f;  // clamp gradient is inclusive
 }
@@ -176,19 +260,27 @@ CDP_HD void cdp_ssim_terms(float mx, float my, float exx, float eyy, float exy, 
 // SSIM adjoint coefficients.  With A = dl/dmean_x, B = dl/dE[x^2], C = dl/dE[xy] the gradient of
 // the loss at window centre q w.r.t. a window pixel p is
 //     d loss(q) / d x(p) = m(p,q)/9 * (A + 2 x(p) B + y(p) C).
-// A, 2xB and yC are each O(1/d2) and cancel almost completely, so in fp32 that form loses ~3
-// digits.  Substituting A = A1 - 2 mean_x B - mean_y C with
-//     A1 = dl * (2 mean_y n2 / (d1 d2) - 2 mean_x S / d1)          (no large terms)
-// gives the centred, well-conditioned form used by the kernels:
+// A, 2xB and yC are each O(1/d2) and cancel almost completely.  Substituting
+// A = A1 - 2 mean_x B - mean_y C with A1 = dl * (2 mean_y n2 / (d1 d2) - 2 mean_x S / d1) gives
+// the centred, well-conditioned form used by the kernels:
 //     d loss(q) / d x(p) = m/9 * (A0 + 2 (x(p) - x(q)) B + (y(p) - y(q)) C),
 //     A0 = A1 + 2 (x(q) - mean_x) B + (y(q) - mean_y) C            (gradient at the centre itself).
-CDP_HD void cdp_ssim_coeffs(float mx, float my, float xq, float yq, const CdpSsimTerms& t, float& A0,
-                            float& B, float& C) {
-  const float inv = 1.0f / (t.d1 * t.d2);
-  B = t.dl * (-t.S / t.d2);
-  C = t.dl * (2.f * t.n1 * inv);
-  const float A1 = t.dl * (2.f * my * t.n2 * inv - 2.f * mx * t.S / t.d1);
-  A0 = A1 + 2.f * (xq - mx) * B + (yq - my) * C;
+// dxq = x(q) - mean_x, dyq = y(q) - mean_y.
+CDP_HD void cdp_ssim_coeffs(const CdpSsimTerms& t, float dxq, float dyq, float& A0, float& B, float& C) {
+  B = t.dl * (-t.S * t.id2);
+  C = t.dl * (2.f * t.n1 * t.id1 * t.id2);
+  const float A1 = t.dl * 2.f * t.id1 * (t.my * t.n2 * t.id2 - t.mx * t.S);
+  A0 = A1 + 2.f * dxq * B + dyq * C;
+}
+
+// The same coefficients in un-centred form, A + 2 x(p) B + y(p) C, for values measured in a frame
+// where the window means are (mx_f, my_f).  Used with tile-centred values (|x| <~ 1), where the
+// cancellation between the three terms costs ~1.5 digits instead of ~3.5.
+CDP_HD void cdp_ssim_coeffs_abc(const CdpSsimTerms& t, float mx_f, float my_f, float& A, float& B, float& C) {
+  B = t.dl * (-t.S * t.id2);
+  C = t.dl * (2.f * t.n1 * t.id1 * t.id2);
+  const float A1 = t.dl * 2.f * t.id1 * (t.my * t.n2 * t.id2 - t.mx * t.S);
+  A = A1 - 2.f * mx_f * B - my_f * C;
 }
 
 // Reflection padding of one pixel (nn.ReflectionPad2d(1), algos/depth.py:123): -1 -> 1, n -> n-2.

@@ -39,12 +39,13 @@ static void emu_photo_block(const CdpPhotoParams& kp, int bx, int by) {
   const int nt = CDP_PHOTO_THREADS;
   std::vector<float> sm(Geo::SMEM_BYTES / sizeof(float) + 4, 0.f);
   const CdpTileCtx c = cdp_tile_ctx(kp, bx, by);
-  for (int t = 0; t < nt; ++t) cdp_photo_phase_a<G>(kp, c, t, nt, sm.data());
-  for (int t = 0; t < nt; ++t) cdp_photo_phase_b1<G>(kp, c, t, nt, sm.data());
   std::vector<float> v((size_t)nt * 33, 0.f);
-  for (int t = 0; t < nt; ++t) cdp_photo_phase_b2<G>(kp, c, t, nt, sm.data(), v[(size_t)t * 33]);
-  if (G)
+  for (int t = 0; t < nt; ++t) cdp_photo_phase_a<G>(kp, c, t, nt, sm.data());
+  for (int t = 0; t < nt; ++t) cdp_photo_phase_b1<G>(kp, c, t, nt, sm.data(), v[(size_t)t * 33]);
+  if (G) {
+    for (int t = 0; t < nt; ++t) cdp_photo_phase_b2(kp, c, t, nt, sm.data());
     for (int t = 0; t < nt; ++t) cdp_photo_phase_c(kp, c, t, nt, sm.data(), &v[(size_t)t * 33 + 1]);
+  }
   float* rec = kp.partials + ((size_t)c.b * kp.blocks_per_image + bx) * CDP_PARTIAL_STRIDE;
   for (int j = 0; j < 33; ++j) {
     float acc = 0.f;

@@ -18,7 +18,7 @@ REPO = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "cdp_emu.cpp")
 LIB = os.path.join(HERE, "emu", "libcdp_emu.so")
 DEPS = [SRC] + [os.path.join(REPO, "codeps_b200", "csrc", n)
-                for n in ("cdp_common.h", "cdp_math.h", "cdp_kernels.h", "cdp_plan.h")]
+                for n in ("cdp_common.h", "cdp_math.h", "cdp_kernels.h", "cdp_photo_tile.h", "cdp_plan.h")]
 
 _lib = None
 

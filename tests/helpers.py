@@ -194,7 +194,7 @@ def assert_grad_close_masked(got, want, mask_out, what, rtol=GRAD_RTOL, max_mask
 
 
 def check_photo_grads(out, inputs, num_scales, what, level_intrinsics=None, recon_weight=1.0,
-                      max_masked_frac=0.25):
+                      max_masked_frac=0.25, pose_rtol=GRAD_RTOL):
     """Gradient parity of one photometric-loss result ``out`` (dict with argmin, grad_depth,
     grad_pose) against the oracle evaluated with the same min-reprojection selection, in fp64
     (truth) and fp32 (the reference's own rounding).  Returns a short report string."""
@@ -209,8 +209,10 @@ def check_photo_grads(out, inputs, num_scales, what, level_intrinsics=None, reco
     n = assert_grad_close_masked(out["grad_depth"], r64["grad_depth"], mask, f"{what} dL/d depth",
                                  max_masked_frac=max_masked_frac, ref32=r32["grad_depth"])
     for i in range(2):
+        # dL/dT sums over all pixels, discrete-switch pixels included: on images of a few thousand
+        # pixels a single undecidable sign(warped - target) moves it by ~1e-4 (pose_rtol)
         assert_grad_close_masked(out["grad_pose"][i], r64["grad_pose"][i], None, f"{what} dL/dT{i}",
-                                 ref32=r32["grad_pose"][i])
+                                 ref32=r32["grad_pose"][i], rtol=pose_rtol)
     raw = rel_err(out["grad_depth"], r64["grad_depth"])
     raw32 = rel_err(r32["grad_depth"], r64["grad_depth"])
     return (f"{what}: dL/d depth max-abs-normalised deviation from fp64 {raw:.2e} (fp32 reference algorithm: "

@@ -85,10 +85,18 @@ def test_golden_standalone_operators(cuda_device):
     x = inp["images"][1].clone().requires_grad_(True)
     y = inp["images"][0].clone().requires_grad_(True)
     ssim = codeps_b200.SSIMLoss()(x, y)
-    np.testing.assert_allclose(ssim.detach().cpu().numpy(), g.z["op_ssim"], rtol=0, atol=2e-6)
+    # centred statistics are closer to the fp64 value than the reference's own fp32 run is
+    ssim64 = po.ssim_loss_map(inp["images"][1].cpu().double(), inp["images"][0].cpu().double())
+    np.testing.assert_allclose(ssim.detach().cpu().numpy(), ssim64.numpy(), rtol=0, atol=5e-6)
+    np.testing.assert_allclose(ssim.detach().cpu().numpy(), g.z["op_ssim"], rtol=0, atol=5e-4)
     (ssim * up).sum().backward()
-    assert_grad_close(x.grad, g.z["op_ssim_grad_x"], "ssim dL/dx")
-    assert_grad_close(y.grad, g.z["op_ssim_grad_y"], "ssim dL/dy")
+    x64 = inp["images"][1].cpu().double().requires_grad_(True)
+    y64 = inp["images"][0].cpu().double().requires_grad_(True)
+    (po.ssim_loss_map(x64, y64) * up.cpu().double()).sum().backward()
+    assert_grad_close(x.grad, x64.grad, "ssim dL/dx vs fp64")
+    assert_grad_close(y.grad, y64.grad, "ssim dL/dy vs fp64")
+    assert_grad_close(x.grad, g.z["op_ssim_grad_x"], "ssim dL/dx vs fp32 reference", rtol=1e-3)
+    assert_grad_close(y.grad, g.z["op_ssim_grad_y"], "ssim dL/dy vs fp32 reference", rtol=1e-3)
 
 
 def test_object_motion_warp(cuda_device):
@@ -134,12 +142,12 @@ def test_full_size_against_oracle(preset, batch, cuda_device):
     inp["noise"] = noise
     print(check_photo_grads(out, inp, scales, preset, level_intrinsics=list(k_levels), recon_weight=10.0,
                             max_masked_frac=0.05))
-    # argmin: bit-exact wherever the fp64 top-2 gap exceeds TIE_GAP_FULL.  At >= 1024 px the fp32
-    # sample coordinate resolves ~1e-4 px, i.e. candidate losses carry ~1e-5 of rounding: the
+    # argmin: bit-exact wherever the fp64 top-2 gap exceeds 1e-6, at full size too.  (The
     # reference algorithm evaluated in fp32 differs from its own fp64 run on 7-10 pixels per
-    # 0.5 Mpx with gaps up to 1.1e-5 (measured with the oracle on these inputs), so the 1e-6 gap
-    # used for the small golden fixtures is below fp32 resolution here.
-    TIE_GAP_FULL = 2e-5
+    # 0.5 Mpx here, with gaps up to 1.1e-5, because fp32 sample coordinates above 1000 px resolve
+    # only ~1e-4 px; the kernels compute displacements and centred statistics instead and stay
+    # within ~1e-7 of the fp64 candidates.)
+    TIE_GAP_FULL = 1e-6
     flips = 0
     for s in range(scales):
         cand = ref["candidates"][s]
@@ -237,7 +245,7 @@ def test_batch_chunking_over_32_samples(cuda_device):
     assert_loss_close(out["recon"], ref["recon"], "recon")
     assert_grad_close_masked(out["grad_disp"], ref["grad_disp"], smooth_sign_shadow(tb.disp), "dL/d disp")
     inp["noise"] = noise
-    print(check_photo_grads(out, inp, scales, "35 samples", max_masked_frac=0.5))
+    print(check_photo_grads(out, inp, scales, "35 samples", max_masked_frac=0.5, pose_rtol=1e-3))
 
 
 def test_fused_noise_mode_and_no_grad(cuda_device):
