@@ -79,6 +79,10 @@ class NativeError(RuntimeError):
 
 
 def library_path() -> str:
+    # CODEPS_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
+    override = os.environ.get("CODEPS_B200_LIB")
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcodeps_photo.so")
 
 

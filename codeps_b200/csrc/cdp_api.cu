@@ -140,6 +140,25 @@ __device__ __forceinline__ void cdp_block_reduce_store(float (&v)[N], float* red
   }
 }
 
+// Same result type for many values per thread (N ~ 33): every thread parks its values in shared
+// memory (value-major, conflict free), then each warp sums whole values: lane l adds the entries
+// of threads l, l+32, ... in order, a shuffle tree combines the lanes.  ~4x fewer instructions
+// than N shuffle trees per warp.  red: >= N * blockDim.x floats.  Fixed order, no atomics.
+template <int N>
+__device__ __forceinline__ void cdp_block_reduce_store_wide(const float (&v)[N], float* red, float* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, nt = blockDim.x;
+#pragma unroll
+  for (int i = 0; i < N; ++i) red[i * nt + threadIdx.x] = v[i];
+  __syncthreads();
+  for (int i = warp; i < N; i += nwarps) {
+    float acc = 0.f;
+    for (int t = lane; t < nt; t += 32) acc += red[i * nt + t];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[i] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
@@ -148,7 +167,7 @@ __global__ void __launch_bounds__(256) cdp_pyramid_fwd_kernel(const __grid_const
 }
 
 template <bool G>
-__global__ void __launch_bounds__(CDP_PHOTO_THREADS, 2)
+__global__ void __launch_bounds__(CDP_PHOTO_THREADS, CDP_PHOTO_MIN_CTAS)
 cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p) {
   extern __shared__ __align__(16) float sm[];
   const CdpTileCtx c = cdp_tile_ctx(p, blockIdx.x, blockIdx.y);
@@ -167,25 +186,31 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p) {
   v[0] *= p.lv[c.lvl].weight;
   __syncthreads();  // tile planes are dead: reuse shared memory for the reduction
   float* rec = p.partials + ((size_t)c.b * p.blocks_per_image + blockIdx.x) * CDP_PARTIAL_STRIDE;
-  cdp_block_reduce_store(v, sm, rec);
-  if (!G && threadIdx.x >= 1 && threadIdx.x < 33) rec[threadIdx.x] = 0.f;
+  if constexpr (G) {
+    cdp_block_reduce_store_wide(v, sm, rec);
+  } else {
+    cdp_block_reduce_store(v, sm, rec);
+    if (threadIdx.x >= 1 && threadIdx.x < 33) rec[threadIdx.x] = 0.f;
+  }
 }
 
 __global__ void __launch_bounds__(CDP_FINALIZE_THREADS) cdp_finalize_kernel(const CdpFinalizeParams p) {
-  __shared__ double sm[32 * 33];
-  double loss_acc = 0.0;
-  for (int b = 0; b < p.B; ++b) {
-    cdp_finalize_phase_a(p, b, threadIdx.x, sm);
-    __syncthreads();
-    cdp_finalize_phase_b(p, b, threadIdx.x, sm, &loss_acc);
-    __syncthreads();
-  }
-  if (threadIdx.x == 32) p.loss[0] = (float)loss_acc;
+  __shared__ double sm[2048];
+  cdp_finalize_phase_a(p, blockIdx.x, threadIdx.x, sm);
+  __syncthreads();
+  cdp_finalize_phase_b(p, blockIdx.x, threadIdx.x, sm);
+}
+
+__device__ __forceinline__ double cdp_warp_butterfly(double v) {  // same order as cdp_butterfly_host
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  return v;
 }
 
 __global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_constant__ CdpDepthGradParams p) {
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix < p.H * p.W) cdp_depth_grad_pixel(p, blockIdx.y, pix);
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;  // two horizontally adjacent pixels
+  const int pairs_per_row = (p.W + 1) >> 1;
+  if (pair < p.H * pairs_per_row) cdp_depth_grad_pair(p, blockIdx.y, pair / pairs_per_row, (pair % pairs_per_row) * 2);
   if (blockIdx.x == 0 && blockIdx.y == 0)
     for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
 }
@@ -199,15 +224,40 @@ __global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_sum_kernel(cons
 __global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_main_kernel(const CdpSmoothParams p) {
   __shared__ float red[3 * CDP_SMOOTH_THREADS / 32];
   __shared__ float mean_s;
-  if (threadIdx.x == 0) mean_s = cdp_smooth_mean(p, blockIdx.y);
+  if (threadIdx.x < 32) {
+    const double tot = cdp_warp_butterfly(cdp_smooth_lane_sum(p.part_sum + (size_t)blockIdx.y * CDP_SMOOTH_BLOCKS, 1, threadIdx.x));
+    if (threadIdx.x == 0) mean_s = (float)(tot / (double)((size_t)p.H * p.W));
+  }
   __syncthreads();
   float v[3] = {0.f, 0.f, 0.f};
   cdp_smooth_main_thread(p, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, mean_s, v);
   cdp_block_reduce_store(v, red, p.part_main + ((size_t)blockIdx.y * CDP_SMOOTH_BLOCKS + blockIdx.x) * 4);
 }
 
-__global__ void cdp_smooth_finalize_kernel(const CdpSmoothParams p) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) cdp_smooth_finalize(p);
+// one warp per image (fixed order), then warp 0 combines the images in index order
+__global__ void __launch_bounds__(1024) cdp_smooth_finalize_kernel(const CdpSmoothParams p) {
+  __shared__ double sxs[CDP_MAX_BATCH_PER_LAUNCH], sys[CDP_MAX_BATCH_PER_LAUNCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  double sx_tot = 0.0, sy_tot = 0.0;
+  for (int b0 = 0; b0 < p.B; b0 += nwarps) {
+    const int b = b0 + warp;
+    if (b < p.B) {
+      const float* rec = p.part_main + (size_t)b * CDP_SMOOTH_BLOCKS * 4;
+      const double sx = cdp_warp_butterfly(cdp_smooth_lane_sum(rec + 0, 4, lane));
+      const double sy = cdp_warp_butterfly(cdp_smooth_lane_sum(rec + 1, 4, lane));
+      const double gd = cdp_warp_butterfly(cdp_smooth_lane_sum(rec + 2, 4, lane));
+      const double ps = cdp_warp_butterfly(cdp_smooth_lane_sum(p.part_sum + (size_t)b * CDP_SMOOTH_BLOCKS, 1, lane));
+      if (lane == 0) {
+        sxs[warp] = sx; sys[warp] = sy;
+        if (p.with_grad) cdp_smooth_finalize_image(p, b, gd, ps);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int w = 0; w < nwarps && b0 + w < p.B; ++w) { sx_tot += sxs[w]; sy_tot += sys[w]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cdp_smooth_finalize_loss(p, sx_tot, sy_tot);
 }
 
 __global__ void __launch_bounds__(256)
@@ -370,7 +420,7 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   // 3. fixed-order reduction of the per-CTA records
   CdpFinalizeParams fp;
   cdp_fill_finalize_params(plan, a, &fp);
-  { ProfScope prof_(CDP_KERNEL_FINALIZE, stream); cdp_finalize_kernel<<<1, CDP_FINALIZE_THREADS, 0, stream>>>(fp); }
+  { ProfScope prof_(CDP_KERNEL_FINALIZE, stream); cdp_finalize_kernel<<<plan.B, CDP_FINALIZE_THREADS, 0, stream>>>(fp); }
   CDP_LAUNCH_CHECK("cdp_finalize_kernel");
   return CDP_OK;
 }
@@ -386,7 +436,7 @@ extern "C" int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32
   if (saved_bytes < plan.saved_floats * sizeof(float)) return cdp_fail(CDP_ERR_WORKSPACE, "saved too small");
   CdpDepthGradParams p;
   cdp_fill_depth_grad_params(plan, saved_, resize_tables, grad_loss, grad_depth, grad_pose0, grad_pose1, &p);
-  dim3 grid((plan.H * plan.W + 255) / 256, plan.B);
+  dim3 grid((plan.H * ((plan.W + 1) / 2) + 255) / 256, plan.B);
   { ProfScope prof_(CDP_KERNEL_DEPTH_GRAD, stream); cdp_depth_grad_kernel<<<grid, 256, 0, stream>>>(p); }
   CDP_LAUNCH_CHECK("cdp_depth_grad_kernel");
   return CDP_OK;
@@ -415,7 +465,7 @@ extern "C" int cdp_smooth_fwd(const float* image, const float* disp, int32_t bat
   CDP_LAUNCH_CHECK("cdp_smooth_sum_kernel");
   { ProfScope prof_(CDP_KERNEL_SMOOTH_MAIN, stream); cdp_smooth_main_kernel<<<grid, CDP_SMOOTH_THREADS, 0, stream>>>(p); }
   CDP_LAUNCH_CHECK("cdp_smooth_main_kernel");
-  { ProfScope prof_(CDP_KERNEL_SMOOTH_FINALIZE, stream); cdp_smooth_finalize_kernel<<<1, 32, 0, stream>>>(p); }
+  { ProfScope prof_(CDP_KERNEL_SMOOTH_FINALIZE, stream); cdp_smooth_finalize_kernel<<<1, 1024, 0, stream>>>(p); }
   CDP_LAUNCH_CHECK("cdp_smooth_finalize_kernel");
   return CDP_OK;
 }

@@ -47,8 +47,13 @@ struct alignas(8) float2 {  // CUDA's vector type, for the host build of the ker
 // Fused photometric tile kernel geometry.
 // ------------------------------------------------------------------------------------------
 #define CDP_TILE_X 32
+#ifndef CDP_TILE_Y
 #define CDP_TILE_Y 32
+#endif
 #define CDP_PHOTO_THREADS 256
+#ifndef CDP_PHOTO_MIN_CTAS
+#define CDP_PHOTO_MIN_CTAS 2  // resident CTAs per SM the register allocation targets
+#endif
 // Per-CTA partial record: [0] loss sum, [1..16] dL/dT0, [17..32] dL/dT1 (row-major 4x4), padded.
 #define CDP_PARTIAL_STRIDE 36
 #define CDP_NOISE_SCALE 0.00001f  // algos/depth.py:317-318

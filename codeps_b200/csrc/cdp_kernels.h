@@ -65,28 +65,32 @@ struct CdpFinalizeParams {
 
 #define CDP_FINALIZE_THREADS 1024
 
-// step 1: per-thread strided sums into sm[r][33] (double precision)
+// Block b, step 1: per-thread strided sums of image b's records into sm[r][32] (double precision).
+// Block 0 additionally strides over ALL records' loss entries into sm[1024 + tid].
 CDP_HD void cdp_finalize_phase_a(const CdpFinalizeParams& p, int b, int tid, double* sm) {
   const int r = tid >> 5, j = tid & 31;
-  double acc = 0.0, lacc = 0.0;
-  for (int blk = r; blk < p.blocks_per_image; blk += 32) {
-    const float* rec = p.partials + ((size_t)b * p.blocks_per_image + blk) * CDP_PARTIAL_STRIDE;
-    acc += (double)rec[1 + j];
-    if (j == 0) lacc += (double)rec[0];
-  }
-  sm[r * 33 + j] = acc;
-  if (j == 0) sm[r * 33 + 32] = lacc;
-}
-// step 2: combine the 32 rows in order; threads 0..32 each own one output column
-CDP_HD void cdp_finalize_phase_b(const CdpFinalizeParams& p, int b, int tid, const double* sm,
-                                 double* loss_acc /* thread 32's running loss over images */) {
-  if (tid > 32) return;
   double acc = 0.0;
-  for (int r = 0; r < 32; ++r) acc += sm[r * 33 + tid];
+  for (int blk = r; blk < p.blocks_per_image; blk += 32)
+    acc += (double)p.partials[((size_t)b * p.blocks_per_image + blk) * CDP_PARTIAL_STRIDE + 1 + j];
+  sm[r * 32 + j] = acc;
+  if (b == 0) {
+    double lacc = 0.0;
+    const int total = p.B * p.blocks_per_image;
+    for (int i = tid; i < total; i += CDP_FINALIZE_THREADS) lacc += (double)p.partials[(size_t)i * CDP_PARTIAL_STRIDE];
+    sm[1024 + tid] = lacc;
+  }
+}
+// step 2: combine in index order; threads 0..31 own one pose-gradient column, thread 32 of block 0
+// the loss
+CDP_HD void cdp_finalize_phase_b(const CdpFinalizeParams& p, int b, int tid, const double* sm) {
   if (tid < 32) {
+    double acc = 0.0;
+    for (int r = 0; r < 32; ++r) acc += sm[r * 32 + tid];
     if (p.pose_unit) p.pose_unit[((size_t)(tid >> 4) * p.B + b) * 16 + (tid & 15)] = (float)acc;
-  } else {
-    *loss_acc += acc;
+  } else if (tid == 32 && b == 0) {
+    double acc = 0.0;
+    for (int i = 0; i < CDP_FINALIZE_THREADS; ++i) acc += sm[1024 + i];
+    p.loss[0] = (float)acc;
   }
 }
 
@@ -105,24 +109,43 @@ struct CdpDepthGradParams {
   int32_t B, H, W, L;
 };
 
-CDP_HD void cdp_depth_grad_pixel(const CdpDepthGradParams& p, int b, int pix) {
-  const int y = pix / p.W, x = pix - y * p.W;
-  float acc = CDP_LDG(p.gdepth[0] + (size_t)b * p.W * p.H + pix);
-  for (int s = 1; s < p.L; ++s) {
-    const CdpResizeInv ex = p.inv_x[s][x], ey = p.inv_y[s][y];
-    const float* g = p.gdepth[s] + (size_t)b * p.Ws[s] * p.Hs[s];
-    float row_a = 0.f, row_b = 0.f;
-    if (ey.ja >= 0) {
-      if (ex.ja >= 0) row_a += ex.wa * CDP_LDG(g + ey.ja * p.Ws[s] + ex.ja);
-      if (ex.jb >= 0) row_a += ex.wb * CDP_LDG(g + ey.ja * p.Ws[s] + ex.jb);
-    }
-    if (ey.jb >= 0) {
-      if (ex.ja >= 0) row_b += ex.wa * CDP_LDG(g + ey.jb * p.Ws[s] + ex.ja);
-      if (ex.jb >= 0) row_b += ex.wb * CDP_LDG(g + ey.jb * p.Ws[s] + ex.jb);
-    }
-    acc += ey.wa * row_a + ey.wb * row_b;
+// contribution of level s to full-resolution pixel (x, y): transpose of the bilinear resize
+CDP_HD float cdp_depth_grad_level(const float* g, int ws, const CdpResizeInv& ex, const CdpResizeInv& ey) {
+  float row_a = 0.f, row_b = 0.f;
+  if (ey.ja >= 0) {
+    const float* r = g + ey.ja * ws;
+    if (ex.ja >= 0) row_a = ex.wa * CDP_LDG(r + ex.ja);
+    if (ex.jb >= 0) row_a += ex.wb * CDP_LDG(r + ex.jb);
   }
-  p.grad_depth[(size_t)b * p.W * p.H + pix] = CDP_LDG(p.grad_loss) * acc;
+  if (ey.jb >= 0) {
+    const float* r = g + ey.jb * ws;
+    if (ex.ja >= 0) row_b = ex.wa * CDP_LDG(r + ex.ja);
+    if (ex.jb >= 0) row_b += ex.wb * CDP_LDG(r + ex.jb);
+  }
+  return ey.wa * row_a + ey.wb * row_b;
+}
+
+// two horizontally adjacent pixels (x, x+1) of row y: they share the row taps of every level
+CDP_HD void cdp_depth_grad_pair(const CdpDepthGradParams& p, int b, int y, int x) {
+  const int W = p.W, pix = y * W + x;
+  const bool two = x + 1 < W;
+  const float* g0 = p.gdepth[0] + (size_t)b * W * p.H;
+  float acc0 = CDP_LDG(g0 + pix), acc1 = two ? CDP_LDG(g0 + pix + 1) : 0.f;
+  for (int s = 1; s < p.L; ++s) {
+    const CdpResizeInv ey = p.inv_y[s][y];
+    const float* g = p.gdepth[s] + (size_t)b * p.Ws[s] * p.Hs[s];
+    acc0 += cdp_depth_grad_level(g, p.Ws[s], p.inv_x[s][x], ey);
+    if (two) acc1 += cdp_depth_grad_level(g, p.Ws[s], p.inv_x[s][x + 1], ey);
+  }
+  const float go = CDP_LDG(p.grad_loss);
+  float* out = p.grad_depth + (size_t)b * W * p.H + pix;
+  out[0] = go * acc0;
+  if (two) out[1] = go * acc1;
+}
+
+CDP_HD void cdp_depth_grad_pixel(const CdpDepthGradParams& p, int b, int pix) {  // single-pixel form
+  const int y = pix / p.W, x = pix - y * p.W;
+  if ((x & 1) == 0) cdp_depth_grad_pair(p, b, y, x);
 }
 
 CDP_HD void cdp_pose_grad_scale(const CdpDepthGradParams& p, int i) {  // i in [0, 2*B*16)
@@ -133,7 +156,7 @@ CDP_HD void cdp_pose_grad_scale(const CdpDepthGradParams& p, int i) {  // i in [
 // ==========================================================================================
 // 5. Edge-aware smoothness (algos/depth.py:58-107).
 // ==========================================================================================
-#define CDP_SMOOTH_BLOCKS 64   // blocks per image for the two reduction passes
+#define CDP_SMOOTH_BLOCKS 256  // blocks per image for the two reduction passes
 #define CDP_SMOOTH_THREADS 256
 
 struct CdpSmoothParams {
@@ -164,11 +187,22 @@ CDP_HD float cdp_smooth_sum_thread(const CdpSmoothParams& p, int b, int blk, int
   return acc;
 }
 
-// mean disparity of image b from the per-block partial sums (fixed order)
-CDP_HD float cdp_smooth_mean(const CdpSmoothParams& p, int b) {
+// mean disparity of image b from the per-block partial sums, in a fixed order that one warp can
+// evaluate in parallel: lane l sums partials l, l+32, ... then lanes are combined by a butterfly
+CDP_HD double cdp_smooth_lane_sum(const float* part, int stride, int lane) {
   double acc = 0.0;
-  for (int i = 0; i < CDP_SMOOTH_BLOCKS; ++i) acc += (double)p.part_sum[b * CDP_SMOOTH_BLOCKS + i];
-  return (float)(acc / (double)((size_t)p.H * p.W));
+  for (int i = lane; i < CDP_SMOOTH_BLOCKS; i += 32) acc += (double)part[(size_t)i * stride];
+  return acc;
+}
+CDP_HD double cdp_butterfly_host(double v[32]) {  // same combination order as the shuffle tree
+  for (int off = 16; off > 0; off >>= 1)
+    for (int l = 0; l < off; ++l) v[l] += v[l + off];
+  return v[0];
+}
+CDP_HD float cdp_smooth_mean(const CdpSmoothParams& p, int b) {  // host / single-thread form
+  double v[32];
+  for (int l = 0; l < 32; ++l) v[l] = cdp_smooth_lane_sum(p.part_sum + (size_t)b * CDP_SMOOTH_BLOCKS, 1, l);
+  return (float)(cdp_butterfly_host(v) / (double)((size_t)p.H * p.W));
 }
 
 CDP_HD float cdp_edge_weight(const float* img, size_t plane, int a, int bidx) {
@@ -225,24 +259,34 @@ CDP_HD void cdp_smooth_main_thread(const CdpSmoothParams& p, int b, int blk, int
   }
 }
 
-// one thread: combine the block partials of all images (fixed order)
+// Combine the block partials (fixed order).  Written per (image, quantity) so that one warp can
+// evaluate each sum in parallel: quantity 0 = sum tx, 1 = sum ty, 2 = sum g*disp.
+CDP_HD void cdp_smooth_finalize_image(const CdpSmoothParams& p, int b, double gd_sum, double part_sum) {
+  const float mean = (float)(part_sum / (double)((size_t)p.H * p.W));
+  const float den = mean + 1e-7f;
+  const double a = 1.0 / (double)den;
+  p.scal[b * 2 + 0] = (float)a;
+  p.scal[b * 2 + 1] = (float)(gd_sum * a * a / (double)((size_t)p.H * p.W));
+}
+CDP_HD void cdp_smooth_finalize_loss(const CdpSmoothParams& p, double sx, double sy) {
+  const double nx = (double)p.B * p.H * (p.W - 1), ny = (double)p.B * (p.H - 1) * p.W;
+  p.loss[0] = (float)(sx / nx) + (float)(sy / ny);
+}
+// host / single-thread form of the whole finalize step
 CDP_HD void cdp_smooth_finalize(const CdpSmoothParams& p) {
   double sx = 0.0, sy = 0.0;
   for (int b = 0; b < p.B; ++b) {
-    double gd = 0.0;
-    for (int i = 0; i < CDP_SMOOTH_BLOCKS; ++i) {
-      const float* rec = p.part_main + ((size_t)b * CDP_SMOOTH_BLOCKS + i) * 4;
-      sx += (double)rec[0]; sy += (double)rec[1]; gd += (double)rec[2];
+    double v[3][32], ps[32];
+    for (int l = 0; l < 32; ++l) {
+      for (int q = 0; q < 3; ++q) v[q][l] = cdp_smooth_lane_sum(p.part_main + (size_t)b * CDP_SMOOTH_BLOCKS * 4 + q, 4, l);
+      ps[l] = cdp_smooth_lane_sum(p.part_sum + (size_t)b * CDP_SMOOTH_BLOCKS, 1, l);
     }
-    if (p.with_grad) {
-      const float den = cdp_smooth_mean(p, b) + 1e-7f;
-      const double a = 1.0 / (double)den;
-      p.scal[b * 2 + 0] = (float)a;
-      p.scal[b * 2 + 1] = (float)(gd * a * a / (double)((size_t)p.H * p.W));
-    }
+    sx += cdp_butterfly_host(v[0]);
+    sy += cdp_butterfly_host(v[1]);
+    const double gd = cdp_butterfly_host(v[2]), psum = cdp_butterfly_host(ps);
+    if (p.with_grad) cdp_smooth_finalize_image(p, b, gd, psum);
   }
-  const double nx = (double)p.B * p.H * (p.W - 1), ny = (double)p.B * (p.H - 1) * p.W;
-  p.loss[0] = (float)(sx / nx) + (float)(sy / ny);
+  cdp_smooth_finalize_loss(p, sx, sy);
 }
 
 CDP_HD void cdp_smooth_bwd_pixel(const float* g, const float* scal, const float* grad_loss, int b,

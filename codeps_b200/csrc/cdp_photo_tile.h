@@ -19,7 +19,9 @@
 
 #include "cdp_math.h"
 
+#ifndef CDP_STRIP
 #define CDP_STRIP 5  // pixels per thread strip in phases B1/B2
+#endif
 
 template <bool G>
 struct CdpTileGeom {
@@ -199,14 +201,19 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
 #pragma unroll
     for (int o = 0; o < CDP_STRIP; ++o) { acc_id[o] = cdp_set2(0.f); acc_pe[o] = cdp_set2(0.f); }
     const bool col_ok = qx >= 0 && qx < W;
+    const int qc = qy0 + CDP_STRIP / 2 < 0 ? 0 : (qy0 + CDP_STRIP / 2 > H - 1 ? H - 1 : qy0 + CDP_STRIP / 2);
+    const int cs_idx = (qc - c.y0 + Geo::HALO) * Geo::RW + bx + 1;
     if (col_ok && qy0 < H && qy0 + CDP_STRIP > 0) {
-#pragma unroll
+      // the channel loop stays rolled: unrolled, this phase alone is ~60 KB of SASS that every
+      // warp streams through once per tile, and instruction fetch becomes the top stall reason
+#pragma unroll 1
       for (int ch = 0; ch < 3; ++ch) {
         const float* ty = sm + (size_t)(Geo::P_TGT + ch) * Geo::RN;
         const float2* ts = cdp_pair_plane<G>(sm, Geo::P_SRC, ch);
         const float2* tw = cdp_pair_plane<G>(sm, Geo::P_WARP, ch);
-        // strip constant: target value at the strip's middle pixel (already tile-centred)
-        const float cs = ty[r00 + 2 * Geo::RW];
+        // strip constant: target value at the strip's middle pixel (already tile-centred),
+        // clamped into the image so that it is always a staged value
+        const float cs = ty[cs_idx];
         const float ct = cs + centre[ch];
         const float2 cs2 = cdp_set2(-cs);
         CdpRowTgt hy[3];
@@ -303,17 +310,18 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
       any = any || kk[o] < 2;
     }
     if (!any) continue;  // every pixel of the strip is auto-masked or outside the image
-#pragma unroll
+    const int qy0 = c.y0 - Geo::HB + by0;
+    const int qc = qy0 + CDP_STRIP / 2 < 0 ? 0 : (qy0 + CDP_STRIP / 2 > lv.H - 1 ? lv.H - 1 : qy0 + CDP_STRIP / 2);
+    const int cs_idx = (qc - c.y0 + Geo::HALO) * Geo::RW + bx + 1;
+#pragma unroll 1
     for (int ch = 0; ch < 3; ++ch) {
       const float* ty = sm + (size_t)(Geo::P_TGT + ch) * Geo::RN;
       const float2* tw = cdp_pair_plane<true>(sm, Geo::P_WARP, ch);
-      const float cs = ty[r00 + 2 * Geo::RW];
+      const float cs = ty[cs_idx];
       const float ct = cs + centre[ch];
       const float2 cs2 = cdp_set2(-cs);
       CdpRowTgt hy[3];
       CdpRowPair hw[3];
-      float yc_prev = 0.f;
-      float2 wc_prev = cdp_set2(0.f);
 #pragma unroll
       for (int r = 0; r < CDP_STRIP + 2; ++r) {
         const int row = r00 + (r - 1) * Geo::RW;
@@ -350,9 +358,7 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
             sm[(size_t)(Geo::P_COEF + ch * 3 + 2) * Geo::RN + ridx] = C;
           }
         }
-        yc_prev = y[1]; wc_prev = w[1];
       }
-      (void)yc_prev; (void)wc_prev;
     }
   }
 }
@@ -367,10 +373,6 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
   const int W = lv.W, H = lv.H;
   const size_t plane = (size_t)W * H;
   const CdpCam cam = cdp_tile_cam(p, c);
-  CdpPose T[2];
-  cdp_load_pose(p.pose0 + (size_t)c.b * 16, T[0]);
-  cdp_load_pose(p.pose1 + (size_t)c.b * 16, T[1]);
-  const float* src[2] = {lv.src0 + (size_t)c.b * 3 * plane, lv.src1 + (size_t)c.b * 3 * plane};
   const uint8_t* kplane = reinterpret_cast<const uint8_t*>(sm + (size_t)Geo::NPLANES * Geo::RN);
   const float w_ssim = p.alpha / 27.0f;  // alpha * (1/3 channels) * (1/9 window)
   const float w_l1 = (float)(1.0 - (double)p.alpha) * (1.0f / 3.0f);
@@ -384,22 +386,32 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
     int kn[9];
     float mn[9];
     bool any0 = kown == 0, any1 = kown == 1;
+    if (px >= 2 && px <= W - 3 && py >= 2 && py <= H - 3) {  // no reflection in reach: weights are 1
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const float my = cdp_reflect_mult(py, dy, H);
-#pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int j = (dy + 1) * 3 + dx + 1;
-        mn[j] = my * cdp_reflect_mult(px, dx, W);
-        kn[j] = mn[j] != 0.f ? (int)kplane[ridx + dy * Geo::RW + dx] : 255;
+      for (int j = 0; j < 9; ++j) {
+        mn[j] = 1.f;
+        kn[j] = (int)kplane[ridx + (j / 3 - 1) * Geo::RW + (j % 3 - 1)];
         any0 = any0 || kn[j] == 0;
         any1 = any1 || kn[j] == 1;
+      }
+    } else {
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const float my = cdp_reflect_mult(py, dy, H);
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int j = (dy + 1) * 3 + dx + 1;
+          mn[j] = my * cdp_reflect_mult(px, dx, W);
+          kn[j] = mn[j] != 0.f ? (int)kplane[ridx + dy * Geo::RW + dx] : 255;
+          any0 = any0 || kn[j] == 0;
+          any1 = any1 || kn[j] == 1;
+        }
       }
     }
     float gd = 0.f;
     if (any0 || any1) {
       const float depth = CDP_LDG(lv.depth + (size_t)c.b * plane + py * W + px);
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < 2; ++k) {
         if (!(k == 0 ? any0 : any1)) continue;
         float sa[3] = {0.f, 0.f, 0.f}, sb[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f};
@@ -414,8 +426,12 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
             sc[ch] += mn[j] * sm[(size_t)(Geo::P_COEF + ch * 3 + 2) * Geo::RN + n];
           }
         }
+        // (the source loop is rolled to keep the code small: no register arrays indexed by k)
+        CdpPose T;
+        cdp_load_pose((k == 0 ? p.pose0 : p.pose1) + (size_t)c.b * 16, T);
+        const float* srck = (k == 0 ? lv.src0 : lv.src1) + (size_t)c.b * 3 * plane;
         CdpWarp w;
-        cdp_warp_point((float)px, (float)py, depth, cam, T[k], nullptr, w);
+        cdp_warp_point((float)px, (float)py, depth, cam, T, nullptr, w);
         CdpTaps t;
         cdp_taps(px, py, w, W, H, t);
         float gix = 0.f, giy = 0.f;
@@ -428,11 +444,21 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
           if (kown == k) gw += w_l1 * (x > y ? 1.f : (x < y ? -1.f : 0.f));
           gw *= lv.weight;
           float dix, diy;
-          cdp_bilinear_grad(src[k] + ch * plane, t, dix, diy);
+          cdp_bilinear_grad(srck + ch * plane, t, dix, diy);
           gix += gw * dix;
           giy += gw * diy;
         }
-        cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T[k], gd, dT + 16 * k, nullptr);
+        float dTk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dTk[i] = 0.f;
+        cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dTk, nullptr);
+        if (k == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dT[i] += dTk[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dT[16 + i] += dTk[i];
+        }
       }
     }
     lv.gdepth[(size_t)c.b * plane + py * W + px] = gd;

@@ -75,13 +75,11 @@ EMU_API int emu_photo_fwd(const cdp_photo_args* a) {
   }
   CdpFinalizeParams fp;
   cdp_fill_finalize_params(plan, a, &fp);
-  std::vector<double> sm(32 * 33);
-  double loss_acc = 0.0;
+  std::vector<double> sm(2048);
   for (int b = 0; b < fp.B; ++b) {
     for (int t = 0; t < CDP_FINALIZE_THREADS; ++t) cdp_finalize_phase_a(fp, b, t, sm.data());
-    for (int t = 0; t < CDP_FINALIZE_THREADS; ++t) cdp_finalize_phase_b(fp, b, t, sm.data(), &loss_acc);
+    for (int t = 0; t < CDP_FINALIZE_THREADS; ++t) cdp_finalize_phase_b(fp, b, t, sm.data());
   }
-  fp.loss[0] = (float)loss_acc;
   return CDP_OK;
 }
 
