@@ -61,6 +61,25 @@ def parse_args():
     return ap.parse_args()
 
 
+def profiled_kernel(workload: str, kernel_substr: str):
+    """Latest tracked ncu record (profiles/*_ncu.json, written by tools/ncu_to_profile.py) of a
+    kernel for this workload: DRAM traffic per launch, issue-slot utilisation, L2 hit rate."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "*_ncu.json"))):
+        try:
+            with open(path) as f:
+                blob = json.load(f)
+        except (OSError, ValueError):
+            continue
+        if blob.get("workload") != workload:
+            continue
+        for rec in blob.get("launches", []):
+            if kernel_substr in rec.get("kernel", "") and "dram_bytes" in rec:
+                best = dict(rec, profile=os.path.relpath(path, REPO))
+    return best
+
+
 def measured_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -295,9 +314,15 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = photo_alg_bytes / (photo_ms * 1e-3) / 1e9
     step_kernel_ms = sum(v for v in kernel_ms.values() if v)
+    prof_rec = profiled_kernel(args.workload, "cdp_photo_kernel<1>") or profiled_kernel(args.workload, "cdp_photo_kernel")
     roofline = {
         "bound": "hbm", "kernel": "cdp_photo_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": prof_rec["dram_bytes"] if prof_rec else None, "peak_source": peak_src,
+        "ncu": ({k: prof_rec.get(k) for k in ("profile", "duration_us", "issue_slot_pct", "sm_pct_of_peak",
+                                              "dram_pct_of_peak", "l2_hit_pct", "l1_hit_pct",
+                                              "achieved_occupancy_pct", "registers_per_thread")}
+                if prof_rec else None),
+        "limiter": "fp32 issue slots, not HBM (DESIGN.md section 6): see ncu.issue_slot_pct vs ncu.dram_pct_of_peak",
         "algorithmic_bytes_per_launch": photo_alg_bytes, "kernel_ms": photo_ms,
         "kernel_share_of_step": photo_ms / step_kernel_ms if step_kernel_ms else None,
         "kernel_ms_all": kernel_ms,
@@ -364,10 +389,11 @@ def main():
                         "sample": f"1 triplet of the workload per iteration (B=1, {w}x{h}), {iters} iterations, "
                                   f"median {med * 1e3:.0f} ms, torch {torch.__version__} CPU"}
 
-    checksum = torch.tensor([recon_val, smooth_val], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(checksum)  # scalar statistics only; the data path has no collective
-        checksum /= world
+    # scalar statistics only (one coalesced all-reduce of 3 doubles); the data path has no collective
+    from codeps_b200.distributed import reduce_loss_dict
+    stats = reduce_loss_dict({"recon": torch.tensor(recon_val, device=dev, dtype=torch.float64),
+                              "smooth": torch.tensor(smooth_val, device=dev, dtype=torch.float64)}, batch)
+    checksum = [float(stats["recon"]), float(stats["smooth"])]
 
     if rank == 0:
         line = {

@@ -201,6 +201,18 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
 #pragma unroll
     for (int o = 0; o < CDP_STRIP; ++o) { acc_id[o] = cdp_set2(0.f); acc_pe[o] = cdp_set2(0.f); }
     const bool col_ok = qx >= 0 && qx < W;
+    // tie-break noise of the strip's pixels, requested early so the loads overlap the strip walk
+    float2 nz[CDP_STRIP];
+#pragma unroll
+    for (int o = 0; o < CDP_STRIP; ++o) {
+      const int qy = qy0 + o;
+      nz[o] = cdp_set2(0.f);
+      if (lv.noise && col_ok && qy >= 0 && qy < H && by0 + o < Geo::BH) {
+        const size_t nplane = (size_t)W * H;
+        nz[o].x = CDP_LDG(lv.noise + ((size_t)c.b * 2 + 0) * nplane + qy * W + qx);
+        nz[o].y = CDP_LDG(lv.noise + ((size_t)c.b * 2 + 1) * nplane + qy * W + qx);
+      }
+    }
     const int qc = qy0 + CDP_STRIP / 2 < 0 ? 0 : (qy0 + CDP_STRIP / 2 > H - 1 ? H - 1 : qy0 + CDP_STRIP / 2);
     const int cs_idx = (qc - c.y0 + Geo::HALO) * Geo::RW + bx + 1;
     if (col_ok && qy0 < H && qy0 + CDP_STRIP > 0) {
@@ -264,14 +276,8 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
         if (G) kplane[ridx] = 255;
         continue;
       }
-      float n0, n1;
-      if (lv.noise) {
-        const size_t plane = (size_t)W * H;
-        n0 = CDP_LDG(lv.noise + ((size_t)c.b * 2 + 0) * plane + qy * W + qx);
-        n1 = CDP_LDG(lv.noise + ((size_t)c.b * 2 + 1) * plane + qy * W + qx);
-      } else {
-        cdp_noise_pair(p.seed, (uint32_t)(qy * W + qx), (uint32_t)c.lvl, (uint32_t)c.b, n0, n1);
-      }
+      float n0 = nz[o].x, n1 = nz[o].y;
+      if (!lv.noise) cdp_noise_pair(p.seed, (uint32_t)(qy * W + qx), (uint32_t)c.lvl, (uint32_t)c.b, n0, n1);
       const float id0 = acc_id[o].x + n0 * CDP_NOISE_SCALE, id1 = acc_id[o].y + n1 * CDP_NOISE_SCALE;
       float best = acc_pe[o].x;
       int kb = 0;
