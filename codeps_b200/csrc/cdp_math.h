@@ -143,17 +143,32 @@ struct CdpTaps {
   float mx, my;                // 1 where the coordinate gradient passes the border clip
 };
 
-// one axis: integer pixel index p, displacement d (= i - p), absolute position i, extent n
+// one axis: integer pixel index p, displacement d (= i - p), absolute position i, extent n.
+// Outside (0, n-1) the coordinate is clipped to the border (weight 1 on the border pixel, gradient
+// mask 0: clip_coordinates_set_grad); NaN compares false and lands on border 0.
+#ifndef CDP_OPT_BRANCHFREE_TAPS
+#define CDP_OPT_BRANCHFREE_TAPS 1
+#endif
 CDP_HD void cdp_tap_axis(int p, float d, float i, int n, int& i0, int& i1, float& w0, float& w1, float& m) {
   const float nm1 = (float)(n - 1);
+#if CDP_OPT_BRANCHFREE_TAPS
+  const bool pos = i > 0.f, inside = pos && i < nm1;
+  const float fl = floorf(d);
+  const float frac = inside ? d - fl : 0.f;
+  int a = inside ? p + (int)fl : (pos ? n - 1 : 0);
+  a = a < 0 ? 0 : (a > n - 1 ? n - 1 : a);
+  i0 = a;
+  m = inside ? 1.f : 0.f;
+#else
   float frac;
-  if (!(i > 0.f)) { i0 = 0; frac = 0.f; m = 0.f; }            // clip_coordinates_set_grad; NaN lands here
+  if (!(i > 0.f)) { i0 = 0; frac = 0.f; m = 0.f; }
   else if (i >= nm1) { i0 = n - 1; frac = 0.f; m = 0.f; }
   else {
     const float fl = floorf(d);
     i0 = p + (int)fl; frac = d - fl; m = 1.f;
   }
   i0 = i0 < 0 ? 0 : (i0 > n - 1 ? n - 1 : i0);
+#endif
   i1 = i0 + 1 > n - 1 ? n - 1 : i0 + 1;  // a tap one past the border has weight exactly 0
   w1 = frac; w0 = 1.0f - frac;
 }

@@ -19,6 +19,12 @@
 
 #include "cdp_math.h"
 
+#ifndef CDP_OPT_PACKED_GATHER
+#define CDP_OPT_PACKED_GATHER 0  // float2-packed coefficient gather in phase C: measured slower (spills), off
+#endif
+#ifndef CDP_OPT_DIRECT_DT
+#define CDP_OPT_DIRECT_DT 1  // phase C accumulates dL/dT without a per-pixel temporary
+#endif
 #ifndef CDP_STRIP
 #define CDP_STRIP 5  // pixels per thread strip in phases B1/B2
 #endif
@@ -35,8 +41,10 @@ struct CdpTileGeom {
   static constexpr int P_TGT = 0;    // 3 planes: target, channel c
   static constexpr int P_WARP = 3;   // 3 float2 planes (6 floats): warped (source 0, source 1), channel c
   static constexpr int P_SRC = 9;    // 3 float2 planes: un-warped (source 0, source 1) = identity candidates
-  static constexpr int P_COEF = 9;   // with grad, after B1: 9 planes A,B,C per channel of the winner
-  static constexpr int NPLANES = G ? 18 : 15;
+  // with grad, after B1: adjoint coefficients of the winner as 5 float2 planes
+  // (A0,A1) (B0,B1) (C0,C1) (A2,B2) (C2,-)  [letter = coefficient, digit = channel]
+  static constexpr int P_COEF = 9;
+  static constexpr int NPLANES = G ? (CDP_OPT_PACKED_GATHER ? 19 : 18) : 15;
   static constexpr size_t SMEM_BYTES = (size_t)NPLANES * RN * sizeof(float) + ((RN + 15) & ~15);
 };
 
@@ -358,10 +366,20 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
             float A, B, C;
             // means in the tile-centred frame are mxc + cs, myc + cs
             cdp_ssim_coeffs_abc(t, mxc + cs, myc + cs, A, B, C);
+            // packed layout: see CdpTileGeom::P_COEF
+#if CDP_OPT_PACKED_GATHER
+            float* cf = sm + (size_t)Geo::P_COEF * Geo::RN + 2 * (r00 + o * Geo::RW);
+            if (ch < 2) {
+              cf[0 * 2 * Geo::RN + ch] = A; cf[1 * 2 * Geo::RN + ch] = B; cf[2 * 2 * Geo::RN + ch] = C;
+            } else {
+              cf[3 * 2 * Geo::RN + 0] = A; cf[3 * 2 * Geo::RN + 1] = B; cf[4 * 2 * Geo::RN + 0] = C;
+            }
+#else
             const int ridx = r00 + o * Geo::RW;
             sm[(size_t)(Geo::P_COEF + ch * 3 + 0) * Geo::RN + ridx] = A;
             sm[(size_t)(Geo::P_COEF + ch * 3 + 1) * Geo::RN + ridx] = B;
             sm[(size_t)(Geo::P_COEF + ch * 3 + 2) * Geo::RN + ridx] = C;
+#endif
           }
         }
       }
@@ -392,7 +410,8 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
     int kn[9];
     float mn[9];
     bool any0 = kown == 0, any1 = kown == 1;
-    if (px >= 2 && px <= W - 3 && py >= 2 && py <= H - 3) {  // no reflection in reach: weights are 1
+    const bool interior = px >= 2 && px <= W - 3 && py >= 2 && py <= H - 3;
+    if (interior) {  // no reflection in reach: weights are 1
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
         mn[j] = 1.f;
@@ -420,6 +439,34 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
 #pragma unroll 1
       for (int k = 0; k < 2; ++k) {
         if (!(k == 0 ? any0 : any1)) continue;
+#if CDP_OPT_PACKED_GATHER
+        // masked, reflection-weighted 3x3 sums of the packed coefficient planes
+        float2 acc[5];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) acc[f] = cdp_set2(0.f);
+        const float2* cf = reinterpret_cast<const float2*>(sm + (size_t)Geo::P_COEF * Geo::RN);
+        if (interior) {
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            if (kn[j] != k) continue;
+            const int n = ridx + (j / 3 - 1) * Geo::RW + (j % 3 - 1);
+#pragma unroll
+            for (int f = 0; f < 5; ++f) acc[f] = cdp_add2(acc[f], cf[(size_t)f * Geo::RN + n]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            if (kn[j] != k) continue;
+            const int n = ridx + (j / 3 - 1) * Geo::RW + (j % 3 - 1);
+            const float2 m2 = cdp_set2(mn[j]);
+#pragma unroll
+            for (int f = 0; f < 5; ++f) acc[f] = cdp_fma2(cf[(size_t)f * Geo::RN + n], m2, acc[f]);
+          }
+        }
+        const float sa[3] = {acc[0].x, acc[0].y, acc[3].x};
+        const float sb[3] = {acc[1].x, acc[1].y, acc[3].y};
+        const float sc[3] = {acc[2].x, acc[2].y, acc[4].x};
+#else
         float sa[3] = {0.f, 0.f, 0.f}, sb[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
@@ -432,6 +479,7 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
             sc[ch] += mn[j] * sm[(size_t)(Geo::P_COEF + ch * 3 + 2) * Geo::RN + n];
           }
         }
+#endif
         // (the source loop is rolled to keep the code small: no register arrays indexed by k)
         CdpPose T;
         cdp_load_pose((k == 0 ? p.pose0 : p.pose1) + (size_t)c.b * 16, T);
@@ -454,6 +502,10 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
           gix += gw * dix;
           giy += gw * diy;
         }
+#if CDP_OPT_DIRECT_DT
+        if (k == 0) cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dT, nullptr);
+        else cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dT + 16, nullptr);
+#else
         float dTk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) dTk[i] = 0.f;
@@ -465,6 +517,7 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
 #pragma unroll
           for (int i = 0; i < 16; ++i) dT[16 + i] += dTk[i];
         }
+#endif
       }
     }
     lv.gdepth[(size_t)c.b * plane + py * W + px] = gd;
