@@ -215,49 +215,40 @@ __global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_consta
     for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
 }
 
-__global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_sum_kernel(const CdpSmoothParams p) {
-  __shared__ float red[CDP_SMOOTH_THREADS / 32];
-  float v[1] = {cdp_smooth_sum_thread(p, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x)};
-  cdp_block_reduce_store(v, red, p.part_sum + blockIdx.y * CDP_SMOOTH_BLOCKS + blockIdx.x);
-}
-
 __global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_main_kernel(const CdpSmoothParams p) {
-  __shared__ float red[3 * CDP_SMOOTH_THREADS / 32];
-  __shared__ float mean_s;
-  if (threadIdx.x < 32) {
-    const double tot = cdp_warp_butterfly(cdp_smooth_lane_sum(p.part_sum + (size_t)blockIdx.y * CDP_SMOOTH_BLOCKS, 1, threadIdx.x));
-    if (threadIdx.x == 0) mean_s = (float)(tot / (double)((size_t)p.H * p.W));
-  }
+  __shared__ float sm[CDP_SMOOTH_SMEM_FLOATS];
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  cdp_smooth_phase_load(p, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, sm);
   __syncthreads();
-  float v[3] = {0.f, 0.f, 0.f};
-  cdp_smooth_main_thread(p, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, mean_s, v);
-  cdp_block_reduce_store(v, red, p.part_main + ((size_t)blockIdx.y * CDP_SMOOTH_BLOCKS + blockIdx.x) * 4);
+  cdp_smooth_phase_edges(p, blockIdx.x, threadIdx.x, blockDim.x, sm, v);
+  __syncthreads();
+  cdp_smooth_phase_grad(p, blockIdx.y, blockIdx.x, threadIdx.x, blockDim.x, sm, v);
+  __syncthreads();  // staged planes are dead: reuse them for the reduction
+  cdp_block_reduce_store(v, sm, p.part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4);
 }
 
-// one warp per image (fixed order), then warp 0 combines the images in index order
+// one warp per image (fixed order), then thread 0 combines the images in index order
 __global__ void __launch_bounds__(1024) cdp_smooth_finalize_kernel(const CdpSmoothParams p) {
-  __shared__ double sxs[CDP_MAX_BATCH_PER_LAUNCH], sys[CDP_MAX_BATCH_PER_LAUNCH];
+  __shared__ double contrib[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  double sx_tot = 0.0, sy_tot = 0.0;
+  const int nb = p.tiles_x * p.tiles_y;
+  double loss = 0.0;
   for (int b0 = 0; b0 < p.B; b0 += nwarps) {
     const int b = b0 + warp;
     if (b < p.B) {
-      const float* rec = p.part_main + (size_t)b * CDP_SMOOTH_BLOCKS * 4;
-      const double sx = cdp_warp_butterfly(cdp_smooth_lane_sum(rec + 0, 4, lane));
-      const double sy = cdp_warp_butterfly(cdp_smooth_lane_sum(rec + 1, 4, lane));
-      const double gd = cdp_warp_butterfly(cdp_smooth_lane_sum(rec + 2, 4, lane));
-      const double ps = cdp_warp_butterfly(cdp_smooth_lane_sum(p.part_sum + (size_t)b * CDP_SMOOTH_BLOCKS, 1, lane));
-      if (lane == 0) {
-        sxs[warp] = sx; sys[warp] = sy;
-        if (p.with_grad) cdp_smooth_finalize_image(p, b, gd, ps);
-      }
+      const float* rec = p.part + (size_t)b * nb * 4;
+      const double s0 = cdp_warp_butterfly(cdp_lane_sum(rec + 0, nb, 4, lane));
+      const double s1 = cdp_warp_butterfly(cdp_lane_sum(rec + 1, nb, 4, lane));
+      const double s2 = cdp_warp_butterfly(cdp_lane_sum(rec + 2, nb, 4, lane));
+      const double s3 = cdp_warp_butterfly(cdp_lane_sum(rec + 3, nb, 4, lane));
+      if (lane == 0) contrib[warp] = cdp_smooth_finalize_image(p, b, s0, s1, s2, s3);
     }
     __syncthreads();
     if (threadIdx.x == 0)
-      for (int w = 0; w < nwarps && b0 + w < p.B; ++w) { sx_tot += sxs[w]; sy_tot += sys[w]; }
+      for (int w = 0; w < nwarps && b0 + w < p.B; ++w) loss += contrib[w];
     __syncthreads();
   }
-  if (threadIdx.x == 0) cdp_smooth_finalize_loss(p, sx_tot, sy_tot);
+  if (threadIdx.x == 0) p.loss[0] = (float)loss;
 }
 
 __global__ void __launch_bounds__(256)
@@ -460,9 +451,7 @@ extern "C" int cdp_smooth_fwd(const float* image, const float* disp, int32_t bat
   float* saved = static_cast<float*>(saved_);
   CdpSmoothParams p;
   cdp_fill_smooth_params(image, disp, batch, height, width, with_grad, loss, saved, &p);
-  dim3 grid(CDP_SMOOTH_BLOCKS, batch);
-  { ProfScope prof_(CDP_KERNEL_SMOOTH_SUM, stream); cdp_smooth_sum_kernel<<<grid, CDP_SMOOTH_THREADS, 0, stream>>>(p); }
-  CDP_LAUNCH_CHECK("cdp_smooth_sum_kernel");
+  dim3 grid(p.tiles_x * p.tiles_y, batch);
   { ProfScope prof_(CDP_KERNEL_SMOOTH_MAIN, stream); cdp_smooth_main_kernel<<<grid, CDP_SMOOTH_THREADS, 0, stream>>>(p); }
   CDP_LAUNCH_CHECK("cdp_smooth_main_kernel");
   { ProfScope prof_(CDP_KERNEL_SMOOTH_FINALIZE, stream); cdp_smooth_finalize_kernel<<<1, 1024, 0, stream>>>(p); }

@@ -156,137 +156,152 @@ CDP_HD void cdp_pose_grad_scale(const CdpDepthGradParams& p, int i) {  // i in [
 // ==========================================================================================
 // 5. Edge-aware smoothness (algos/depth.py:58-107).
 // ==========================================================================================
-#define CDP_SMOOTH_BLOCKS 256  // blocks per image for the two reduction passes
+// |d^(p) - d^(q)| = |disp(p) - disp(q)| / (mean + eps): the per-image normalisation factors out of
+// both sums, so ONE pass over the image produces the un-normalised edge sums, the un-normalised
+// gradient field g and the disparity sum; the normalisation is applied in the tiny finalize step
+// (loss) and in the backward kernel (gradient).  Each block handles a 64x16 pixel tile staged in
+// shared memory with a one-pixel ring, so every edge weight exp(-mean_c |dI|) is evaluated once.
+#define CDP_SMOOTH_TX 64
+#define CDP_SMOOTH_TY 16
 #define CDP_SMOOTH_THREADS 256
+#define CDP_SMOOTH_RW (CDP_SMOOTH_TX + 2)
+#define CDP_SMOOTH_RH (CDP_SMOOTH_TY + 2)
+#define CDP_SMOOTH_RN (CDP_SMOOTH_RW * CDP_SMOOTH_RH)
+#define CDP_SMOOTH_SMEM_FLOATS (6 * CDP_SMOOTH_RN)  // image x3, disp, hx, hy
 
 struct CdpSmoothParams {
   const float* image;  // [B,3,H,W]
   const float* disp;   // [B,1,H,W]
-  float* g;            // [B,H,W]   d loss / d normalised disparity (unit)
-  float* part_sum;     // [B][CDP_SMOOTH_BLOCKS]          partial sums of disp
-  float* part_main;    // [B][CDP_SMOOTH_BLOCKS][4]       sum tx, sum ty, sum g*disp
-  float* scal;         // [B][2]  a_b = 1/(mean+eps), c_b = sum(g*disp) a_b^2 / (H W)
+  float* g;            // [B,H,W]   un-normalised d loss / d normalised disparity
+  float* part;         // [B][tiles][4]  sum disp, sum |dx disp| e_x, sum |dy disp| e_y, sum g*disp
+  float* scal;         // [B][2]  |a_b|, sign(a_b) * sum(g*disp) a_b^2 / (H W),  a_b = 1/(mean_b + eps)
   float* loss;         // [1]
   int32_t B, H, W, with_grad;
+  int32_t tiles_x, tiles_y;
 };
 
-// chunk of pixels handled by block `blk` of an image
-CDP_HD void cdp_smooth_chunk(int HW, int blk, int& lo, int& hi) {
-  const int per = (HW + CDP_SMOOTH_BLOCKS - 1) / CDP_SMOOTH_BLOCKS;
-  lo = blk * per;
-  hi = lo + per < HW ? lo + per : HW;
-  if (lo > HW) lo = HW;
+CDP_HD float cdp_sign(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+
+// phase 1: stage image and disparity of the tile + ring (zeros outside the image)
+CDP_HD void cdp_smooth_phase_load(const CdpSmoothParams& p, int b, int tile, int tid, int nthreads, float* sm) {
+  const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+  const int x0 = tx * CDP_SMOOTH_TX - 1, y0 = ty * CDP_SMOOTH_TY - 1;
+  const size_t plane = (size_t)p.H * p.W;
+  const float* img = p.image + (size_t)b * 3 * plane;
+  const float* d = p.disp + (size_t)b * plane;
+  for (int idx = tid; idx < CDP_SMOOTH_RN; idx += nthreads) {
+    const int ry = idx / CDP_SMOOTH_RW, rx = idx - ry * CDP_SMOOTH_RW;
+    const int x = x0 + rx, y = y0 + ry;
+    const bool ok = x >= 0 && x < p.W && y >= 0 && y < p.H;
+    const int o = y * p.W + x;
+    sm[0 * CDP_SMOOTH_RN + idx] = ok ? CDP_LDG(img + o) : 0.f;
+    sm[1 * CDP_SMOOTH_RN + idx] = ok ? CDP_LDG(img + plane + o) : 0.f;
+    sm[2 * CDP_SMOOTH_RN + idx] = ok ? CDP_LDG(img + 2 * plane + o) : 0.f;
+    sm[3 * CDP_SMOOTH_RN + idx] = ok ? CDP_LDG(d + o) : 0.f;
+  }
 }
 
-CDP_HD float cdp_smooth_sum_thread(const CdpSmoothParams& p, int b, int blk, int tid, int nthreads) {
-  int lo, hi;
-  cdp_smooth_chunk(p.H * p.W, blk, lo, hi);
-  const float* d = p.disp + (size_t)b * p.H * p.W;
-  float acc = 0.f;
-  for (int i = lo + tid; i < hi; i += nthreads) acc += CDP_LDG(d + i);
-  return acc;
+// phase 2: signed edge weights hx = sign(disp(p) - disp(p+1x)) e_x(p), hy likewise, for every
+// staged position that has its right / lower neighbour staged; per-thread loss sums over the
+// tile proper: acc[1] += |dx disp| e_x, acc[2] += |dy disp| e_y   (algos/depth.py:79-87)
+CDP_HD void cdp_smooth_phase_edges(const CdpSmoothParams& p, int tile, int tid, int nthreads, float* sm, float acc[4]) {
+  const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+  const int x0 = tx * CDP_SMOOTH_TX - 1, y0 = ty * CDP_SMOOTH_TY - 1;
+  const float third = 1.0f / 3.0f;
+  for (int idx = tid; idx < CDP_SMOOTH_RN; idx += nthreads) {
+    const int ry = idx / CDP_SMOOTH_RW, rx = idx - ry * CDP_SMOOTH_RW;
+    const int x = x0 + rx, y = y0 + ry;
+    const bool ok = x >= 0 && x < p.W && y >= 0 && y < p.H;
+    const bool own = ok && rx >= 1 && rx <= CDP_SMOOTH_TX && ry >= 1 && ry <= CDP_SMOOTH_TY;
+    float hx = 0.f, hy = 0.f;
+    const float dc = sm[3 * CDP_SMOOTH_RN + idx];
+    if (ok && rx + 1 < CDP_SMOOTH_RW && x + 1 < p.W) {
+      const float s = fabsf(sm[idx] - sm[idx + 1]) + fabsf(sm[CDP_SMOOTH_RN + idx] - sm[CDP_SMOOTH_RN + idx + 1]) +
+                      fabsf(sm[2 * CDP_SMOOTH_RN + idx] - sm[2 * CDP_SMOOTH_RN + idx + 1]);
+      const float e = cdp_exp(-(s * third));
+      const float diff = dc - sm[3 * CDP_SMOOTH_RN + idx + 1];
+      hx = cdp_sign(diff) * e;
+      if (own) acc[1] += fabsf(diff) * e;
+    }
+    if (ok && ry + 1 < CDP_SMOOTH_RH && y + 1 < p.H) {
+      const int dn = idx + CDP_SMOOTH_RW;
+      const float s = fabsf(sm[idx] - sm[dn]) + fabsf(sm[CDP_SMOOTH_RN + idx] - sm[CDP_SMOOTH_RN + dn]) +
+                      fabsf(sm[2 * CDP_SMOOTH_RN + idx] - sm[2 * CDP_SMOOTH_RN + dn]);
+      const float e = cdp_exp(-(s * third));
+      const float diff = dc - sm[3 * CDP_SMOOTH_RN + dn];
+      hy = cdp_sign(diff) * e;
+      if (own) acc[2] += fabsf(diff) * e;
+    }
+    sm[4 * CDP_SMOOTH_RN + idx] = hx;
+    sm[5 * CDP_SMOOTH_RN + idx] = hy;
+  }
 }
 
-// mean disparity of image b from the per-block partial sums, in a fixed order that one warp can
-// evaluate in parallel: lane l sums partials l, l+32, ... then lanes are combined by a butterfly
-CDP_HD double cdp_smooth_lane_sum(const float* part, int stride, int lane) {
+// phase 3: g(p) = cx (hx(p) - hx(p-1x)) + cy (hy(p) - hy(p-1y)); acc[0] += disp, acc[3] += g disp
+CDP_HD void cdp_smooth_phase_grad(const CdpSmoothParams& p, int b, int tile, int tid, int nthreads, const float* sm,
+                                  float acc[4]) {
+  const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+  const int x0 = tx * CDP_SMOOTH_TX, y0 = ty * CDP_SMOOTH_TY;
+  const float cx = 1.0f / ((float)p.B * (float)p.H * (float)(p.W - 1));
+  const float cy = 1.0f / ((float)p.B * (float)(p.H - 1) * (float)p.W);
+  for (int i = tid; i < CDP_SMOOTH_TX * CDP_SMOOTH_TY; i += nthreads) {
+    const int ly = i / CDP_SMOOTH_TX, lx = i - ly * CDP_SMOOTH_TX;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x >= p.W || y >= p.H) continue;
+    const int idx = (ly + 1) * CDP_SMOOTH_RW + lx + 1;
+    const float dv = sm[3 * CDP_SMOOTH_RN + idx];
+    acc[0] += dv;
+    if (p.with_grad) {
+      const float g = cx * (sm[4 * CDP_SMOOTH_RN + idx] - sm[4 * CDP_SMOOTH_RN + idx - 1]) +
+                      cy * (sm[5 * CDP_SMOOTH_RN + idx] - sm[5 * CDP_SMOOTH_RN + idx - CDP_SMOOTH_RW]);
+      p.g[(size_t)b * p.H * p.W + (size_t)y * p.W + x] = g;
+      acc[3] += g * dv;
+    }
+  }
+}
+
+// Fixed-order combination of per-block records that one warp can evaluate in parallel: lane l sums
+// records l, l+32, ...; lanes are combined by a butterfly (cdp_butterfly_host = same order).
+CDP_HD double cdp_lane_sum(const float* part, int count, int stride, int lane) {
   double acc = 0.0;
-  for (int i = lane; i < CDP_SMOOTH_BLOCKS; i += 32) acc += (double)part[(size_t)i * stride];
+  for (int i = lane; i < count; i += 32) acc += (double)part[(size_t)i * stride];
   return acc;
 }
-CDP_HD double cdp_butterfly_host(double v[32]) {  // same combination order as the shuffle tree
+CDP_HD double cdp_butterfly_host(double v[32]) {
   for (int off = 16; off > 0; off >>= 1)
     for (int l = 0; l < off; ++l) v[l] += v[l + off];
   return v[0];
 }
-CDP_HD float cdp_smooth_mean(const CdpSmoothParams& p, int b) {  // host / single-thread form
-  double v[32];
-  for (int l = 0; l < 32; ++l) v[l] = cdp_smooth_lane_sum(p.part_sum + (size_t)b * CDP_SMOOTH_BLOCKS, 1, l);
-  return (float)(cdp_butterfly_host(v) / (double)((size_t)p.H * p.W));
-}
 
-CDP_HD float cdp_edge_weight(const float* img, size_t plane, int a, int bidx) {
-  const float s = fabsf(CDP_LDG(img + a) - CDP_LDG(img + bidx)) +
-                  fabsf(CDP_LDG(img + plane + a) - CDP_LDG(img + plane + bidx)) +
-                  fabsf(CDP_LDG(img + 2 * plane + a) - CDP_LDG(img + 2 * plane + bidx));
-  return cdp_exp(-(s * (1.0f / 3.0f)));
-}
-
-CDP_HD float cdp_sign(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
-
-// per-thread partial sums over this block's chunk: acc[0] += sum tx, acc[1] += sum ty,
-// acc[2] += sum g*disp; writes g.
-CDP_HD void cdp_smooth_main_thread(const CdpSmoothParams& p, int b, int blk, int tid, int nthreads,
-                                   float mean, float acc[3]) {
-  const int W = p.W, H = p.H;
-  int lo, hi;
-  cdp_smooth_chunk(H * W, blk, lo, hi);
-  const size_t plane = (size_t)H * W;
-  const float* d = p.disp + (size_t)b * plane;
-  const float* img = p.image + (size_t)b * 3 * plane;
-  const float iden = 1.0f / (mean + 1e-7f);
-  const float cx = 1.0f / ((float)p.B * (float)H * (float)(W - 1));
-  const float cy = 1.0f / ((float)p.B * (float)(H - 1) * (float)W);
-  for (int i = lo + tid; i < hi; i += nthreads) {
-    const int y = i / W, x = i - y * W;
-    const float raw = CDP_LDG(d + i);
-    const float dc = raw * iden;
-    float g = 0.f;
-    if (x < W - 1) {
-      const float diff = dc - CDP_LDG(d + i + 1) * iden;
-      const float e = cdp_edge_weight(img, plane, i, i + 1);
-      acc[0] += fabsf(diff) * e;
-      g += cdp_sign(diff) * e * cx;
-    }
-    if (y < H - 1) {
-      const float diff = dc - CDP_LDG(d + i + W) * iden;
-      const float e = cdp_edge_weight(img, plane, i, i + W);
-      acc[1] += fabsf(diff) * e;
-      g += cdp_sign(diff) * e * cy;
-    }
-    if (p.with_grad) {
-      if (x > 0) {
-        const float diff = CDP_LDG(d + i - 1) * iden - dc;
-        g -= cdp_sign(diff) * cdp_edge_weight(img, plane, i - 1, i) * cx;
-      }
-      if (y > 0) {
-        const float diff = CDP_LDG(d + i - W) * iden - dc;
-        g -= cdp_sign(diff) * cdp_edge_weight(img, plane, i - W, i) * cy;
-      }
-      p.g[(size_t)b * plane + i] = g;
-      acc[2] += g * raw;
-    }
+// per image: normalisation scalars; returns the image's contribution to the loss
+CDP_HD double cdp_smooth_finalize_image(const CdpSmoothParams& p, int b, double sum_disp, double sx, double sy,
+                                        double gd) {
+  const double hw = (double)((size_t)p.H * p.W);
+  const float mean = (float)(sum_disp / hw);
+  const double a = 1.0 / (double)(mean + 1e-7f);  // mean_disparity + 1e-7, algos/depth.py:104-105
+  const double aa = a < 0 ? -a : a;
+  if (p.with_grad) {
+    p.scal[b * 2 + 0] = (float)aa;
+    p.scal[b * 2 + 1] = (float)((a < 0 ? -1.0 : 1.0) * gd * a * a / hw);
   }
+  const double nx = (double)p.B * p.H * (p.W - 1), ny = (double)p.B * (p.H - 1) * p.W;
+  return aa * (sx / nx + sy / ny);
 }
 
-// Combine the block partials (fixed order).  Written per (image, quantity) so that one warp can
-// evaluate each sum in parallel: quantity 0 = sum tx, 1 = sum ty, 2 = sum g*disp.
-CDP_HD void cdp_smooth_finalize_image(const CdpSmoothParams& p, int b, double gd_sum, double part_sum) {
-  const float mean = (float)(part_sum / (double)((size_t)p.H * p.W));
-  const float den = mean + 1e-7f;
-  const double a = 1.0 / (double)den;
-  p.scal[b * 2 + 0] = (float)a;
-  p.scal[b * 2 + 1] = (float)(gd_sum * a * a / (double)((size_t)p.H * p.W));
-}
-CDP_HD void cdp_smooth_finalize_loss(const CdpSmoothParams& p, double sx, double sy) {
-  const double nx = (double)p.B * p.H * (p.W - 1), ny = (double)p.B * (p.H - 1) * p.W;
-  p.loss[0] = (float)(sx / nx) + (float)(sy / ny);
-}
 // host / single-thread form of the whole finalize step
 CDP_HD void cdp_smooth_finalize(const CdpSmoothParams& p) {
-  double sx = 0.0, sy = 0.0;
+  const int nb = p.tiles_x * p.tiles_y;
+  double loss = 0.0;
   for (int b = 0; b < p.B; ++b) {
-    double v[3][32], ps[32];
-    for (int l = 0; l < 32; ++l) {
-      for (int q = 0; q < 3; ++q) v[q][l] = cdp_smooth_lane_sum(p.part_main + (size_t)b * CDP_SMOOTH_BLOCKS * 4 + q, 4, l);
-      ps[l] = cdp_smooth_lane_sum(p.part_sum + (size_t)b * CDP_SMOOTH_BLOCKS, 1, l);
+    double v[4][32];
+    for (int q = 0; q < 4; ++q) {
+      for (int l = 0; l < 32; ++l) v[q][l] = cdp_lane_sum(p.part + ((size_t)b * nb) * 4 + q, nb, 4, l);
     }
-    sx += cdp_butterfly_host(v[0]);
-    sy += cdp_butterfly_host(v[1]);
-    const double gd = cdp_butterfly_host(v[2]), psum = cdp_butterfly_host(ps);
-    if (p.with_grad) cdp_smooth_finalize_image(p, b, gd, psum);
+    const double s0 = cdp_butterfly_host(v[0]), s1 = cdp_butterfly_host(v[1]);
+    const double s2 = cdp_butterfly_host(v[2]), s3 = cdp_butterfly_host(v[3]);
+    loss += cdp_smooth_finalize_image(p, b, s0, s1, s2, s3);
   }
-  cdp_smooth_finalize_loss(p, sx, sy);
+  p.loss[0] = (float)loss;
 }
 
 CDP_HD void cdp_smooth_bwd_pixel(const float* g, const float* scal, const float* grad_loss, int b,

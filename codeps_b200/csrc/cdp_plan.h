@@ -93,13 +93,14 @@ static inline bool cdp_build_resize_tables(const CdpPlan& plan, void* host_out, 
   return true;
 }
 
-struct CdpSmoothLayout { size_t g, part_sum, part_main, scal, total; };
+struct CdpSmoothLayout { size_t g, part, scal, total; int tiles_x, tiles_y; };
 static inline CdpSmoothLayout cdp_smooth_layout(int32_t B, int32_t H, int32_t W) {
   CdpSmoothLayout l;
+  l.tiles_x = (W + CDP_SMOOTH_TX - 1) / CDP_SMOOTH_TX;
+  l.tiles_y = (H + CDP_SMOOTH_TY - 1) / CDP_SMOOTH_TY;
   size_t o = 0;
   l.g = o; o += cdp_align_floats((size_t)B * H * W);
-  l.part_sum = o; o += cdp_align_floats((size_t)B * CDP_SMOOTH_BLOCKS);
-  l.part_main = o; o += cdp_align_floats((size_t)B * CDP_SMOOTH_BLOCKS * 4);
+  l.part = o; o += cdp_align_floats((size_t)B * l.tiles_x * l.tiles_y * 4);
   l.scal = o; o += cdp_align_floats((size_t)B * 2);
   l.total = o;
   return l;
@@ -108,9 +109,10 @@ static inline CdpSmoothLayout cdp_smooth_layout(int32_t B, int32_t H, int32_t W)
 static inline void cdp_fill_smooth_params(const float* image, const float* disp, int B, int H, int W, int with_grad,
                                           float* loss, float* saved, CdpSmoothParams* p) {
   const CdpSmoothLayout l = cdp_smooth_layout(B, H, W);
-  p->image = image; p->disp = disp; p->g = saved + l.g; p->part_sum = saved + l.part_sum;
-  p->part_main = saved + l.part_main; p->scal = saved + l.scal; p->loss = loss;
+  p->image = image; p->disp = disp; p->g = saved + l.g; p->part = saved + l.part;
+  p->scal = saved + l.scal; p->loss = loss;
   p->B = B; p->H = H; p->W = W; p->with_grad = with_grad;
+  p->tiles_x = l.tiles_x; p->tiles_y = l.tiles_y;
 }
 
 static inline void cdp_fill_warp_params(CdpWarpParams* p, const float* src, int C, const float* depth,

@@ -202,7 +202,7 @@ class _Smoothness(torch.autograd.Function):
         with torch.cuda.device(device):
             check(lib.cdp_smooth_fwd(_ptr(image), _ptr(disp), b, h, w, int(need_grad), _ptr(loss),
                                      _ptr(saved), saved.numel(), _stream(device)), "cdp_smooth_fwd")
-        _LAUNCHES["count"] += 3
+        _LAUNCHES["count"] += 2
         ctx.saved_buf = saved if need_grad else None
         ctx.shape = (b, h, w)
         return loss[0]

@@ -103,25 +103,20 @@ EMU_API int emu_smooth_fwd(const float* image, const float* disp, int32_t B, int
                            float* loss, void* saved) {
   CdpSmoothParams p;
   cdp_fill_smooth_params(image, disp, B, H, W, with_grad, loss, static_cast<float*>(saved), &p);
-  const int nt = CDP_SMOOTH_THREADS;
+  const int nt = CDP_SMOOTH_THREADS, nb = p.tiles_x * p.tiles_y;
+  std::vector<float> sm(CDP_SMOOTH_SMEM_FLOATS);
   for (int b = 0; b < B; ++b)
-    for (int blk = 0; blk < CDP_SMOOTH_BLOCKS; ++blk) {
-      float acc = 0.f;
-      for (int t = 0; t < nt; ++t) acc += cdp_smooth_sum_thread(p, b, blk, t, nt);
-      p.part_sum[b * CDP_SMOOTH_BLOCKS + blk] = acc;
-    }
-  for (int b = 0; b < B; ++b) {
-    const float mean = cdp_smooth_mean(p, b);
-    for (int blk = 0; blk < CDP_SMOOTH_BLOCKS; ++blk) {
-      float tot[3] = {0.f, 0.f, 0.f};
-      for (int t = 0; t < nt; ++t) {
-        float v[3] = {0.f, 0.f, 0.f};
-        cdp_smooth_main_thread(p, b, blk, t, nt, mean, v);
-        for (int j = 0; j < 3; ++j) tot[j] += v[j];
+    for (int tile = 0; tile < nb; ++tile) {
+      std::vector<float> v((size_t)nt * 4, 0.f);
+      for (int t = 0; t < nt; ++t) cdp_smooth_phase_load(p, b, tile, t, nt, sm.data());
+      for (int t = 0; t < nt; ++t) cdp_smooth_phase_edges(p, tile, t, nt, sm.data(), &v[(size_t)t * 4]);
+      for (int t = 0; t < nt; ++t) cdp_smooth_phase_grad(p, b, tile, t, nt, sm.data(), &v[(size_t)t * 4]);
+      for (int j = 0; j < 4; ++j) {
+        float tot = 0.f;
+        for (int t = 0; t < nt; ++t) tot += v[(size_t)t * 4 + j];
+        p.part[((size_t)b * nb + tile) * 4 + j] = tot;
       }
-      for (int j = 0; j < 3; ++j) p.part_main[((size_t)b * CDP_SMOOTH_BLOCKS + blk) * 4 + j] = tot[j];
     }
-  }
   cdp_smooth_finalize(p);
   return CDP_OK;
 }
