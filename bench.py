@@ -229,71 +229,83 @@ def main():
     w_recon = torch.tensor(RECON_WEIGHT, device=dev)
     w_smooth = torch.tensor(SMOOTH_WEIGHT, device=dev)
 
-    def step(i):
-        """fwd + bwd on resident input set i; returns (recon, smooth, grads)."""
-        ds = dev_sets[i]
-        # fresh autograd leaves every step (views, no copies), created on the launching stream
-        depth, disp = ds.depth.detach().requires_grad_(True), ds.disp.detach().requires_grad_(True)
-        p0, p1 = ds.poses[0].detach().requires_grad_(True), ds.poses[1].detach().requires_grad_(True)
-        recon = recon_fn(cams[i], ds.images, depth, (p0, p1))
-        smooth = smooth_fn(ds.images[0], disp)
-        # the caller's  loss = 10*recon + 0.001*smooth; loss.backward()  (train_codeps.py:102-107)
-        grads = torch.autograd.grad([recon, smooth], [depth, disp, p0, p1], grad_outputs=[w_recon, w_smooth])
-        return recon, smooth, grads
+    def make_step(loss_fn):
+        def step(i):
+            """fwd + bwd on resident input set i; returns (recon, smooth, grads)."""
+            ds = dev_sets[i]
+            # fresh autograd leaves every step (views, no copies), created on the launching stream
+            depth, disp = ds.depth.detach().requires_grad_(True), ds.disp.detach().requires_grad_(True)
+            p0, p1 = ds.poses[0].detach().requires_grad_(True), ds.poses[1].detach().requires_grad_(True)
+            recon = loss_fn(cams[i], ds.images, depth, (p0, p1))
+            smooth = smooth_fn(ds.images[0], disp)
+            # the caller's  loss = 10*recon + 0.001*smooth; loss.backward()  (train_codeps.py:102-107)
+            grads = torch.autograd.grad([recon, smooth], [depth, disp, p0, p1], grad_outputs=[w_recon, w_smooth])
+            return recon, smooth, grads
+        return step
 
-    # eager warm-up (also sizes the allocator pools and sets kernel attributes before capture)
+    def make_runner(step_fn, use_graph):
+        """Warm up, optionally capture one CUDA graph per input set, return run(i)."""
+        for i in range(3):
+            step_fn(i % INPUT_SETS)
+        torch.cuda.synchronize()
+        if not use_graph:
+            return lambda i: step_fn(i % INPUT_SETS)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(INPUT_SETS):
+                step_fn(i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graphs, outs = [], []
+        for i in range(INPUT_SETS):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs.append(step_fn(i))
+            graphs.append(g)
+
+        def run(i):
+            graphs[i % INPUT_SETS].replay()
+            return outs[i % INPUT_SETS]
+        return run
+
+    step = make_step(recon_fn)
+    use_graph = not args.no_graph
     torch.manual_seed(1234 + rank)
-    for i in range(3):
+    for i in range(3):  # eager warm-up (sizes the allocator pools, sets kernel attributes)
         out = step(i % INPUT_SETS)
     torch.cuda.synchronize()
     launches_before = ops.launch_count()
     out = step(0)
     launches_per_step = ops.launch_count() - launches_before
     torch.cuda.synchronize()
-
-    graphs, graph_out = [], []
-    use_graph = not args.no_graph
-    if use_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for i in range(INPUT_SETS):
-                step(i)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        for i in range(INPUT_SETS):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                graph_out.append(step(i))
-            graphs.append(g)
-
-    def run_step(i):
-        if use_graph:
-            graphs[i % INPUT_SETS].replay()
-            return graph_out[i % INPUT_SETS]
-        return step(i % INPUT_SETS)
+    run_step = make_runner(step, use_graph)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- timed region: device-resident inputs
-    for i in range(max(args.warmup, 3)):
-        run_step(i)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    def timed(run, steps, sampler=None):
+        """W warm-up steps, then exactly `steps` steps between barriers; device ms, max over ranks."""
+        for i in range(max(args.warmup, 3)):
+            run(i)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        for i in range(args.steps):
-            last = run_step(i)
+        last = None
+        for i in range(steps):
+            last = run(i)
         ev1.record()
         barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), last
+
+    # ---- timed region: device-resident inputs
+    with ClockSampler(local_rank) as clocks:
+        elapsed_ms, last = timed(run_step, args.steps)
     value = n_gpus * batch * args.steps / (elapsed_ms * 1e-3)
     recon_val, smooth_val = float(last[0]), float(last[1])
 
@@ -329,6 +341,15 @@ def main():
         "path_bytes_per_triplet": a_alg,
         "path_frac": (value / n_gpus) * a_alg / 1e9 / peak,
     }
+
+    # ---- same steps with the kernel's counter-based tie-break noise instead of torch.randn per level
+    extras = {}
+    if args.noise == "torch":
+        fused_fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), NUM_SCALES, dev, noise="fused")
+        fused_ms, _ = timed(make_runner(make_step(fused_fn), use_graph), args.steps)
+        extras["value_fused_noise"] = n_gpus * batch * args.steps / (fused_ms * 1e-3)
+        extras["note"] = ("value_fused_noise: same step with ReconstructionLoss(noise='fused') -- no torch.randn "
+                          "launches / noise traffic; different random numbers than the reference's stream")
 
     # ---- end to end: host (pinned) inputs -> public classes -> loss read back on the host
     e2e = None
@@ -412,6 +433,7 @@ def main():
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "extras": extras,
             "loss": {"recon": float(checksum[0]), "smooth": float(checksum[1])},
         }
         print(json.dumps(line), flush=True)

@@ -279,3 +279,27 @@ def test_error_behaviour(cuda_device):
             gpu.camera_models(), gpu.images, gpu.depth, gpu.poses)
     with pytest.raises(RuntimeError, match="CUDA only"):
         codeps_b200.EdgeAwareSmoothnessLoss()(tb.images[0], tb.disp)
+
+
+@pytest.mark.parametrize("w,h,scales", [(32, 32, 5), (40, 18, 4), (34, 66, 3)])
+def test_tiny_and_ragged_sizes(w, h, scales, cuda_device):
+    """Coarsest level down to 2x2 (reflection padding of a 2-pixel axis), sizes that are not
+    multiples of the tile, single-tile images."""
+    tb = make_batch(2, w, h, (0.9 * w, 0.95 * w, 0.5 * w, 0.5 * h), seed=31, shift_px=1, flip_every_other=True)
+    noise = po.draw_noise(2, w, h, scales, seed=8)
+    inp = dict(images=tb.images, depth=tb.depth, disp=tb.disp, poses=tb.poses, intrinsics=tb.intrinsics.numpy())
+    out = run_cuda(inp, w, h, scales, cuda_device, noise)
+    cams = cams_from(inp["intrinsics"], w, h)
+    k_levels = codeps_b200.ReconstructionLoss(w, h, None, scales, "cpu")._level_intrinsics(cams)
+    ref = po.loss_and_grads(inp["intrinsics"], tb.images, tb.depth, tb.disp, tb.poses, noise, scales,
+                            dtype=torch.float64, level_intrinsics=list(k_levels))
+    assert_loss_close(out["recon"], ref["recon"], "recon")
+    assert_loss_close(out["smooth"], ref["smooth"], "smooth")
+    for s in range(scales):
+        top2 = torch.sort(ref["candidates"][s], dim=1).values[:, :2]
+        decided = (top2[:, 1] - top2[:, 0]) > 1e-6
+        assert not ((out["argmin"][s] != ref["argmin"][s]) & decided).any()
+    inp["noise"] = noise
+    print(check_photo_grads(out, inp, scales, f"{w}x{h}", level_intrinsics=list(k_levels), max_masked_frac=0.6,
+                            pose_rtol=1e-3))
+    assert_grad_close_masked(out["grad_disp"], ref["grad_disp"], smooth_sign_shadow(tb.disp), "dL/d disp")

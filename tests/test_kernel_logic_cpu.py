@@ -109,3 +109,27 @@ def test_emulated_object_motion_warp():
     assert_grad_close(gd, depth.grad, "motion warp dL/d depth")
     assert_grad_close(gp, pose.grad, "motion warp dL/dT")
     assert_grad_close(gm, mo.grad, "motion warp dL/d motion")
+
+
+@pytest.mark.parametrize("w,h,scales", [(32, 32, 5), (40, 18, 4), (34, 66, 3)])
+def test_emulated_tiny_and_ragged_sizes(w, h, scales):
+    """Coarsest level down to 2x2 (reflection padding of a 2-pixel axis), sizes that are not
+    multiples of the tile, single-tile images."""
+    from codeps_b200 import synthetic
+    import codeps_b200
+    from helpers import check_photo_grads
+    tb = synthetic.make_batch(2, w, h, (0.9 * w, 0.95 * w, 0.5 * w, 0.5 * h), seed=31, shift_px=1, flip_every_other=True)
+    noise = po.draw_noise(2, w, h, scales, seed=8)
+    k = codeps_b200.ReconstructionLoss(w, h, None, scales, "cpu")._level_intrinsics(tb.camera_models())
+    out = emu.photo(k, tb.images, tb.depth, tb.poses, noise, scales)
+    ref = po.loss_and_grads(tb.intrinsics.numpy(), tb.images, tb.depth, tb.disp, tb.poses, noise, scales,
+                            dtype=torch.float64, level_intrinsics=list(k))
+    assert_loss_close(out["recon"], ref["recon"], "recon")
+    for s in range(scales):
+        top2 = torch.sort(ref["candidates"][s], dim=1).values[:, :2]
+        decided = (top2[:, 1] - top2[:, 0]) > 1e-6
+        assert not ((out["argmin"][s] != ref["argmin"][s]) & decided).any()
+    inp = dict(intrinsics=tb.intrinsics.numpy(), images=tb.images, depth=tb.depth, disp=tb.disp, poses=tb.poses, noise=noise)
+    check_photo_grads(out, inp, scales, f"{w}x{h}", level_intrinsics=list(k), max_masked_frac=0.6, pose_rtol=1e-3)
+    sm = emu.smooth(tb.images[0], tb.disp)
+    assert_loss_close(sm["smooth"], ref["smooth"], "smooth")
