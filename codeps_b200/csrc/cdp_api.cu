@@ -208,10 +208,9 @@ __device__ __forceinline__ double cdp_warp_butterfly(double v) {  // same order 
 }
 
 __global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_constant__ CdpDepthGradParams p) {
-  const int pair = blockIdx.x * blockDim.x + threadIdx.x;  // two horizontally adjacent pixels
-  const int pairs_per_row = (p.W + 1) >> 1;
-  if (pair < p.H * pairs_per_row) cdp_depth_grad_pair(p, blockIdx.y, pair / pairs_per_row, (pair % pairs_per_row) * 2);
-  if (blockIdx.x == 0 && blockIdx.y == 0)
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;  // one row per blockIdx.y: no index division
+  if (x < p.W) cdp_depth_grad_px(p, blockIdx.z, blockIdx.y, x);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
 }
 
@@ -253,8 +252,8 @@ __global__ void __launch_bounds__(1024) cdp_smooth_finalize_kernel(const CdpSmoo
 
 __global__ void __launch_bounds__(256)
 cdp_smooth_bwd_kernel(const float* g, const float* scal, const float* grad_loss, int plane, float* grad_disp) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < plane) cdp_smooth_bwd_pixel(g, scal, grad_loss, blockIdx.y, (size_t)plane, i, grad_disp);
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i < plane) cdp_smooth_bwd_run(g, scal, grad_loss, blockIdx.y, (size_t)plane, i, plane - i < 4 ? plane - i : 4, grad_disp);
 }
 
 __global__ void __launch_bounds__(256) cdp_warp_grid_kernel(const __grid_constant__ CdpWarpParams p) {
@@ -385,7 +384,7 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   if (plan.L > 1) {
     CdpPyrParams pp;
     cdp_fill_pyr_params(plan, a, &pp);
-    dim3 grid((plan.pyr_begin[plan.L] + 255) / 256, plan.B);
+    dim3 grid((pp.begin[plan.L] + 255) / 256, plan.B);
     { ProfScope prof_(CDP_KERNEL_PYRAMID, stream); cdp_pyramid_fwd_kernel<<<grid, 256, 0, stream>>>(pp); }
     CDP_LAUNCH_CHECK("cdp_pyramid_fwd_kernel");
   }
@@ -427,7 +426,7 @@ extern "C" int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32
   if (saved_bytes < plan.saved_floats * sizeof(float)) return cdp_fail(CDP_ERR_WORKSPACE, "saved too small");
   CdpDepthGradParams p;
   cdp_fill_depth_grad_params(plan, saved_, resize_tables, grad_loss, grad_depth, grad_pose0, grad_pose1, &p);
-  dim3 grid((plan.H * ((plan.W + 1) / 2) + 255) / 256, plan.B);
+  dim3 grid((plan.W + 255) / 256, plan.H, plan.B);
   { ProfScope prof_(CDP_KERNEL_DEPTH_GRAD, stream); cdp_depth_grad_kernel<<<grid, 256, 0, stream>>>(p); }
   CDP_LAUNCH_CHECK("cdp_depth_grad_kernel");
   return CDP_OK;
@@ -468,7 +467,7 @@ extern "C" int cdp_smooth_bwd(const void* saved_, size_t saved_bytes, const floa
   if (saved_bytes < l.total * sizeof(float)) return cdp_fail(CDP_ERR_WORKSPACE, "saved too small");
   const float* saved = static_cast<const float*>(saved_);
   const int plane = height * width;
-  dim3 grid((plane + 255) / 256, batch);
+  dim3 grid(((plane + 3) / 4 + 255) / 256, batch);
   { ProfScope prof_(CDP_KERNEL_SMOOTH_BWD, stream); cdp_smooth_bwd_kernel<<<grid, 256, 0, stream>>>(saved + l.g, saved + l.scal, grad_loss, plane, grad_disp); }
   CDP_LAUNCH_CHECK("cdp_smooth_bwd_kernel");
   return CDP_OK;

@@ -22,8 +22,11 @@
 #endif
 
 #if !defined(__CUDACC__)
-struct alignas(8) float2 {  // CUDA's vector type, for the host build of the kernel bodies
+struct alignas(8) float2 {  // CUDA's vector types, for the host build of the kernel bodies
   float x, y;
+};
+struct alignas(16) float4 {
+  float x, y, z, w;
 };
 #endif
 

@@ -18,8 +18,9 @@ struct CdpPyrParams {
   const CdpResizeTap* tab_x[CDP_MAX_LEVELS];
   const CdpResizeTap* tab_y[CDP_MAX_LEVELS];
   int32_t Ws[CDP_MAX_LEVELS], Hs[CDP_MAX_LEVELS];
-  int32_t begin[CDP_MAX_LEVELS + 1];   // prefix offsets of level outputs within one image
+  int32_t begin[CDP_MAX_LEVELS + 1];   // prefix offsets of level work items within one image
   int32_t W, H, L;
+  int32_t fast1;  // level 1 is an exact 2x2 mean (W % 4 == 0, H even): one item = two outputs
 };
 
 CDP_HD void cdp_pyramid_fwd_item(const CdpPyrParams& p, int b, int item) {
@@ -28,6 +29,29 @@ CDP_HD void cdp_pyramid_fwd_item(const CdpPyrParams& p, int b, int item) {
   while (s + 1 < p.L && item >= p.begin[s + 1]) ++s;
   const int local = item - p.begin[s];
   const int ws = p.Ws[s], hs = p.Hs[s];
+  if (s == 1 && p.fast1) {
+    // exact ratio 2: outputs (x, x+1) of row y are the 2x2 means of input columns 2x..2x+3, rows
+    // 2y, 2y+1 -- two 16-byte loads per channel instead of eight 4-byte ones (same arithmetic
+    // as the table path: taps weighted 1/2 horizontally, then 1/2 vertically)
+    const int half = ws >> 1;
+    const int y = local / half, x = (local - y * half) * 2;
+    const size_t in_plane = (size_t)p.W * p.H, out_plane = (size_t)ws * hs;
+    const int o0 = (2 * y) * p.W + 2 * x, o1 = o0 + p.W;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int ch = t == 3 ? 1 : 3;
+      for (int c = 0; c < ch; ++c) {
+        const float* src = p.in[t] + ((size_t)b * ch + c) * in_plane;
+        const float4 a = CDP_LDG(reinterpret_cast<const float4*>(src + o0));
+        const float4 d = CDP_LDG(reinterpret_cast<const float4*>(src + o1));
+        float2 r;
+        r.x = (a.x * 0.5f + a.y * 0.5f) * 0.5f + (d.x * 0.5f + d.y * 0.5f) * 0.5f;
+        r.y = (a.z * 0.5f + a.w * 0.5f) * 0.5f + (d.z * 0.5f + d.w * 0.5f) * 0.5f;
+        *reinterpret_cast<float2*>(p.out[t][s] + ((size_t)b * ch + c) * out_plane + y * ws + x) = r;
+      }
+    }
+    return;
+  }
   const int y = local / ws, x = local - y * ws;
   const CdpResizeTap tx = p.tab_x[s][x], ty = p.tab_y[s][y];
   const size_t in_plane = (size_t)p.W * p.H, out_plane = (size_t)ws * hs;
@@ -102,6 +126,9 @@ struct CdpDepthGradParams {
   const CdpResizeInv* inv_x[CDP_MAX_LEVELS];
   const CdpResizeInv* inv_y[CDP_MAX_LEVELS];
   int32_t Ws[CDP_MAX_LEVELS], Hs[CDP_MAX_LEVELS];
+  // level s halves the axis exactly s times (in = out << s): the resize taps are then the two
+  // middle pixels of every 2^s block with weight 1/2, and the adjoint needs no table
+  uint8_t exact_x[CDP_MAX_LEVELS], exact_y[CDP_MAX_LEVELS];
   const float* grad_loss;  // device scalar
   const float* pose_unit;  // [2][B][16]
   float* grad_depth;       // [B,1,H,W]
@@ -109,43 +136,56 @@ struct CdpDepthGradParams {
   int32_t B, H, W, L;
 };
 
-// contribution of level s to full-resolution pixel (x, y): transpose of the bilinear resize
-CDP_HD float cdp_depth_grad_level(const float* g, int ws, const CdpResizeInv& ex, const CdpResizeInv& ey) {
-  float row_a = 0.f, row_b = 0.f;
-  if (ey.ja >= 0) {
-    const float* r = g + ey.ja * ws;
-    if (ex.ja >= 0) row_a = ex.wa * CDP_LDG(r + ex.ja);
-    if (ex.jb >= 0) row_a += ex.wb * CDP_LDG(r + ex.jb);
+// references of input index i into level s along one axis: transpose of the bilinear resize taps
+CDP_HD void cdp_inv_taps(bool exact, const CdpResizeInv* table, int i, int s, int& ja, int& jb, float& wa, float& wb) {
+  if (exact) {
+    const int r = 1 << s, m = i & (r - 1);
+    ja = (m == (r >> 1) - 1 || m == (r >> 1)) ? (i >> s) : -1;
+    wa = 0.5f; jb = -1; wb = 0.f;
+  } else {
+    const CdpResizeInv e = table[i];
+    ja = e.ja; jb = e.jb; wa = e.wa; wb = e.wb;
   }
-  if (ey.jb >= 0) {
-    const float* r = g + ey.jb * ws;
-    if (ex.ja >= 0) row_b = ex.wa * CDP_LDG(r + ex.ja);
-    if (ex.jb >= 0) row_b += ex.wb * CDP_LDG(r + ex.jb);
-  }
-  return ey.wa * row_a + ey.wb * row_b;
 }
 
-// two horizontally adjacent pixels (x, x+1) of row y: they share the row taps of every level
-CDP_HD void cdp_depth_grad_pair(const CdpDepthGradParams& p, int b, int y, int x) {
+// dL/d depth at full-resolution pixel (x, y) = grad_loss * (G_0 + sum_s resize_s^T G_s)
+CDP_HD void cdp_depth_grad_px(const CdpDepthGradParams& p, int b, int y, int x) {
   const int W = p.W, pix = y * W + x;
-  const bool two = x + 1 < W;
-  const float* g0 = p.gdepth[0] + (size_t)b * W * p.H;
-  float acc0 = CDP_LDG(g0 + pix), acc1 = two ? CDP_LDG(g0 + pix + 1) : 0.f;
-  for (int s = 1; s < p.L; ++s) {
-    const CdpResizeInv ey = p.inv_y[s][y];
-    const float* g = p.gdepth[s] + (size_t)b * p.Ws[s] * p.Hs[s];
-    acc0 += cdp_depth_grad_level(g, p.Ws[s], p.inv_x[s][x], ey);
-    if (two) acc1 += cdp_depth_grad_level(g, p.Ws[s], p.inv_x[s][x + 1], ey);
+  float acc = CDP_LDG(p.gdepth[0] + (size_t)b * W * p.H + pix);
+#pragma unroll
+  for (int s = 1; s < CDP_MAX_LEVELS; ++s) {
+    if (s >= p.L) break;
+    int xa, xb, ya, yb;
+    float wxa, wxb, wya, wyb;
+    cdp_inv_taps(p.exact_y[s] != 0, p.inv_y[s], y, s, ya, yb, wya, wyb);
+    if (ya < 0 && yb < 0) continue;
+    cdp_inv_taps(p.exact_x[s] != 0, p.inv_x[s], x, s, xa, xb, wxa, wxb);
+    if (xa < 0 && xb < 0) continue;
+    const int ws = p.Ws[s];
+    const float* g = p.gdepth[s] + (size_t)b * ws * p.Hs[s];
+    float t = 0.f;
+    if (ya >= 0) {
+      const float* r = g + ya * ws;
+      float u = 0.f;
+      if (xa >= 0) u = wxa * CDP_LDG(r + xa);
+      if (xb >= 0) u += wxb * CDP_LDG(r + xb);
+      t = wya * u;
+    }
+    if (yb >= 0) {
+      const float* r = g + yb * ws;
+      float u = 0.f;
+      if (xa >= 0) u = wxa * CDP_LDG(r + xa);
+      if (xb >= 0) u += wxb * CDP_LDG(r + xb);
+      t += wyb * u;
+    }
+    acc += t;
   }
-  const float go = CDP_LDG(p.grad_loss);
-  float* out = p.grad_depth + (size_t)b * W * p.H + pix;
-  out[0] = go * acc0;
-  if (two) out[1] = go * acc1;
+  p.grad_depth[(size_t)b * W * p.H + pix] = CDP_LDG(p.grad_loss) * acc;
 }
 
-CDP_HD void cdp_depth_grad_pixel(const CdpDepthGradParams& p, int b, int pix) {  // single-pixel form
-  const int y = pix / p.W, x = pix - y * p.W;
-  if ((x & 1) == 0) cdp_depth_grad_pair(p, b, y, x);
+CDP_HD void cdp_depth_grad_pixel(const CdpDepthGradParams& p, int b, int pix) {
+  const int y = pix / p.W;
+  cdp_depth_grad_px(p, b, y, pix - y * p.W);
 }
 
 CDP_HD void cdp_pose_grad_scale(const CdpDepthGradParams& p, int i) {  // i in [0, 2*B*16)
@@ -159,10 +199,11 @@ CDP_HD void cdp_pose_grad_scale(const CdpDepthGradParams& p, int i) {  // i in [
 // |d^(p) - d^(q)| = |disp(p) - disp(q)| / (mean + eps): the per-image normalisation factors out of
 // both sums, so ONE pass over the image produces the un-normalised edge sums, the un-normalised
 // gradient field g and the disparity sum; the normalisation is applied in the tiny finalize step
-// (loss) and in the backward kernel (gradient).  Each block handles a 64x16 pixel tile staged in
-// shared memory with a one-pixel ring, so every edge weight exp(-mean_c |dI|) is evaluated once.
-#define CDP_SMOOTH_TX 64
-#define CDP_SMOOTH_TY 16
+// (loss) and in the backward kernel (gradient).  Each block handles a 62x14 pixel tile staged in
+// shared memory with a one-pixel ring (64x16 positions, no index divisions), so every edge weight
+// exp(-mean_c |dI|) is evaluated once.
+#define CDP_SMOOTH_TX 62  // staged region is 64 x 16: thread t owns column t & 63, rows (t >> 6) + 4 i
+#define CDP_SMOOTH_TY 14
 #define CDP_SMOOTH_THREADS 256
 #define CDP_SMOOTH_RW (CDP_SMOOTH_TX + 2)
 #define CDP_SMOOTH_RH (CDP_SMOOTH_TY + 2)
@@ -189,9 +230,12 @@ CDP_HD void cdp_smooth_phase_load(const CdpSmoothParams& p, int b, int tile, int
   const size_t plane = (size_t)p.H * p.W;
   const float* img = p.image + (size_t)b * 3 * plane;
   const float* d = p.disp + (size_t)b * plane;
-  for (int idx = tid; idx < CDP_SMOOTH_RN; idx += nthreads) {
-    const int ry = idx / CDP_SMOOTH_RW, rx = idx - ry * CDP_SMOOTH_RW;
-    const int x = x0 + rx, y = y0 + ry;
+  (void)nthreads;  // CDP_SMOOTH_THREADS
+  const int rx = tid & 63, x = x0 + rx;
+#pragma unroll
+  for (int i = 0; i < CDP_SMOOTH_RH / 4; ++i) {
+    const int ry = (tid >> 6) + 4 * i, idx = ry * CDP_SMOOTH_RW + rx;
+    const int y = y0 + ry;
     const bool ok = x >= 0 && x < p.W && y >= 0 && y < p.H;
     const int o = y * p.W + x;
     sm[0 * CDP_SMOOTH_RN + idx] = ok ? CDP_LDG(img + o) : 0.f;
@@ -208,9 +252,12 @@ CDP_HD void cdp_smooth_phase_edges(const CdpSmoothParams& p, int tile, int tid, 
   const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
   const int x0 = tx * CDP_SMOOTH_TX - 1, y0 = ty * CDP_SMOOTH_TY - 1;
   const float third = 1.0f / 3.0f;
-  for (int idx = tid; idx < CDP_SMOOTH_RN; idx += nthreads) {
-    const int ry = idx / CDP_SMOOTH_RW, rx = idx - ry * CDP_SMOOTH_RW;
-    const int x = x0 + rx, y = y0 + ry;
+  (void)nthreads;
+  const int rx = tid & 63, x = x0 + rx;
+#pragma unroll
+  for (int i = 0; i < CDP_SMOOTH_RH / 4; ++i) {
+    const int ry = (tid >> 6) + 4 * i, idx = ry * CDP_SMOOTH_RW + rx;
+    const int y = y0 + ry;
     const bool ok = x >= 0 && x < p.W && y >= 0 && y < p.H;
     const bool own = ok && rx >= 1 && rx <= CDP_SMOOTH_TX && ry >= 1 && ry <= CDP_SMOOTH_TY;
     float hx = 0.f, hy = 0.f;
@@ -244,10 +291,12 @@ CDP_HD void cdp_smooth_phase_grad(const CdpSmoothParams& p, int b, int tile, int
   const int x0 = tx * CDP_SMOOTH_TX, y0 = ty * CDP_SMOOTH_TY;
   const float cx = 1.0f / ((float)p.B * (float)p.H * (float)(p.W - 1));
   const float cy = 1.0f / ((float)p.B * (float)(p.H - 1) * (float)p.W);
-  for (int i = tid; i < CDP_SMOOTH_TX * CDP_SMOOTH_TY; i += nthreads) {
-    const int ly = i / CDP_SMOOTH_TX, lx = i - ly * CDP_SMOOTH_TX;
-    const int x = x0 + lx, y = y0 + ly;
-    if (x >= p.W || y >= p.H) continue;
+  (void)nthreads;
+  const int lx = tid & 63, x = x0 + lx;
+#pragma unroll
+  for (int i = 0; i < (CDP_SMOOTH_TY + 3) / 4; ++i) {
+    const int ly = (tid >> 6) + 4 * i, y = y0 + ly;
+    if (lx >= CDP_SMOOTH_TX || ly >= CDP_SMOOTH_TY || x >= p.W || y >= p.H) continue;
     const int idx = (ly + 1) * CDP_SMOOTH_RW + lx + 1;
     const float dv = sm[3 * CDP_SMOOTH_RN + idx];
     acc[0] += dv;
@@ -304,10 +353,19 @@ CDP_HD void cdp_smooth_finalize(const CdpSmoothParams& p) {
   p.loss[0] = (float)loss;
 }
 
-CDP_HD void cdp_smooth_bwd_pixel(const float* g, const float* scal, const float* grad_loss, int b,
-                                 size_t plane, int i, float* grad_disp) {
-  grad_disp[(size_t)b * plane + i] =
-      CDP_LDG(grad_loss) * (CDP_LDG(g + (size_t)b * plane + i) * scal[b * 2] - scal[b * 2 + 1]);
+// grad_disp = grad_loss * (g * |a_b| - c_b) for `n` (<= 4) consecutive pixels starting at i (multiple of 4)
+CDP_HD void cdp_smooth_bwd_run(const float* g, const float* scal, const float* grad_loss, int b,
+                               size_t plane, int i, int n, float* grad_disp) {
+  const float go = CDP_LDG(grad_loss), a = scal[b * 2], c = scal[b * 2 + 1];
+  const float* src = g + (size_t)b * plane + i;
+  float* dst = grad_disp + (size_t)b * plane + i;
+  if (n == 4 && (plane & 3) == 0) {
+    const float4 v = CDP_LDG(reinterpret_cast<const float4*>(src));
+    float4 o; o.x = go * (v.x * a - c); o.y = go * (v.y * a - c); o.z = go * (v.z * a - c); o.w = go * (v.w * a - c);
+    *reinterpret_cast<float4*>(dst) = o;
+  } else {
+    for (int k = 0; k < n; ++k) dst[k] = go * (CDP_LDG(src + k) * a - c);
+  }
 }
 
 // ==========================================================================================

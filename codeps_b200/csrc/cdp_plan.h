@@ -20,8 +20,14 @@ static inline void cdp_fill_pyr_params(const CdpPlan& plan, const cdp_photo_args
     pp->tab_x[s] = tab + plan.tab_fwd_x[s]; pp->tab_y[s] = tab + plan.tab_fwd_y[s];
   }
   for (int s = 0; s < plan.L; ++s) { pp->Ws[s] = plan.Ws[s]; pp->Hs[s] = plan.Hs[s]; }
-  for (int s = 0; s <= plan.L; ++s) pp->begin[s] = plan.pyr_begin[s];
   pp->W = plan.W; pp->H = plan.H; pp->L = plan.L;
+  pp->fast1 = (plan.L > 1 && plan.W % 4 == 0 && plan.H % 2 == 0) ? 1 : 0;
+  int off = 0;
+  pp->begin[0] = pp->begin[1] = 0;
+  for (int s = 1; s < plan.L; ++s) {
+    off += (s == 1 && pp->fast1) ? plan.Hs[s] * (plan.Ws[s] / 2) : plan.Hs[s] * plan.Ws[s];
+    pp->begin[s + 1] = off;
+  }
 }
 
 static inline void cdp_fill_photo_params(const CdpPlan& plan, const cdp_photo_args* a, int b0, int nb,
@@ -73,6 +79,8 @@ static inline void cdp_fill_depth_grad_params(const CdpPlan& plan, const void* s
     p->gdepth[s] = saved + plan.off_gdepth[s];
     p->Ws[s] = plan.Ws[s]; p->Hs[s] = plan.Hs[s];
     if (s > 0) { p->inv_x[s] = tab + plan.tab_inv_x[s]; p->inv_y[s] = tab + plan.tab_inv_y[s]; }
+    p->exact_x[s] = (plan.Ws[s] << s) == plan.W ? 1 : 0;
+    p->exact_y[s] = (plan.Hs[s] << s) == plan.H ? 1 : 0;
   }
   p->grad_loss = grad_loss;
   p->pose_unit = saved + plan.off_pose_unit;

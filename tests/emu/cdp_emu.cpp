@@ -61,7 +61,7 @@ EMU_API int emu_photo_fwd(const cdp_photo_args* a) {
     CdpPyrParams pp;
     cdp_fill_pyr_params(plan, a, &pp);
     for (int b = 0; b < plan.B; ++b)
-      for (int i = 0; i < plan.pyr_begin[plan.L]; ++i) cdp_pyramid_fwd_item(pp, b, i);
+      for (int i = 0; i < pp.begin[plan.L]; ++i) cdp_pyramid_fwd_item(pp, b, i);
   }
   for (int b0 = 0; b0 < plan.B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
     const int nb = cdp_chunk_size(plan.B, b0);
@@ -126,8 +126,8 @@ EMU_API int emu_smooth_bwd(const void* saved_, const float* grad_loss, int32_t B
   const CdpSmoothLayout l = cdp_smooth_layout(B, H, W);
   const float* saved = static_cast<const float*>(saved_);
   for (int b = 0; b < B; ++b)
-    for (int i = 0; i < H * W; ++i)
-      cdp_smooth_bwd_pixel(saved + l.g, saved + l.scal, grad_loss, b, (size_t)H * W, i, grad_disp);
+    for (int i = 0; i < H * W; i += 4)
+      cdp_smooth_bwd_run(saved + l.g, saved + l.scal, grad_loss, b, (size_t)H * W, i, H * W - i < 4 ? H * W - i : 4, grad_disp);
   return CDP_OK;
 }
 
