@@ -207,9 +207,13 @@ __device__ __forceinline__ double cdp_warp_butterfly(double v) {  // same order 
   return v;
 }
 
+template <bool EXACT>
 __global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_constant__ CdpDepthGradParams p) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;  // one row per blockIdx.y: no index division
-  if (x < p.W) cdp_depth_grad_px(p, blockIdx.z, blockIdx.y, x);
+  if (x < p.W) {
+    if (EXACT) cdp_depth_grad_px_exact(p, blockIdx.z, blockIdx.y, x);
+    else cdp_depth_grad_px(p, blockIdx.z, blockIdx.y, x);
+  }
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
 }
@@ -427,7 +431,11 @@ extern "C" int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32
   CdpDepthGradParams p;
   cdp_fill_depth_grad_params(plan, saved_, resize_tables, grad_loss, grad_depth, grad_pose0, grad_pose1, &p);
   dim3 grid((plan.W + 255) / 256, plan.H, plan.B);
-  { ProfScope prof_(CDP_KERNEL_DEPTH_GRAD, stream); cdp_depth_grad_kernel<<<grid, 256, 0, stream>>>(p); }
+  {
+    ProfScope prof_(CDP_KERNEL_DEPTH_GRAD, stream);
+    if (cdp_depth_grad_all_exact(p)) cdp_depth_grad_kernel<true><<<grid, 256, 0, stream>>>(p);
+    else cdp_depth_grad_kernel<false><<<grid, 256, 0, stream>>>(p);
+  }
   CDP_LAUNCH_CHECK("cdp_depth_grad_kernel");
   return CDP_OK;
 }

@@ -183,9 +183,34 @@ CDP_HD void cdp_depth_grad_px(const CdpDepthGradParams& p, int b, int y, int x) 
   p.grad_depth[(size_t)b * W * p.H + pix] = CDP_LDG(p.grad_loss) * acc;
 }
 
+// Same for pyramids whose every level is an exact power-of-two reduction on both axes (the common
+// case): level s contributes 1/4 of G_s(x >> s, y >> s) iff x and y are one of the two middle
+// positions of their 2^s block.
+CDP_HD void cdp_depth_grad_px_exact(const CdpDepthGradParams& p, int b, int y, int x) {
+  const int W = p.W, pix = y * W + x;
+  float acc = CDP_LDG(p.gdepth[0] + (size_t)b * W * p.H + pix);
+#pragma unroll
+  for (int s = 1; s < CDP_MAX_LEVELS; ++s) {
+    if (s >= p.L) break;
+    const int r = 1 << s, half = r >> 1;
+    // m in {half-1, half}  <=>  (unsigned)(m - (half-1)) < 2
+    const bool hy = (unsigned)((y & (r - 1)) - (half - 1)) < 2u;
+    const bool hx = (unsigned)((x & (r - 1)) - (half - 1)) < 2u;
+    if (hy && hx) acc += 0.25f * CDP_LDG(p.gdepth[s] + (size_t)b * p.Ws[s] * p.Hs[s] + (y >> s) * p.Ws[s] + (x >> s));
+  }
+  p.grad_depth[(size_t)b * W * p.H + pix] = CDP_LDG(p.grad_loss) * acc;
+}
+
+CDP_HD bool cdp_depth_grad_all_exact(const CdpDepthGradParams& p) {
+  for (int s = 1; s < p.L; ++s)
+    if (!p.exact_x[s] || !p.exact_y[s]) return false;
+  return true;
+}
+
 CDP_HD void cdp_depth_grad_pixel(const CdpDepthGradParams& p, int b, int pix) {
   const int y = pix / p.W;
-  cdp_depth_grad_px(p, b, y, pix - y * p.W);
+  if (cdp_depth_grad_all_exact(p)) cdp_depth_grad_px_exact(p, b, y, pix - y * p.W);
+  else cdp_depth_grad_px(p, b, y, pix - y * p.W);
 }
 
 CDP_HD void cdp_pose_grad_scale(const CdpDepthGradParams& p, int i) {  // i in [0, 2*B*16)
