@@ -5,10 +5,11 @@ Drop-in replacements for the reference's hot-path classes (``CameraModel``, ``Im
 sm_100a CUDA kernels behind a C ABI (include/codeps_photo.h).  See DESIGN.md.
 """
 from .camera import CameraModel
+from .heads import disp_to_depth, transformation_from_parameters
 from .install import install, uninstall
 from .losses import EdgeAwareSmoothnessLoss, ReconstructionLoss, SSIMLoss
 from .warper import CoordinateWarper, ImageWarper
 
 __all__ = ["CameraModel", "ImageWarper", "CoordinateWarper", "SSIMLoss", "ReconstructionLoss",
-           "EdgeAwareSmoothnessLoss", "install", "uninstall"]
+           "EdgeAwareSmoothnessLoss", "install", "uninstall", "transformation_from_parameters", "disp_to_depth"]
 __version__ = "0.1.0"

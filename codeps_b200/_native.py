@@ -68,6 +68,10 @@ SIGNATURES = {
     "cdp_ssim_bwd_scratch_bytes": (c_size_t, [c_int32] * 3),
     "cdp_ssim_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
                                c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_pose_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "cdp_pose_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "cdp_disp_to_depth_fwd": (c_int32, [c_void_p, c_size_t, c_float, c_float, c_void_p, c_void_p]),
+    "cdp_disp_to_depth_bwd": (c_int32, [c_void_p, c_void_p, c_size_t, c_float, c_float, c_void_p, c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -583,3 +583,86 @@ extern "C" int cdp_ssim_bwd(const float* grad_out, const float* x, const float* 
   CDP_LAUNCH_CHECK("cdp_ssim_bwd_gather_kernel");
   return CDP_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// pose / depth conversions
+// ------------------------------------------------------------------------------------------
+__global__ void cdp_pose_fwd_kernel(const float* aa, const float* tr, int B, int invert, float* M) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) cdp_pose_fwd_sample(aa + 3 * b, tr + 3 * b, invert, M + 16 * b);
+}
+__global__ void cdp_pose_bwd_kernel(const float* gM, const float* aa, const float* tr, int B, int invert, float* gaa,
+                                    float* gtr) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) cdp_pose_bwd_sample(gM + 16 * b, aa + 3 * b, tr + 3 * b, invert, gaa + 3 * b, gtr + 3 * b);
+}
+__global__ void __launch_bounds__(256) cdp_disp_to_depth_fwd_kernel(const float* disp, size_t n, float lo, float span, float* depth) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    depth[i] = cdp_disp_to_depth(__ldg(disp + i), lo, span);
+}
+__global__ void __launch_bounds__(256) cdp_disp_to_depth_bwd_kernel(const float* gdepth, const float* depth, size_t n, float span, float* gdisp) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    gdisp[i] = cdp_disp_to_depth_grad(__ldg(gdepth + i), __ldg(depth + i), span);
+}
+
+extern "C" int cdp_pose_fwd(const float* axisangle, const float* translation, int32_t batch, int32_t invert, float* T,
+                            cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(batch > 0, "invalid batch");
+  CDP_REQUIRE(axisangle && translation && T, "null pointer");
+  cdp_pose_fwd_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(axisangle, translation, batch, invert, T);
+  CDP_LAUNCH_CHECK("cdp_pose_fwd_kernel");
+  return CDP_OK;
+}
+
+extern "C" int cdp_pose_bwd(const float* grad_T, const float* axisangle, const float* translation, int32_t batch,
+                            int32_t invert, float* grad_axisangle, float* grad_translation, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(batch > 0, "invalid batch");
+  CDP_REQUIRE(grad_T && axisangle && translation && grad_axisangle && grad_translation, "null pointer");
+  cdp_pose_bwd_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(grad_T, axisangle, translation, batch, invert,
+                                                              grad_axisangle, grad_translation);
+  CDP_LAUNCH_CHECK("cdp_pose_bwd_kernel");
+  return CDP_OK;
+}
+
+static int cdp_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// grid-stride elementwise launches: a multiple of the SM count
+static int cdp_elementwise_grid(size_t n) {
+  size_t blocks = (n + 255) / 256;
+  const size_t cap = (size_t)cdp_sm_count() * 16;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+extern "C" int cdp_disp_to_depth_fwd(const float* disp, size_t count, float min_depth, float max_depth, float* depth,
+                                     cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(count > 0 && min_depth > 0.f && max_depth > min_depth, "invalid arguments");
+  CDP_REQUIRE(disp && depth, "null pointer");
+  const float lo = 1.0f / max_depth, span = 1.0f / min_depth - 1.0f / max_depth;
+  cdp_disp_to_depth_fwd_kernel<<<cdp_elementwise_grid(count), 256, 0, stream>>>(disp, count, lo, span, depth);
+  CDP_LAUNCH_CHECK("cdp_disp_to_depth_fwd_kernel");
+  return CDP_OK;
+}
+
+extern "C" int cdp_disp_to_depth_bwd(const float* grad_depth, const float* depth, size_t count, float min_depth,
+                                     float max_depth, float* grad_disp, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(count > 0 && min_depth > 0.f && max_depth > min_depth, "invalid arguments");
+  CDP_REQUIRE(grad_depth && depth && grad_disp, "null pointer");
+  const float span = 1.0f / min_depth - 1.0f / max_depth;
+  cdp_disp_to_depth_bwd_kernel<<<cdp_elementwise_grid(count), 256, 0, stream>>>(grad_depth, depth, count, span, grad_disp);
+  CDP_LAUNCH_CHECK("cdp_disp_to_depth_bwd_kernel");
+  return CDP_OK;
+}

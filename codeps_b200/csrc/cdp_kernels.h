@@ -541,3 +541,83 @@ CDP_HD void cdp_ssim_bwd_gather_pixel(const float* x, const float* y, int W, int
   if (grad_x) grad_x[base + pix] = gx * (1.0f / 9.0f);
   if (grad_y) grad_y[base + pix] = gy * (1.0f / 9.0f);
 }
+
+// ==========================================================================================
+// 7. The two conversions that feed the loss: PoseHead.transformation_from_parameters
+//    (models/pose_head.py:56-137) and DepthHead.disp_to_depth (models/depth_head.py:49-54).
+// ==========================================================================================
+struct CdpRodrigues {
+  float x, y, z, ca, sa, C, theta, n;
+  float R[9];
+};
+
+CDP_HD void cdp_rodrigues(const float v[3], CdpRodrigues& o) {
+  o.theta = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  o.n = o.theta + 1e-7f;  // axis = axisangle / (angle + 1e-7), pose_head.py:85
+  o.x = v[0] / o.n; o.y = v[1] / o.n; o.z = v[2] / o.n;
+  o.ca = cosf(o.theta); o.sa = sinf(o.theta); o.C = 1.0f - o.ca;
+  const float x = o.x, y = o.y, z = o.z, C = o.C, sa = o.sa, ca = o.ca;
+  o.R[0] = x * (x * C) + ca; o.R[1] = x * (y * C) - z * sa; o.R[2] = z * (x * C) + y * sa;
+  o.R[3] = x * (y * C) + z * sa; o.R[4] = y * (y * C) + ca; o.R[5] = y * (z * C) - x * sa;
+  o.R[6] = z * (x * C) - y * sa; o.R[7] = y * (z * C) + x * sa; o.R[8] = z * (z * C) + ca;
+}
+
+// one sample: M = T(t) R, or (invert) M = R^T T(-t)
+CDP_HD void cdp_pose_fwd_sample(const float* axisangle, const float* translation, int invert, float* M) {
+  const float v[3] = {axisangle[0], axisangle[1], axisangle[2]};
+  const float t[3] = {translation[0], translation[1], translation[2]};
+  CdpRodrigues q;
+  cdp_rodrigues(v, q);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) M[4 * r + c] = invert ? q.R[3 * c + r] : q.R[3 * r + c];
+    M[4 * r + 3] = invert ? -(q.R[0 + r] * t[0] + q.R[3 + r] * t[1] + q.R[6 + r] * t[2]) : t[r];
+  }
+  M[12] = 0.f; M[13] = 0.f; M[14] = 0.f; M[15] = 1.f;
+}
+
+CDP_HD void cdp_pose_bwd_sample(const float* gM, const float* axisangle, const float* translation, int invert,
+                                float* g_axisangle, float* g_translation) {
+  const float v[3] = {axisangle[0], axisangle[1], axisangle[2]};
+  const float t[3] = {translation[0], translation[1], translation[2]};
+  CdpRodrigues q;
+  cdp_rodrigues(v, q);
+  float gR[9], gt[3];
+  if (!invert) {
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) gR[3 * r + c] = gM[4 * r + c];
+      gt[r] = gM[4 * r + 3];
+    }
+  } else {
+    // M[:3,:3] = R^T ; M[:3,3] = -R^T t
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) gR[3 * r + c] = gM[4 * c + r] - gM[4 * c + 3] * t[r];
+    for (int j = 0; j < 3; ++j) gt[j] = -(q.R[3 * j + 0] * gM[3] + q.R[3 * j + 1] * gM[7] + q.R[3 * j + 2] * gM[11]);
+  }
+  const float x = q.x, y = q.y, z = q.z, C = q.C, sa = q.sa;
+  float gx = 0.f, gy = 0.f, gz = 0.f, gC = 0.f, gsa = 0.f, gca = 0.f;
+  // diagonal: a^2 C + ca
+  gx += 2.f * x * C * gR[0]; gC += x * x * gR[0]; gca += gR[0];
+  gy += 2.f * y * C * gR[4]; gC += y * y * gR[4]; gca += gR[4];
+  gz += 2.f * z * C * gR[8]; gC += z * z * gR[8]; gca += gR[8];
+  // R01 = xyC - z sa, R10 = xyC + z sa
+  { const float s2 = gR[1] + gR[3], d = gR[3] - gR[1];
+    gx += y * C * s2; gy += x * C * s2; gC += x * y * s2; gz += sa * d; gsa += z * d; }
+  // R02 = zxC + y sa, R20 = zxC - y sa
+  { const float s2 = gR[2] + gR[6], d = gR[2] - gR[6];
+    gz += x * C * s2; gx += z * C * s2; gC += z * x * s2; gy += sa * d; gsa += y * d; }
+  // R12 = yzC - x sa, R21 = yzC + x sa
+  { const float s2 = gR[5] + gR[7], d = gR[7] - gR[5];
+    gy += z * C * s2; gz += y * C * s2; gC += y * z * s2; gx += sa * d; gsa += x * d; }
+  float gtheta = -sa * gca + q.ca * gsa + sa * gC;     // ca = cos, sa = sin, C = 1 - cos
+  const float inv_n = 1.0f / q.n;
+  float gv[3] = {gx * inv_n, gy * inv_n, gz * inv_n};  // a = v / n
+  gtheta += -(gx * v[0] + gy * v[1] + gz * v[2]) * inv_n * inv_n;  // n = theta + eps
+  if (q.theta > 0.f) {                                 // torch.norm backward is 0 at the origin
+    const float k = gtheta / q.theta;
+    gv[0] += k * v[0]; gv[1] += k * v[1]; gv[2] += k * v[2];
+  }
+  for (int i = 0; i < 3; ++i) { g_axisangle[i] = gv[i]; g_translation[i] = gt[i]; }
+}
+
+CDP_HD float cdp_disp_to_depth(float disp, float min_disp, float span) { return 1.0f / (min_disp + span * disp); }
+CDP_HD float cdp_disp_to_depth_grad(float g_depth, float depth, float span) { return -g_depth * span * depth * depth; }

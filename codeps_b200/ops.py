@@ -356,3 +356,87 @@ def ssim_loss_map(src_img: torch.Tensor, target_img: torch.Tensor) -> torch.Tens
     if x.shape[2] < 2 or x.shape[3] < 2:
         raise ValueError("SSIM with reflection padding needs at least 2x2 pixels")
     return _Ssim.apply(x, y)
+
+
+class _PoseMatrix(torch.autograd.Function):
+    """cdp_pose_fwd / cdp_pose_bwd."""
+
+    @staticmethod
+    def forward(ctx, axisangle, translation, invert):
+        b = axisangle.shape[0]
+        device = axisangle.device
+        lib = _lib_for(device)
+        out = torch.empty(b, 4, 4, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            check(lib.cdp_pose_fwd(_ptr(axisangle), _ptr(translation), b, int(invert), _ptr(out), _stream(device)),
+                  "cdp_pose_fwd")
+        _LAUNCHES["count"] += 1
+        ctx.save_for_backward(axisangle, translation)
+        ctx.invert = bool(invert)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        axisangle, translation = ctx.saved_tensors
+        b = axisangle.shape[0]
+        device = axisangle.device
+        lib = _lib_for(device)
+        grad_out = _require_cuda_f32(grad_out, "grad_output", (b, 4, 4))
+        ga, gt = torch.empty_like(axisangle), torch.empty_like(translation)
+        with torch.cuda.device(device):
+            check(lib.cdp_pose_bwd(_ptr(grad_out), _ptr(axisangle), _ptr(translation), b, int(ctx.invert), _ptr(ga),
+                                   _ptr(gt), _stream(device)), "cdp_pose_bwd")
+        _LAUNCHES["count"] += 1
+        return ga, gt, None
+
+
+def pose_matrix(axisangle: torch.Tensor, translation: torch.Tensor, invert: bool = False) -> torch.Tensor:
+    """6-DoF -> [B,4,4].  axisangle / translation: [B,3] or [B,1,3] (the pose head's layout)."""
+    shape_ok = lambda t: t.dim() in (2, 3) and t.shape[-1] == 3 and (t.dim() == 2 or t.shape[1] == 1)
+    if not (isinstance(axisangle, torch.Tensor) and isinstance(translation, torch.Tensor)):
+        raise TypeError("axisangle and translation must be tensors")
+    if not shape_ok(axisangle) or not shape_ok(translation) or axisangle.shape[0] != translation.shape[0]:
+        raise ValueError(f"expected [B,3] or [B,1,3] inputs, got {tuple(axisangle.shape)} and {tuple(translation.shape)}")
+    b = axisangle.shape[0]
+    aa = _require_cuda_f32(axisangle.reshape(b, 3), "axisangle")
+    tr = _require_cuda_f32(translation.reshape(b, 3), "translation")
+    return _PoseMatrix.apply(aa, tr, bool(invert))
+
+
+class _DispToDepth(torch.autograd.Function):
+    """cdp_disp_to_depth_fwd / cdp_disp_to_depth_bwd."""
+
+    @staticmethod
+    def forward(ctx, disp, min_depth, max_depth):
+        device = disp.device
+        lib = _lib_for(device)
+        depth = torch.empty_like(disp)
+        with torch.cuda.device(device):
+            check(lib.cdp_disp_to_depth_fwd(_ptr(disp), disp.numel(), float(min_depth), float(max_depth), _ptr(depth),
+                                            _stream(device)), "cdp_disp_to_depth_fwd")
+        _LAUNCHES["count"] += 1
+        ctx.save_for_backward(depth)
+        ctx.range = (float(min_depth), float(max_depth))
+        return depth
+
+    @staticmethod
+    def backward(ctx, grad_depth):
+        (depth,) = ctx.saved_tensors
+        device = depth.device
+        lib = _lib_for(device)
+        grad_depth = _require_cuda_f32(grad_depth, "grad_output", tuple(depth.shape))
+        grad_disp = torch.empty_like(depth)
+        with torch.cuda.device(device):
+            check(lib.cdp_disp_to_depth_bwd(_ptr(grad_depth), _ptr(depth), depth.numel(), ctx.range[0], ctx.range[1],
+                                            _ptr(grad_disp), _stream(device)), "cdp_disp_to_depth_bwd")
+        _LAUNCHES["count"] += 1
+        return grad_disp, None, None
+
+
+def disp_to_depth(disp: torch.Tensor, min_depth: float = 0.1, max_depth: float = 100.0) -> torch.Tensor:
+    disp = _require_cuda_f32(disp, "disp")
+    if disp.numel() == 0:
+        raise ValueError("empty disparity tensor")
+    if not (min_depth > 0 and max_depth > min_depth):
+        raise ValueError("need 0 < min_depth < max_depth")
+    return _DispToDepth.apply(disp, min_depth, max_depth)

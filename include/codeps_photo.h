@@ -162,6 +162,22 @@ int cdp_ssim_bwd(const float* grad_out, const float* x, const float* y, int32_t 
                  float* grad_y /*nullable*/, void* scratch, size_t scratch_bytes,
                  cdp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The two conversions that feed the loss.
+ * ------------------------------------------------------------------------------------------- */
+/* PoseHead.transformation_from_parameters (models/pose_head.py:56-137): axis-angle [B,3] and
+ * translation [B,3] -> T [B,4,4]; invert != 0 gives R^T T(-t) (the t -> t-1 pose). */
+int cdp_pose_fwd(const float* axisangle, const float* translation, int32_t batch, int32_t invert,
+                 float* T, cdp_stream_t stream);
+int cdp_pose_bwd(const float* grad_T /*[B,4,4]*/, const float* axisangle, const float* translation,
+                 int32_t batch, int32_t invert, float* grad_axisangle /*[B,3]*/,
+                 float* grad_translation /*[B,3]*/, cdp_stream_t stream);
+/* DepthHead.disp_to_depth (models/depth_head.py:49-54): depth = 1 / (1/max + (1/min - 1/max) disp). */
+int cdp_disp_to_depth_fwd(const float* disp, size_t count, float min_depth, float max_depth,
+                          float* depth, cdp_stream_t stream);
+int cdp_disp_to_depth_bwd(const float* grad_depth, const float* depth, size_t count, float min_depth,
+                          float max_depth, float* grad_disp, cdp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

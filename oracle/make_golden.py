@@ -133,6 +133,39 @@ def standalone_ops(ref_depth, ref_misc, batch):
     }
 
 
+def heads_fixture(out_dir):
+    """Outputs of the reference's PoseHead.transformation_from_parameters / DepthHead.disp_to_depth."""
+    from models.depth_head import DepthHead
+    from models.pose_head import PoseHead
+    gen = torch.Generator().manual_seed(77)
+    aa = (0.05 * torch.randn(6, 1, 3, generator=gen))
+    aa[4] = 0.0  # zero rotation: norm backward is 0 at the origin
+    tr = 0.3 * torch.randn(6, 1, 3, generator=gen)
+    up = torch.randn(6, 4, 4, generator=gen)
+    disp = torch.rand(2, 1, 12, 20, generator=gen)
+    up_d = torch.randn(2, 1, 12, 20, generator=gen)
+    blob = {"axisangle": aa.numpy(), "translation": tr.numpy(), "upstream": up.numpy(), "disp": disp.numpy(),
+            "upstream_depth": up_d.numpy()}
+    for invert in (False, True):
+        a = aa.clone().double().requires_grad_(True)
+        t = tr.clone().double().requires_grad_(True)
+        m = PoseHead.transformation_from_parameters(a, t, invert)
+        (m * up.double()).sum().backward()
+        tag = "inv" if invert else "fwd"
+        blob[f"T_{tag}"] = m.detach().numpy()
+        blob[f"grad_axisangle_{tag}"] = a.grad.numpy()
+        blob[f"grad_translation_{tag}"] = t.grad.numpy()
+        blob[f"T32_{tag}"] = PoseHead.transformation_from_parameters(aa.clone(), tr.clone(), invert).numpy()
+    d = disp.clone().double().requires_grad_(True)
+    depth = DepthHead.disp_to_depth(d)
+    (depth * up_d.double()).sum().backward()
+    blob["depth"] = depth.detach().numpy()
+    blob["grad_disp"] = d.grad.numpy()
+    path = os.path.join(out_dir, "heads.npz")
+    np.savez_compressed(path, **blob)
+    print(f"heads -> {path} ({os.path.getsize(path) / 1e3:.1f} kB)")
+
+
 CASES = {
     # name: (batch, W, H, intrinsics@WxH, num_scales, data seed, noise seed, kwargs)
     "city_near": (2, 96, 48, (106.06, 106.19, 51.42, 24.05), 5, 11, 1234, dict(depth_range="near")),
@@ -149,6 +182,9 @@ def main():
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order for the committed numbers
+    heads_fixture(out_dir)
+    if "--heads-only" in sys.argv:
+        return
     for name, (b, w, h, k, scales, seed, noise_seed, kw) in CASES.items():
         batch = make_batch(b, w, h, k, seed=seed, **kw)
         blob = {

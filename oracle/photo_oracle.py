@@ -242,3 +242,39 @@ def loss_and_grads(intrinsics, images, depth, disp, poses, noise, num_scales=5, 
         "grad_disp": disp.grad,
         "grad_pose": [p.grad for p in poses],
     }
+
+
+def rot_from_axisangle(axisangle: torch.Tensor) -> torch.Tensor:
+    """PoseHead.rot_from_axisangle (/root/reference/models/pose_head.py:80-119): [B,1,3] -> [B,4,4]."""
+    angle = torch.norm(axisangle, 2, 2, True)
+    axis = axisangle / (angle + 1e-7)
+    ca, sa = torch.cos(angle), torch.sin(angle)
+    c = 1 - ca
+    x, y, z = (axis[..., i].unsqueeze(1) for i in range(3))
+    xs, ys, zs = x * sa, y * sa, z * sa
+    xc, yc, zc = x * c, y * c, z * c
+    xyc, yzc, zxc = x * yc, y * zc, z * xc
+    rows = [[x * xc + ca, xyc - zs, zxc + ys], [xyc + zs, y * yc + ca, yzc - xs], [zxc - ys, yzc + xs, z * zc + ca]]
+    rot = torch.zeros(axisangle.shape[0], 4, 4, dtype=axisangle.dtype, device=axisangle.device)
+    for r in range(3):
+        for col in range(3):
+            rot[:, r, col] = rows[r][col].reshape(-1)
+    rot[:, 3, 3] = 1
+    return rot
+
+
+def transformation_from_parameters(axisangle: torch.Tensor, translation: torch.Tensor, invert: bool = False):
+    """PoseHead.transformation_from_parameters (/root/reference/models/pose_head.py:56-77)."""
+    rot = rot_from_axisangle(axisangle)
+    t = -translation if invert else translation
+    trans = torch.zeros(t.shape[0], 4, 4, dtype=t.dtype, device=t.device)
+    for i in range(4):
+        trans[:, i, i] = 1
+    trans[:, :3, 3] = t.reshape(-1, 3)
+    return torch.matmul(rot.transpose(1, 2), trans) if invert else torch.matmul(trans, rot)
+
+
+def disp_to_depth(disp: torch.Tensor, min_depth: float = 0.1, max_depth: float = 100):
+    """DepthHead.disp_to_depth (/root/reference/models/depth_head.py:49-54)."""
+    min_disp, max_disp = 1 / max_depth, 1 / min_depth
+    return 1 / (min_disp + (max_disp - min_disp) * disp)

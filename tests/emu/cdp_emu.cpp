@@ -195,3 +195,12 @@ EMU_API int emu_ssim_bwd(const float* go, const float* x, const float* y, int32_
     for (int pix = 0; pix < H * W; ++pix) cdp_ssim_bwd_gather_pixel(x, y, W, H, pl, pix, scratch.data(), total, gx, gy);
   return CDP_OK;
 }
+
+EMU_API int emu_pose_fwd(const float* aa, const float* tr, int32_t B, int32_t invert, float* M) {
+  for (int b = 0; b < B; ++b) cdp_pose_fwd_sample(aa + 3 * b, tr + 3 * b, invert, M + 16 * b);
+  return CDP_OK;
+}
+EMU_API int emu_pose_bwd(const float* gM, const float* aa, const float* tr, int32_t B, int32_t invert, float* gaa, float* gtr) {
+  for (int b = 0; b < B; ++b) cdp_pose_bwd_sample(gM + 16 * b, aa + 3 * b, tr + 3 * b, invert, gaa + 3 * b, gtr + 3 * b);
+  return CDP_OK;
+}

@@ -177,4 +177,18 @@ def ssim_bwd(grad_out, x, y):
     return gx, gy
 
 
+def pose(axisangle, translation, invert, grad_out=None):
+    lib = load()
+    b = axisangle.shape[0]
+    aa, tr = _f32(axisangle.reshape(b, 3)), _f32(translation.reshape(b, 3))
+    m = torch.zeros(b, 4, 4)
+    assert lib.emu_pose_fwd(_p(aa), _p(tr), c_int32(b), c_int32(int(invert)), _p(m)) == 0
+    if grad_out is None:
+        return m
+    go = _f32(grad_out)
+    ga, gt = torch.zeros(b, 3), torch.zeros(b, 3)
+    assert lib.emu_pose_bwd(_p(go), _p(aa), _p(tr), c_int32(b), c_int32(int(invert)), _p(ga), _p(gt)) == 0
+    return m, ga, gt
+
+
 _ = (MAX_LEVELS, c_float)
