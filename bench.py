@@ -326,9 +326,9 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = photo_alg_bytes / (photo_ms * 1e-3) / 1e9
     step_kernel_ms = sum(v for v in kernel_ms.values() if v)
-    prof_rec = profiled_kernel(args.workload, "cdp_photo_kernel<1>") or profiled_kernel(args.workload, "cdp_photo_kernel")
+    prof_rec = profiled_kernel(args.workload, "cdp_photo_kernel<1") or profiled_kernel(args.workload, "cdp_photo_kernel")
     roofline = {
-        "bound": "hbm", "kernel": "cdp_photo_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "cdp_photo_kernel<true,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": prof_rec["dram_bytes"] if prof_rec else None, "peak_source": peak_src,
         "ncu": ({k: prof_rec.get(k) for k in ("profile", "duration_us", "issue_slot_pct", "sm_pct_of_peak",
                                               "dram_pct_of_peak", "l2_hit_pct", "l1_hit_pct",

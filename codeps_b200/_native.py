@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_size_t, c_uint8, c_uin
 
 MAX_LEVELS = 6
 MAX_BATCH_PER_LAUNCH = 32
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _fp = POINTER(c_float)
 
@@ -32,6 +32,7 @@ class PhotoArgs(ctypes.Structure):
         ("argmin", c_void_p * MAX_LEVELS),
         ("scratch", c_void_p), ("scratch_bytes", c_size_t),
         ("saved", c_void_p), ("saved_bytes", c_size_t),
+        ("motion0", c_void_p), ("motion1", c_void_p),
     ]
 
 
@@ -44,13 +45,13 @@ SIGNATURES = {
     "cdp_profile_read": (c_int32, [c_int32, POINTER(ctypes.c_double), POINTER(c_int32)]),
     "cdp_resize_tables_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "cdp_resize_tables_build": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_size_t]),
-    "cdp_photo_scratch_bytes": (c_size_t, [c_int32] * 4),
-    "cdp_photo_saved_bytes": (c_size_t, [c_int32] * 4),
+    "cdp_photo_scratch_bytes": (c_size_t, [c_int32] * 5),
+    "cdp_photo_saved_bytes": (c_size_t, [c_int32] * 5),
     "cdp_photo_fwd": (c_int32, [POINTER(PhotoArgs), c_void_p]),
     "cdp_photo_bwd": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "cdp_photo_fwd_launches": (c_int32, [c_int32, c_int32]),
-    "cdp_photo_bwd_launches": (c_int32, [c_int32, c_int32]),
+    "cdp_photo_bwd_launches": (c_int32, [c_int32, c_int32, c_int32]),
     "cdp_smooth_saved_bytes": (c_size_t, [c_int32] * 3),
     "cdp_smooth_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),

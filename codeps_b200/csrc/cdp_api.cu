@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) cdp_pyramid_fwd_kernel(const __grid_const
   cdp_pyramid_fwd_item(p, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-template <bool G>
+template <bool G, bool M>
 __global__ void __launch_bounds__(CDP_PHOTO_THREADS, CDP_PHOTO_MIN_CTAS)
 cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p) {
   extern __shared__ __align__(16) float sm[];
@@ -174,14 +174,14 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p) {
   float v[G ? 33 : 1];
 #pragma unroll
   for (int i = 0; i < (G ? 33 : 1); ++i) v[i] = 0.f;
-  cdp_photo_phase_a<G>(p, c, threadIdx.x, blockDim.x, sm);
+  cdp_photo_phase_a<G, M>(p, c, threadIdx.x, blockDim.x, sm);
   __syncthreads();
   cdp_photo_phase_b1<G>(p, c, threadIdx.x, blockDim.x, sm, v[0]);
   if constexpr (G) {
     __syncthreads();
     cdp_photo_phase_b2(p, c, threadIdx.x, blockDim.x, sm);
     __syncthreads();
-    cdp_photo_phase_c(p, c, threadIdx.x, blockDim.x, sm, &v[1]);
+    cdp_photo_phase_c<M>(p, c, threadIdx.x, blockDim.x, sm, &v[1]);
   }
   v[0] *= p.lv[c.lvl].weight;
   __syncthreads();  // tile planes are dead: reuse shared memory for the reduction
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_consta
     if (EXACT) cdp_depth_grad_px_exact(p, blockIdx.z, blockIdx.y, x);
     else cdp_depth_grad_px(p, blockIdx.z, blockIdx.y, x);
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+  if (p.scale_pose && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
 }
 
@@ -342,15 +342,17 @@ extern "C" int cdp_resize_tables_build(int32_t height, int32_t width, int32_t nu
 // ------------------------------------------------------------------------------------------
 // photometric loss
 // ------------------------------------------------------------------------------------------
-extern "C" size_t cdp_photo_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels) {
+extern "C" size_t cdp_photo_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels,
+                                          int32_t with_motion) {
   CdpPlan plan;
-  if (!cdp_make_plan(batch, height, width, num_levels, &plan)) return 0;
+  if (!cdp_make_plan(batch, height, width, num_levels, &plan, with_motion != 0)) return 0;
   return plan.scratch_floats * sizeof(float);
 }
 
-extern "C" size_t cdp_photo_saved_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels) {
+extern "C" size_t cdp_photo_saved_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels,
+                                        int32_t with_motion) {
   CdpPlan plan;
-  if (!cdp_make_plan(batch, height, width, num_levels, &plan)) return 0;
+  if (!cdp_make_plan(batch, height, width, num_levels, &plan, with_motion != 0)) return 0;
   return plan.saved_floats * sizeof(float);
 }
 
@@ -359,13 +361,14 @@ static int cdp_batch_chunks(int32_t batch) { return (batch + CDP_MAX_BATCH_PER_L
 extern "C" int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels) {
   return (num_levels > 1 ? 1 : 0) + cdp_batch_chunks(batch) + 1;
 }
-extern "C" int cdp_photo_bwd_launches(int32_t, int32_t) { return 1; }
+extern "C" int cdp_photo_bwd_launches(int32_t, int32_t, int32_t with_motion) { return with_motion ? 3 : 1; }
 
 extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   CDP_REQUIRE(a != nullptr, "args is null");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CdpPlan plan;
-  CDP_REQUIRE(cdp_make_plan(a->batch, a->height, a->width, a->num_levels, &plan),
+  CDP_REQUIRE((a->motion0 == nullptr) == (a->motion1 == nullptr), "motion maps must be given for both sources or for none");
+  CDP_REQUIRE(cdp_make_plan(a->batch, a->height, a->width, a->num_levels, &plan, a->motion0 != nullptr),
               "invalid shape: batch %d, %dx%d, %d levels (every level needs >= 2x2 pixels, at most %d levels)",
               a->batch, a->width, a->height, a->num_levels, CDP_MAX_LEVELS);
   CDP_REQUIRE(a->intrinsics_host && a->target && a->source0 && a->source1 && a->depth && a->pose0 && a->pose1 && a->loss,
@@ -395,9 +398,12 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
 
   // 2. fused tile kernel, all levels per launch, <= CDP_MAX_BATCH_PER_LAUNCH samples per launch
   const size_t smem = G ? CdpTileGeom<true>::SMEM_BYTES : CdpTileGeom<false>::SMEM_BYTES;
-  static unsigned long long smem_done[2] = {0ull, 0ull};
-  if (G) CDP_CUDA(cdp_allow_smem(cdp_photo_kernel<true>, smem, &smem_done[1]));
-  else CDP_CUDA(cdp_allow_smem(cdp_photo_kernel<false>, smem, &smem_done[0]));
+  static unsigned long long smem_done[4] = {0ull, 0ull, 0ull, 0ull};
+  const bool M = plan.has_motion != 0;
+  void (*photo_kernel)(const CdpPhotoParams) =
+      G ? (M ? cdp_photo_kernel<true, true> : cdp_photo_kernel<true, false>)
+        : (M ? cdp_photo_kernel<false, true> : cdp_photo_kernel<false, false>);
+  CDP_CUDA(cdp_allow_smem(photo_kernel, smem, &smem_done[(G ? 2 : 0) + (M ? 1 : 0)]));
   for (int b0 = 0; b0 < plan.B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
     const int nb = cdp_chunk_size(plan.B, b0);
     CdpPhotoParams kp;
@@ -405,8 +411,7 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
     dim3 grid(plan.blocks_per_image, nb);
     {
       ProfScope prof_(CDP_KERNEL_PHOTO, stream);
-      if (G) cdp_photo_kernel<true><<<grid, CDP_PHOTO_THREADS, smem, stream>>>(kp);
-      else cdp_photo_kernel<false><<<grid, CDP_PHOTO_THREADS, smem, stream>>>(kp);
+      photo_kernel<<<grid, CDP_PHOTO_THREADS, smem, stream>>>(kp);
     }
     CDP_LAUNCH_CHECK("cdp_photo_kernel");
   }
@@ -421,10 +426,12 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
 
 extern "C" int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32_t num_levels, const void* saved_,
                              size_t saved_bytes, const void* resize_tables, const float* grad_loss,
-                             float* grad_depth, float* grad_pose0, float* grad_pose1, cdp_stream_t stream_) {
+                             float* grad_depth, float* grad_pose0, float* grad_pose1, int32_t with_motion,
+                             float* grad_motion0, float* grad_motion1, cdp_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CdpPlan plan;
-  CDP_REQUIRE(cdp_make_plan(batch, height, width, num_levels, &plan), "invalid shape");
+  CDP_REQUIRE(cdp_make_plan(batch, height, width, num_levels, &plan, with_motion != 0), "invalid shape");
+  CDP_REQUIRE(!with_motion || (grad_motion0 && grad_motion1), "with_motion needs grad_motion0 and grad_motion1");
   CDP_REQUIRE(saved_ && grad_loss && grad_depth && grad_pose0 && grad_pose1, "null pointer");
   CDP_REQUIRE(plan.L == 1 || resize_tables != nullptr, "resize_tables is null");
   if (saved_bytes < plan.saved_floats * sizeof(float)) return cdp_fail(CDP_ERR_WORKSPACE, "saved too small");
@@ -437,6 +444,18 @@ extern "C" int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32
     else cdp_depth_grad_kernel<false><<<grid, 256, 0, stream>>>(p);
   }
   CDP_LAUNCH_CHECK("cdp_depth_grad_kernel");
+  if (with_motion) {
+    float* outs[2] = {grad_motion0, grad_motion1};
+    for (int k = 0; k < 2; ++k) {
+      CdpDepthGradParams pm;
+      cdp_fill_motion_grad_params(plan, saved_, resize_tables, grad_loss, k, outs[k], &pm);
+      dim3 gm((plan.W + 255) / 256, plan.H, 3 * plan.B);
+      ProfScope prof_(CDP_KERNEL_DEPTH_GRAD, stream);
+      if (cdp_depth_grad_all_exact(pm)) cdp_depth_grad_kernel<true><<<gm, 256, 0, stream>>>(pm);
+      else cdp_depth_grad_kernel<false><<<gm, 256, 0, stream>>>(pm);
+      CDP_LAUNCH_CHECK("cdp_depth_grad_kernel (motion)");
+    }
+  }
   return CDP_OK;
 }
 

@@ -88,6 +88,10 @@ struct CdpLevel {
   const float* noise;  // [B,2,H,W] or null
   float* gdepth;       // [B,H,W] unit gradient dL/d depth_s (with grad)
   uint8_t* argmin;     // [B,H,W] or null
+  const float* mot0;   // [B,3,H,W] object motion added to the transformed point, or null
+  const float* mot1;   //           (misc/image_warper.py:133-134)
+  float* gmot0;        // [B,3,H,W] unit gradients dL/d motion_s (with grad and motion)
+  float* gmot1;
   int32_t W, H;
   int32_t tiles_x, tiles_y;
   int32_t block_begin;  // first block index (within one image) belonging to this level
@@ -123,6 +127,9 @@ struct CdpPlan {
   // saved (float offsets): per-level unit depth gradients, unit pose gradients [2][B][16]
   size_t off_gdepth[CDP_MAX_LEVELS];
   size_t off_pose_unit;
+  // optional object-motion maps: pyramid levels (scratch) and per-level unit gradients (saved)
+  int32_t has_motion;
+  size_t off_mot[2][CDP_MAX_LEVELS], off_gmot[2][CDP_MAX_LEVELS];
   size_t saved_floats;
   // pyramid kernel: output pixels of levels >= 1 per image, with prefix offsets
   int32_t pyr_begin[CDP_MAX_LEVELS + 1];
@@ -134,10 +141,11 @@ struct CdpPlan {
 
 static inline size_t cdp_align_floats(size_t n) { return (n + 63) & ~size_t(63); }  // 256 B
 
-static inline bool cdp_make_plan(int32_t B, int32_t H, int32_t W, int32_t L, CdpPlan* p) {
+static inline bool cdp_make_plan(int32_t B, int32_t H, int32_t W, int32_t L, CdpPlan* p, bool motion = false) {
   if (B <= 0 || H <= 0 || W <= 0 || L <= 0 || L > CDP_MAX_LEVELS) return false;
   memset(p, 0, sizeof(*p));
   p->B = B; p->H = H; p->W = W; p->L = L;
+  p->has_motion = motion ? 1 : 0;
   size_t so = 0, sv = 0, tab = 0;
   int32_t blk = 0, pyr = 0;
   for (int s = 0; s < L; ++s) {
@@ -154,6 +162,10 @@ static inline bool cdp_make_plan(int32_t B, int32_t H, int32_t W, int32_t L, Cdp
       p->off_src0[s] = so; so += cdp_align_floats(3 * px);
       p->off_src1[s] = so; so += cdp_align_floats(3 * px);
       p->off_depth[s] = so; so += cdp_align_floats(px);
+      if (motion) {
+        p->off_mot[0][s] = so; so += cdp_align_floats(3 * px);
+        p->off_mot[1][s] = so; so += cdp_align_floats(3 * px);
+      }
       p->pyr_begin[s] = pyr;
       pyr += p->Hs[s] * p->Ws[s];
       p->tab_fwd_x[s] = tab; tab += p->Ws[s];
@@ -162,6 +174,10 @@ static inline bool cdp_make_plan(int32_t B, int32_t H, int32_t W, int32_t L, Cdp
       p->tab_inv_y[s] = tab; tab += H;
     }
     p->off_gdepth[s] = sv; sv += cdp_align_floats(px);
+    if (motion) {
+      p->off_gmot[0][s] = sv; sv += cdp_align_floats(3 * px);
+      p->off_gmot[1][s] = sv; sv += cdp_align_floats(3 * px);
+    }
   }
   p->pyr_begin[L] = pyr;
   p->pyr_begin[0] = 0;

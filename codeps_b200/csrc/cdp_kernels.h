@@ -13,8 +13,10 @@
 //    target, both sources and depth, all levels >= 1 in one launch (algos/depth.py:280-281,295).
 // ==========================================================================================
 struct CdpPyrParams {
-  const float* in[4];                  // target, source0, source1 [B,3,H,W]; depth [B,1,H,W]
-  float* out[4][CDP_MAX_LEVELS];       // per level (index 0 unused)
+  // target, source0, source1 [B,3,H,W]; depth [B,1,H,W]; optionally motion0, motion1 [B,3,H,W]
+  const float* in[6];
+  float* out[6][CDP_MAX_LEVELS];       // per level (index 0 unused)
+  int32_t nt;                          // 4, or 6 with object-motion maps
   const CdpResizeTap* tab_x[CDP_MAX_LEVELS];
   const CdpResizeTap* tab_y[CDP_MAX_LEVELS];
   int32_t Ws[CDP_MAX_LEVELS], Hs[CDP_MAX_LEVELS];
@@ -38,7 +40,8 @@ CDP_HD void cdp_pyramid_fwd_item(const CdpPyrParams& p, int b, int item) {
     const size_t in_plane = (size_t)p.W * p.H, out_plane = (size_t)ws * hs;
     const int o0 = (2 * y) * p.W + 2 * x, o1 = o0 + p.W;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < 6; ++t) {
+      if (t >= p.nt) break;
       const int ch = t == 3 ? 1 : 3;
       for (int c = 0; c < ch; ++c) {
         const float* src = p.in[t] + ((size_t)b * ch + c) * in_plane;
@@ -58,7 +61,8 @@ CDP_HD void cdp_pyramid_fwd_item(const CdpPyrParams& p, int b, int item) {
   const int o00 = ty.i0 * p.W + tx.i0, o01 = ty.i0 * p.W + tx.i1;
   const int o10 = ty.i1 * p.W + tx.i0, o11 = ty.i1 * p.W + tx.i1;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < 6; ++t) {
+    if (t >= p.nt) break;
     const int ch = t == 3 ? 1 : 3;
     for (int c = 0; c < ch; ++c) {
       const float* src = p.in[t] + ((size_t)b * ch + c) * in_plane;
@@ -134,6 +138,7 @@ struct CdpDepthGradParams {
   float* grad_depth;       // [B,1,H,W]
   float* grad_pose[2];     // [B,16]
   int32_t B, H, W, L;
+  int32_t scale_pose;      // also write grad_pose = grad_loss * pose_unit (first launch only)
 };
 
 // references of input index i into level s along one axis: transpose of the bilinear resize taps

@@ -94,7 +94,7 @@ CDP_HD const float2* cdp_pair_plane(const float* sm, int first_plane, int ch) {
 // ------------------------------------------------------------------------------------------
 // Phase A
 // ------------------------------------------------------------------------------------------
-template <bool G>
+template <bool G, bool M>
 CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm) {
   typedef CdpTileGeom<G> Geo;
   const CdpLevel& lv = p.lv[c.lvl];
@@ -116,9 +116,17 @@ CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int 
     const int u = cdp_reflect(px, W), v = cdp_reflect(py, H);
     const int pix = v * W + u;
     const float depth = CDP_LDG(lv.depth + (size_t)c.b * plane + pix);
+    float m0[3], m1[3];
+    if (M) {  // object-motion maps (make_sflow): added to the transformed point
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        m0[ch] = CDP_LDG(lv.mot0 + ((size_t)c.b * 3 + ch) * plane + pix);
+        m1[ch] = CDP_LDG(lv.mot1 + ((size_t)c.b * 3 + ch) * plane + pix);
+      }
+    }
     CdpWarp w0, w1;
-    cdp_warp_point((float)u, (float)v, depth, cam, T[0], nullptr, w0);
-    cdp_warp_point((float)u, (float)v, depth, cam, T[1], nullptr, w1);
+    cdp_warp_point((float)u, (float)v, depth, cam, T[0], M ? m0 : nullptr, w0);
+    cdp_warp_point((float)u, (float)v, depth, cam, T[1], M ? m1 : nullptr, w1);
     CdpTaps t0, t1;
     cdp_taps(u, v, w0, W, H, t0);
     cdp_taps(u, v, w1, W, H, t1);
@@ -390,6 +398,7 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
 // ------------------------------------------------------------------------------------------
 // Phase C (with grad)
 // ------------------------------------------------------------------------------------------
+template <bool M>
 CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads,
                               const float* sm, float* dT /*[32]*/) {
   typedef CdpTileGeom<true> Geo;
@@ -434,6 +443,13 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
       }
     }
     float gd = 0.f;
+    if (M) {  // dL/d motion: zero unless the source contributes below
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        if (!any0) lv.gmot0[((size_t)c.b * 3 + ch) * plane + py * W + px] = 0.f;
+        if (!any1) lv.gmot1[((size_t)c.b * 3 + ch) * plane + py * W + px] = 0.f;
+      }
+    }
     if (any0 || any1) {
       const float depth = CDP_LDG(lv.depth + (size_t)c.b * plane + py * W + px);
 #pragma unroll 1
@@ -484,8 +500,14 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
         CdpPose T;
         cdp_load_pose((k == 0 ? p.pose0 : p.pose1) + (size_t)c.b * 16, T);
         const float* srck = (k == 0 ? lv.src0 : lv.src1) + (size_t)c.b * 3 * plane;
+        float mo[3], gmo[3];
+        const float* motk = k == 0 ? lv.mot0 : lv.mot1;
+        if (M) {
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) mo[ch] = CDP_LDG(motk + ((size_t)c.b * 3 + ch) * plane + py * W + px);
+        }
         CdpWarp w;
-        cdp_warp_point((float)px, (float)py, depth, cam, T, nullptr, w);
+        cdp_warp_point((float)px, (float)py, depth, cam, T, M ? mo : nullptr, w);
         CdpTaps t;
         cdp_taps(px, py, w, W, H, t);
         float gix = 0.f, giy = 0.f;
@@ -503,13 +525,25 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
           giy += gw * diy;
         }
 #if CDP_OPT_DIRECT_DT
-        if (k == 0) cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dT, nullptr);
-        else cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dT + 16, nullptr);
+        float* gmk = M ? gmo : nullptr;
+        if (k == 0) cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dT, gmk);
+        else cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dT + 16, gmk);
+        if (M) {
+          float* dst = (k == 0 ? lv.gmot0 : lv.gmot1) + (size_t)c.b * 3 * plane + py * W + px;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) dst[ch * plane] = gmo[ch];
+        }
 #else
         float dTk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) dTk[i] = 0.f;
-        cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dTk, nullptr);
+        float* gmk = M ? gmo : nullptr;
+        cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dTk, gmk);
+        if (M) {
+          float* dst = (k == 0 ? lv.gmot0 : lv.gmot1) + (size_t)c.b * 3 * plane + py * W + px;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) dst[ch * plane] = gmo[ch];
+        }
         if (k == 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) dT[i] += dTk[i];

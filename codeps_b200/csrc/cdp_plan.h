@@ -13,10 +13,13 @@ static inline void cdp_fill_pyr_params(const CdpPlan& plan, const cdp_photo_args
   memset(pp, 0, sizeof(*pp));
   float* scratch = static_cast<float*>(a->scratch);
   pp->in[0] = a->target; pp->in[1] = a->source0; pp->in[2] = a->source1; pp->in[3] = a->depth;
+  pp->in[4] = a->motion0; pp->in[5] = a->motion1;
+  pp->nt = plan.has_motion ? 6 : 4;
   const CdpResizeTap* tab = static_cast<const CdpResizeTap*>(a->resize_tables);
   for (int s = 1; s < plan.L; ++s) {
     pp->out[0][s] = scratch + plan.off_tgt[s]; pp->out[1][s] = scratch + plan.off_src0[s];
     pp->out[2][s] = scratch + plan.off_src1[s]; pp->out[3][s] = scratch + plan.off_depth[s];
+    if (plan.has_motion) { pp->out[4][s] = scratch + plan.off_mot[0][s]; pp->out[5][s] = scratch + plan.off_mot[1][s]; }
     pp->tab_x[s] = tab + plan.tab_fwd_x[s]; pp->tab_y[s] = tab + plan.tab_fwd_y[s];
   }
   for (int s = 0; s < plan.L; ++s) { pp->Ws[s] = plan.Ws[s]; pp->Hs[s] = plan.Hs[s]; }
@@ -45,6 +48,12 @@ static inline void cdp_fill_photo_params(const CdpPlan& plan, const cdp_photo_ar
     lv.noise = a->noise[s];
     lv.gdepth = G ? saved + plan.off_gdepth[s] : nullptr;
     lv.argmin = a->argmin[s];
+    if (plan.has_motion) {
+      lv.mot0 = s == 0 ? a->motion0 : scratch + plan.off_mot[0][s];
+      lv.mot1 = s == 0 ? a->motion1 : scratch + plan.off_mot[1][s];
+      lv.gmot0 = G ? saved + plan.off_gmot[0][s] : nullptr;
+      lv.gmot1 = G ? saved + plan.off_gmot[1][s] : nullptr;
+    }
     lv.W = plan.Ws[s]; lv.H = plan.Hs[s];
     lv.tiles_x = plan.tiles_x[s]; lv.tiles_y = plan.tiles_y[s];
     lv.block_begin = plan.block_begin[s];
@@ -87,6 +96,17 @@ static inline void cdp_fill_depth_grad_params(const CdpPlan& plan, const void* s
   p->grad_depth = grad_depth;
   p->grad_pose[0] = grad_pose0; p->grad_pose[1] = grad_pose1;
   p->B = plan.B; p->H = plan.H; p->W = plan.W; p->L = plan.L;
+  p->scale_pose = 1;
+}
+
+// dL/d motion_k [B,3,H,W]: the same adjoint over 3B planes of the per-level motion gradients
+static inline void cdp_fill_motion_grad_params(const CdpPlan& plan, const void* saved_, const void* resize_tables,
+                                               const float* grad_loss, int k, float* grad_motion, CdpDepthGradParams* p) {
+  cdp_fill_depth_grad_params(plan, saved_, resize_tables, grad_loss, grad_motion, nullptr, nullptr, p);
+  const float* saved = static_cast<const float*>(saved_);
+  for (int s = 0; s < plan.L; ++s) p->gdepth[s] = saved + plan.off_gmot[k][s];
+  p->B = 3 * plan.B;
+  p->scale_pose = 0;
 }
 
 static inline bool cdp_build_resize_tables(const CdpPlan& plan, void* host_out, int* bad_level) {

@@ -53,6 +53,10 @@ class ReconstructionLoss:
     both poses), and one fixed-order reduction kernel.  ``loss.backward()`` then costs a single
     kernel that assembles dL/d depth from the per-level gradients.
 
+    ``object_motion_maps`` (two [B,3,H,W] maps, depth.py:296-303 -> image_warper.py:133-134) are
+    resized with the images, added to the transformed points inside the tile kernel, and receive
+    their gradient; ``semantic_mask`` (depth.py:284-292, no caller) raises NotImplementedError.
+
     Additive surface (not in the reference, which discards the argmin at depth.py:323):
     ``last_argmin`` -- per level a uint8 [B,H_s,W_s] map, 0/1 = reprojection from t-1/t+1 won,
     2/3 = an identity candidate won, i.e. the pixel is auto-masked.
@@ -108,9 +112,6 @@ class ReconstructionLoss:
         if semantic_mask is not None:
             raise NotImplementedError("the semantic_mask branch (depth.py:284-292) is not taken by any "
                                       "caller in the reference and is not implemented")
-        if object_motion_maps is not None:
-            raise NotImplementedError("object_motion_maps (make_sflow) is not part of the fused loss yet; "
-                                      "every shipped config sets make_sflow: False")
         h, w = images[0].shape[2], images[0].shape[3]
         if (w, h) != (self.scaled_width[0], self.scaled_height[0]):
             raise ValueError(f"images are {w}x{h} but this loss was built for "
@@ -123,7 +124,7 @@ class ReconstructionLoss:
         self._calls += 1
         loss, self.last_argmin = ops.photometric_loss(
             self._level_intrinsics(camera_models), images, depth_map, poses, noise, self.num_scales,
-            self.alpha, seed=self.seed + self._calls)
+            self.alpha, seed=self.seed + self._calls, motions=object_motion_maps)
         return loss
 
     def auto_mask(self, level: int = 0) -> Tensor:

@@ -96,15 +96,16 @@ class _PhotometricLoss(torch.autograd.Function):
     """cdp_photo_fwd / cdp_photo_bwd."""
 
     @staticmethod
-    def forward(ctx, depth, pose0, pose1, target, source0, source1, intrinsics, noise, seed,
+    def forward(ctx, depth, pose0, pose1, motion0, motion1, target, source0, source1, intrinsics, noise, seed,
                 num_levels, alpha, state):
         b, _, h, w = target.shape
         device = target.device
         lib = _lib_for(device)
-        need_grad = any(ctx.needs_input_grad[:3])
+        need_grad = any(ctx.needs_input_grad[:5])
+        has_motion = motion0 is not None
         tables = resize_tables(h, w, num_levels, device)
-        scratch = _bytes(lib.cdp_photo_scratch_bytes(b, h, w, num_levels), device)
-        saved = _bytes(lib.cdp_photo_saved_bytes(b, h, w, num_levels), device) if need_grad else None
+        scratch = _bytes(lib.cdp_photo_scratch_bytes(b, h, w, num_levels, int(has_motion)), device)
+        saved = _bytes(lib.cdp_photo_saved_bytes(b, h, w, num_levels, int(has_motion)), device) if need_grad else None
         loss = torch.empty(1, dtype=torch.float32, device=device)
         argmin = [torch.empty(b, h >> s, w >> s, dtype=torch.uint8, device=device)
                   for s in range(num_levels)]
@@ -123,6 +124,8 @@ class _PhotometricLoss(torch.autograd.Function):
         a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
         if need_grad:
             a.saved, a.saved_bytes = saved.data_ptr(), saved.numel()
+        if has_motion:
+            a.motion0, a.motion1 = motion0.data_ptr(), motion1.data_ptr()
         with torch.cuda.device(device):
             check(lib.cdp_photo_fwd(ctypes.byref(a), _stream(device)), "cdp_photo_fwd")
         _LAUNCHES["count"] += lib.cdp_photo_fwd_launches(b, num_levels)
@@ -130,6 +133,7 @@ class _PhotometricLoss(torch.autograd.Function):
         ctx.shape = (b, h, w, num_levels)
         ctx.saved_buf = saved
         ctx.tables = tables
+        ctx.has_motion = has_motion
         return loss[0]
 
     @staticmethod
@@ -144,17 +148,22 @@ class _PhotometricLoss(torch.autograd.Function):
         grad_depth = torch.empty(b, 1, h, w, dtype=torch.float32, device=device)
         grad_pose0 = torch.empty(b, 4, 4, dtype=torch.float32, device=device)
         grad_pose1 = torch.empty(b, 4, 4, dtype=torch.float32, device=device)
+        gm0 = gm1 = None
+        if ctx.has_motion:
+            gm0 = torch.empty(b, 3, h, w, dtype=torch.float32, device=device)
+            gm1 = torch.empty(b, 3, h, w, dtype=torch.float32, device=device)
         with torch.cuda.device(device):
             check(lib.cdp_photo_bwd(b, h, w, num_levels, _ptr(saved), saved.numel(), _ptr(ctx.tables),
                                     _ptr(go), _ptr(grad_depth), _ptr(grad_pose0), _ptr(grad_pose1),
-                                    _stream(device)), "cdp_photo_bwd")
-        _LAUNCHES["count"] += lib.cdp_photo_bwd_launches(b, num_levels)
-        return (grad_depth, grad_pose0, grad_pose1) + (None,) * 9
+                                    int(ctx.has_motion), _ptr(gm0), _ptr(gm1), _stream(device)), "cdp_photo_bwd")
+        _LAUNCHES["count"] += lib.cdp_photo_bwd_launches(b, num_levels, int(ctx.has_motion))
+        return (grad_depth, grad_pose0, grad_pose1, gm0, gm1) + (None,) * 9
 
 
 def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], depth: torch.Tensor,
                      poses: Sequence[torch.Tensor], noise: Optional[Sequence[torch.Tensor]],
-                     num_levels: int, alpha: float = 0.85, seed: int = 0
+                     num_levels: int, alpha: float = 0.85, seed: int = 0,
+                     motions: Optional[Sequence[torch.Tensor]] = None
                      ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     """Multi-scale min-reprojection loss with identity auto-mask.
 
@@ -182,9 +191,15 @@ def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], dep
             raise ValueError(f"noise has {len(noise)} levels, expected {num_levels}")
         noise = [_require_cuda_f32(n, f"noise[{s}]", (b, 2, h >> s, w >> s))
                  for s, n in enumerate(noise)]
+    motion0 = motion1 = None
+    if motions is not None:
+        if len(motions) != 2:
+            raise ValueError("object_motion_maps must hold one map per source frame")
+        motion0 = _require_cuda_f32(motions[0], "object_motion_maps[0]", (b, 3, h, w))
+        motion1 = _require_cuda_f32(motions[1], "object_motion_maps[1]", (b, 3, h, w))
     state = PhotoState()
-    loss = _PhotometricLoss.apply(depth, pose0, pose1, target, source0, source1, intrinsics, noise,
-                                  seed, num_levels, alpha, state)
+    loss = _PhotometricLoss.apply(depth, pose0, pose1, motion0, motion1, target, source0, source1, intrinsics,
+                                  noise, seed, num_levels, alpha, state)
     return loss, state.argmin
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CDP_ABI_VERSION 1
+#define CDP_ABI_VERSION 2
 #define CDP_MAX_LEVELS 6           /* pyramid levels per call (reference uses 5) */
 #define CDP_MAX_BATCH_PER_LAUNCH 32 /* intrinsics travel in kernel-parameter (constant) space */
 
@@ -104,20 +104,28 @@ typedef struct cdp_photo_args {
                                        (pixel auto-masked); may be NULL per level */
   void* scratch; size_t scratch_bytes; /* pyramid levels; dead after the call */
   void* saved;   size_t saved_bytes;   /* with_grad: state for cdp_photo_bwd */
+  /* Optional object-motion maps [B,3,H,W] per source frame (object_motion_maps of
+   * ReconstructionLoss.__call__, algos/depth.py:296-303; added to the transformed point,
+   * misc/image_warper.py:133-134).  Both or neither. */
+  const float* motion0;
+  const float* motion1;
 } cdp_photo_args;
 
-size_t cdp_photo_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels);
-size_t cdp_photo_saved_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels);
+size_t cdp_photo_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels,
+                               int32_t with_motion);
+size_t cdp_photo_saved_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels,
+                             int32_t with_motion);
 int cdp_photo_fwd(const cdp_photo_args* args, cdp_stream_t stream);
 /* Backward of the above: grad_loss is a DEVICE scalar (dL/d loss).  Writes dL/d depth [B,1,H,W]
- * and dL/dT for both poses [B,4,4] each (autograd of torch.bmm, misc/image_warper.py:129). */
+ * and dL/dT for both poses [B,4,4] each (autograd of torch.bmm, misc/image_warper.py:129); with
+ * motion maps also dL/d motion [B,3,H,W] for both (with_motion must match the forward call). */
 int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32_t num_levels,
                   const void* saved, size_t saved_bytes, const void* resize_tables,
                   const float* grad_loss, float* grad_depth, float* grad_pose0, float* grad_pose1,
-                  cdp_stream_t stream);
+                  int32_t with_motion, float* grad_motion0, float* grad_motion1, cdp_stream_t stream);
 /* Number of kernels one cdp_photo_fwd / cdp_photo_bwd call launches (for launch accounting). */
 int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels);
-int cdp_photo_bwd_launches(int32_t batch, int32_t num_levels);
+int cdp_photo_bwd_launches(int32_t batch, int32_t num_levels, int32_t with_motion);
 
 /* ---------------------------------------------------------------------------------------------
  * EdgeAwareSmoothnessLoss.__call__ (algos/depth.py:58-107).

@@ -215,7 +215,7 @@ def draw_noise(batch: int, width: int, height: int, num_scales: int, seed: int,
 
 def loss_and_grads(intrinsics, images, depth, disp, poses, noise, num_scales=5, alpha=0.85,
                    dtype=torch.float32, recon_weight: float = 1.0, smooth_weight: float = 1.0,
-                   level_intrinsics=None, forced_argmin=None):
+                   level_intrinsics=None, forced_argmin=None, motions=None):
     """Forward + autograd backward of (recon, smooth) on the CPU.  Returns a dict with the two
     loss values, per-level argmin/candidates and dL/d depth, dL/d disp, dL/dT_0, dL/dT_1 of
     ``recon_weight*recon + smooth_weight*smooth`` (depth and disp are treated as independent
@@ -225,8 +225,10 @@ def loss_and_grads(intrinsics, images, depth, disp, poses, noise, num_scales=5, 
     depth = cast(depth).requires_grad_(True)
     disp = cast(disp).requires_grad_(True)
     poses = [cast(p).requires_grad_(True) for p in poses]
+    if motions is not None:
+        motions = [cast(m).requires_grad_(True) for m in motions]
     recon, levels = reconstruction_loss(intrinsics, images, depth, poses, noise, num_scales,
-                                        alpha, level_intrinsics=level_intrinsics, details=True,
+                                        alpha, motions=motions, level_intrinsics=level_intrinsics, details=True,
                                         forced_argmin=forced_argmin)
     smooth = smoothness_loss(images[0], disp)
     (recon_weight * recon + smooth_weight * smooth).backward()
@@ -241,6 +243,7 @@ def loss_and_grads(intrinsics, images, depth, disp, poses, noise, num_scales=5, 
         "grad_depth": depth.grad,
         "grad_disp": disp.grad,
         "grad_pose": [p.grad for p in poses],
+        "grad_motion": [m.grad for m in motions] if motions is not None else None,
     }
 
 

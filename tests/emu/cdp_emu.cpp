@@ -24,27 +24,27 @@ EMU_API int emu_resize_tables_build(int32_t h, int32_t w, int32_t l, void* out) 
   int bad = 0;
   return cdp_build_resize_tables(plan, out, &bad) ? CDP_OK : CDP_ERR_UNSUPPORTED;
 }
-EMU_API size_t emu_photo_scratch_bytes(int32_t b, int32_t h, int32_t w, int32_t l) {
+EMU_API size_t emu_photo_scratch_bytes(int32_t b, int32_t h, int32_t w, int32_t l, int32_t m) {
   CdpPlan plan;
-  return cdp_make_plan(b, h, w, l, &plan) ? plan.scratch_floats * sizeof(float) : 0;
+  return cdp_make_plan(b, h, w, l, &plan, m != 0) ? plan.scratch_floats * sizeof(float) : 0;
 }
-EMU_API size_t emu_photo_saved_bytes(int32_t b, int32_t h, int32_t w, int32_t l) {
+EMU_API size_t emu_photo_saved_bytes(int32_t b, int32_t h, int32_t w, int32_t l, int32_t m) {
   CdpPlan plan;
-  return cdp_make_plan(b, h, w, l, &plan) ? plan.saved_floats * sizeof(float) : 0;
+  return cdp_make_plan(b, h, w, l, &plan, m != 0) ? plan.saved_floats * sizeof(float) : 0;
 }
 
-template <bool G>
+template <bool G, bool M>
 static void emu_photo_block(const CdpPhotoParams& kp, int bx, int by) {
   typedef CdpTileGeom<G> Geo;
   const int nt = CDP_PHOTO_THREADS;
   std::vector<float> sm(Geo::SMEM_BYTES / sizeof(float) + 4, 0.f);
   const CdpTileCtx c = cdp_tile_ctx(kp, bx, by);
   std::vector<float> v((size_t)nt * 33, 0.f);
-  for (int t = 0; t < nt; ++t) cdp_photo_phase_a<G>(kp, c, t, nt, sm.data());
+  for (int t = 0; t < nt; ++t) cdp_photo_phase_a<G, M>(kp, c, t, nt, sm.data());
   for (int t = 0; t < nt; ++t) cdp_photo_phase_b1<G>(kp, c, t, nt, sm.data(), v[(size_t)t * 33]);
   if (G) {
     for (int t = 0; t < nt; ++t) cdp_photo_phase_b2(kp, c, t, nt, sm.data());
-    for (int t = 0; t < nt; ++t) cdp_photo_phase_c(kp, c, t, nt, sm.data(), &v[(size_t)t * 33 + 1]);
+    for (int t = 0; t < nt; ++t) cdp_photo_phase_c<M>(kp, c, t, nt, sm.data(), &v[(size_t)t * 33 + 1]);
   }
   float* rec = kp.partials + ((size_t)c.b * kp.blocks_per_image + bx) * CDP_PARTIAL_STRIDE;
   for (int j = 0; j < 33; ++j) {
@@ -56,7 +56,7 @@ static void emu_photo_block(const CdpPhotoParams& kp, int bx, int by) {
 
 EMU_API int emu_photo_fwd(const cdp_photo_args* a) {
   CdpPlan plan;
-  if (!cdp_make_plan(a->batch, a->height, a->width, a->num_levels, &plan)) return CDP_ERR_INVALID;
+  if (!cdp_make_plan(a->batch, a->height, a->width, a->num_levels, &plan, a->motion0 != nullptr)) return CDP_ERR_INVALID;
   if (plan.L > 1) {
     CdpPyrParams pp;
     cdp_fill_pyr_params(plan, a, &pp);
@@ -69,8 +69,9 @@ EMU_API int emu_photo_fwd(const cdp_photo_args* a) {
     cdp_fill_photo_params(plan, a, b0, nb, &kp);
     for (int by = 0; by < nb; ++by)
       for (int bx = 0; bx < plan.blocks_per_image; ++bx) {
-        if (a->with_grad) emu_photo_block<true>(kp, bx, by);
-        else emu_photo_block<false>(kp, bx, by);
+        const bool m = plan.has_motion != 0;
+        if (a->with_grad) { if (m) emu_photo_block<true, true>(kp, bx, by); else emu_photo_block<true, false>(kp, bx, by); }
+        else { if (m) emu_photo_block<false, true>(kp, bx, by); else emu_photo_block<false, false>(kp, bx, by); }
       }
   }
   CdpFinalizeParams fp;
@@ -84,14 +85,24 @@ EMU_API int emu_photo_fwd(const cdp_photo_args* a) {
 }
 
 EMU_API int emu_photo_bwd(int32_t b, int32_t h, int32_t w, int32_t l, const void* saved, const void* tables,
-                          const float* grad_loss, float* grad_depth, float* gp0, float* gp1) {
+                          const float* grad_loss, float* grad_depth, float* gp0, float* gp1, int32_t with_motion,
+                          float* gm0, float* gm1) {
   CdpPlan plan;
-  if (!cdp_make_plan(b, h, w, l, &plan)) return CDP_ERR_INVALID;
+  if (!cdp_make_plan(b, h, w, l, &plan, with_motion != 0)) return CDP_ERR_INVALID;
   CdpDepthGradParams p;
   cdp_fill_depth_grad_params(plan, saved, tables, grad_loss, grad_depth, gp0, gp1, &p);
   for (int i = 0; i < plan.B; ++i)
     for (int pix = 0; pix < h * w; ++pix) cdp_depth_grad_pixel(p, i, pix);
   for (int i = 0; i < 2 * plan.B * 16; ++i) cdp_pose_grad_scale(p, i);
+  if (with_motion) {
+    float* outs[2] = {gm0, gm1};
+    for (int k = 0; k < 2; ++k) {
+      CdpDepthGradParams pm;
+      cdp_fill_motion_grad_params(plan, saved, tables, grad_loss, k, outs[k], &pm);
+      for (int i = 0; i < pm.B; ++i)
+        for (int pix = 0; pix < h * w; ++pix) cdp_depth_grad_pixel(pm, i, pix);
+    }
+  }
   return CDP_OK;
 }
 

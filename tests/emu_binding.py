@@ -40,7 +40,7 @@ def load():
     for name in ("emu_resize_tables_bytes",):
         getattr(lib, name).argtypes = [c_int32] * 3
     for name in ("emu_photo_scratch_bytes", "emu_photo_saved_bytes"):
-        getattr(lib, name).argtypes = [c_int32] * 4
+        getattr(lib, name).argtypes = [c_int32] * 5
     lib.emu_smooth_saved_bytes.argtypes = [c_int32] * 3
     _lib = lib
     return lib
@@ -63,7 +63,7 @@ def resize_tables(h, w, levels):
 
 
 def photo(level_intrinsics, images, depth, poses, noise, num_scales, alpha=0.85, with_grad=True,
-          grad_loss=1.0, seed=0):
+          grad_loss=1.0, seed=0, motions=None):
     """Run emu_photo_fwd (+ emu_photo_bwd).  level_intrinsics: [L,B,4] float32."""
     lib = load()
     b, _, h, w = depth.shape
@@ -72,8 +72,10 @@ def photo(level_intrinsics, images, depth, poses, noise, num_scales, alpha=0.85,
     k = np.ascontiguousarray(level_intrinsics, dtype=np.float32)
     assert k.shape == (num_scales, b, 4)
     tables = resize_tables(h, w, num_scales)
-    scratch = torch.zeros(lib.emu_photo_scratch_bytes(b, h, w, num_scales), dtype=torch.uint8)
-    saved = torch.zeros(lib.emu_photo_saved_bytes(b, h, w, num_scales), dtype=torch.uint8)
+    hm = int(motions is not None)
+    mo = [_f32(m) for m in motions] if motions is not None else None
+    scratch = torch.zeros(lib.emu_photo_scratch_bytes(b, h, w, num_scales, hm), dtype=torch.uint8)
+    saved = torch.zeros(lib.emu_photo_saved_bytes(b, h, w, num_scales, hm), dtype=torch.uint8)
     loss = torch.zeros(1)
     argmin = [torch.full((b, h >> s, w >> s), 77, dtype=torch.uint8) for s in range(num_scales)]
     noise = [_f32(n) for n in noise] if noise is not None else None
@@ -91,15 +93,19 @@ def photo(level_intrinsics, images, depth, poses, noise, num_scales, alpha=0.85,
     a.loss = loss.data_ptr()
     a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
     a.saved, a.saved_bytes = saved.data_ptr(), saved.numel()
+    if mo is not None:
+        a.motion0, a.motion1 = mo[0].data_ptr(), mo[1].data_ptr()
     assert lib.emu_photo_fwd(ctypes.byref(a)) == 0
     out = {"recon": loss[0].clone(), "argmin": argmin}
     if with_grad:
         go = torch.tensor([grad_loss], dtype=torch.float32)
         gd = torch.zeros_like(depth)
         g0, g1 = torch.zeros(b, 4, 4), torch.zeros(b, 4, 4)
+        gm0 = torch.zeros(b, 3, h, w) if mo is not None else None
+        gm1 = torch.zeros(b, 3, h, w) if mo is not None else None
         assert lib.emu_photo_bwd(c_int32(b), c_int32(h), c_int32(w), c_int32(num_scales), _p(saved), _p(tables),
-                                 _p(go), _p(gd), _p(g0), _p(g1)) == 0
-        out.update(grad_depth=gd, grad_pose=[g0, g1])
+                                 _p(go), _p(gd), _p(g0), _p(g1), c_int32(hm), _p(gm0), _p(gm1)) == 0
+        out.update(grad_depth=gd, grad_pose=[g0, g1], grad_motion=[gm0, gm1])
     return out
 
 

@@ -303,3 +303,40 @@ def test_tiny_and_ragged_sizes(w, h, scales, cuda_device):
     print(check_photo_grads(out, inp, scales, f"{w}x{h}", level_intrinsics=list(k_levels), max_masked_frac=0.6,
                             pose_rtol=1e-3))
     assert_grad_close_masked(out["grad_disp"], ref["grad_disp"], smooth_sign_shadow(tb.disp), "dL/d disp")
+
+
+def test_fused_loss_with_object_motion(cuda_device):
+    """object_motion_maps branch of ReconstructionLoss (algos/depth.py:296-303), through the class."""
+    from helpers import unstable_depth_mask
+    dev = cuda_device
+    tb = make_preset_batch("semkitti", 1, seed=33)
+    w, h, scales = tb.width, tb.height, 5
+    gen = torch.Generator().manual_seed(12)
+    motions = [0.01 * torch.randn(1, 3, h, w, generator=gen) for _ in range(2)]
+    noise = po.draw_noise(1, w, h, scales, seed=3)
+    depth = tb.depth.to(dev).requires_grad_(True)
+    poses = [p.to(dev).requires_grad_(True) for p in tb.poses]
+    mo = [m.to(dev).requires_grad_(True) for m in motions]
+    loss_fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), scales, dev)
+    k_levels = loss_fn._level_intrinsics(tb.camera_models())
+    recon, argmin = ops.photometric_loss(k_levels, tuple(i.to(dev) for i in tb.images), depth, poses,
+                                         [n.to(dev) for n in noise], scales, motions=mo)
+    recon.backward()
+    # the class entry point takes the same argument as the reference
+    torch.manual_seed(0)
+    via_class = loss_fn(tb.camera_models(), tuple(i.to(dev) for i in tb.images), depth.detach(),
+                        [p.detach() for p in poses], object_motion_maps=tuple(m.detach() for m in mo))
+    assert abs(float(via_class) - float(recon)) <= 1e-4 * abs(float(recon))
+    ref = po.loss_and_grads(tb.intrinsics.numpy(), tb.images, tb.depth, tb.disp, tb.poses, noise, scales,
+                            dtype=torch.float64, motions=motions, level_intrinsics=list(k_levels),
+                            forced_argmin=[a.cpu() for a in argmin])
+    free = po.reconstruction_loss(tb.intrinsics.numpy(), [i.double() for i in tb.images], tb.depth.double(),
+                                  [p.double() for p in tb.poses], noise, scales, motions=[m.double() for m in motions],
+                                  level_intrinsics=list(k_levels))
+    assert_loss_close(recon.detach().cpu(), free, "recon with motion")
+    mask = unstable_depth_mask(ref, argmin, h, w).unsqueeze(1)
+    assert_grad_close_masked(depth.grad, ref["grad_depth"], mask, "dL/d depth", max_masked_frac=0.05)
+    for k in range(2):
+        assert_grad_close_masked(mo[k].grad, ref["grad_motion"][k], mask.expand(-1, 3, -1, -1), f"dL/d motion{k}",
+                                 max_masked_frac=0.05)
+        assert_grad_close(poses[k].grad, ref["grad_pose"][k], f"dL/dT{k}")

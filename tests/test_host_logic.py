@@ -41,8 +41,10 @@ def test_host_only_entry_points():
     assert lib.cdp_resize_tables_build(376, 1408, 5, buf.ctypes.data, 8) == -4  # CDP_ERR_WORKSPACE
     assert b"too small" in lib.cdp_last_error()
     assert lib.cdp_resize_tables_bytes(16, 16, 5) == 0  # level 4 would be 1x1: invalid
-    assert lib.cdp_photo_scratch_bytes(8, 512, 1024, 5) > 0
-    assert lib.cdp_photo_scratch_bytes(8, 512, 1024, 9) == 0
+    assert lib.cdp_photo_scratch_bytes(8, 512, 1024, 5, 0) > 0
+    assert lib.cdp_photo_scratch_bytes(8, 512, 1024, 5, 1) > lib.cdp_photo_scratch_bytes(8, 512, 1024, 5, 0)
+    assert lib.cdp_photo_saved_bytes(8, 512, 1024, 5, 1) > lib.cdp_photo_saved_bytes(8, 512, 1024, 5, 0)
+    assert lib.cdp_photo_scratch_bytes(8, 512, 1024, 9, 0) == 0
     # taps for ratio 2: every output reads two neighbouring inputs with weight 1/2
     rec = buf.view(np.int32).reshape(-1, 4)
     first = rec[0]

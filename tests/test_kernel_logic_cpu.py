@@ -133,3 +133,30 @@ def test_emulated_tiny_and_ragged_sizes(w, h, scales):
     check_photo_grads(out, inp, scales, f"{w}x{h}", level_intrinsics=list(k), max_masked_frac=0.6, pose_rtol=1e-3)
     sm = emu.smooth(tb.images[0], tb.disp)
     assert_loss_close(sm["smooth"], ref["smooth"], "smooth")
+
+
+def test_emulated_fused_loss_with_object_motion():
+    """object_motion_maps branch of ReconstructionLoss (algos/depth.py:296-303) inside the fused
+    kernel: loss, selection and all gradients incl. dL/d motion against the fp64 oracle."""
+    from helpers import assert_grad_close_masked, unstable_depth_mask
+    g = Golden("kitti_odd")
+    inp = g.inputs()
+    gen = torch.Generator().manual_seed(12)
+    b = inp["depth"].shape[0]
+    motions = [0.01 * torch.randn(b, 3, g.height, g.width, generator=gen) for _ in range(2)]
+    out = emu.photo(level_tables(g), inp["images"], inp["depth"], inp["poses"], inp["noise"], g.num_scales,
+                    motions=motions)
+    free = po.loss_and_grads(inp["intrinsics"], inp["images"], inp["depth"], inp["disp"], inp["poses"], inp["noise"],
+                             g.num_scales, dtype=torch.float64, motions=motions)
+    assert_loss_close(out["recon"], free["recon"], "recon with motion")
+    for s in range(g.num_scales):
+        top2 = torch.sort(free["candidates"][s], dim=1).values[:, :2]
+        decided = (top2[:, 1] - top2[:, 0]) > 1e-6
+        assert not ((out["argmin"][s] != free["argmin"][s]) & decided).any()
+    ref = po.loss_and_grads(inp["intrinsics"], inp["images"], inp["depth"], inp["disp"], inp["poses"], inp["noise"],
+                            g.num_scales, dtype=torch.float64, motions=motions, forced_argmin=out["argmin"])
+    mask = unstable_depth_mask(ref, out["argmin"], g.height, g.width).unsqueeze(1)
+    assert_grad_close_masked(out["grad_depth"], ref["grad_depth"], mask, "dL/d depth")
+    for k in range(2):
+        assert_grad_close_masked(out["grad_motion"][k], ref["grad_motion"][k], mask.expand(-1, 3, -1, -1), f"dL/d motion{k}")
+        assert_grad_close(out["grad_pose"][k], ref["grad_pose"][k], f"dL/dT{k}", rtol=1e-3)
