@@ -7,9 +7,11 @@ sm_100a CUDA kernels behind a C ABI (include/codeps_photo.h).  See DESIGN.md.
 from .camera import CameraModel
 from .heads import disp_to_depth, transformation_from_parameters
 from .install import install, uninstall
-from .losses import EdgeAwareSmoothnessLoss, ReconstructionLoss, SSIMLoss
+from .losses import (EdgeAwareSmoothnessLoss, FlowSmoothnessLoss, FlowSparsityLoss, ReconstructionLoss,
+                     SSIMLoss)
+from .mixup import warp_c2c
 from .warper import CoordinateWarper, ImageWarper
 
 __all__ = ["CameraModel", "ImageWarper", "CoordinateWarper", "SSIMLoss", "ReconstructionLoss",
-           "EdgeAwareSmoothnessLoss", "install", "uninstall", "transformation_from_parameters", "disp_to_depth"]
+           "EdgeAwareSmoothnessLoss", "FlowSmoothnessLoss", "FlowSparsityLoss", "install", "uninstall", "transformation_from_parameters", "disp_to_depth", "warp_c2c"]
 __version__ = "0.1.0"

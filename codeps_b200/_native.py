@@ -12,6 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_size_t, c_uint8, c_uin
 
 MAX_LEVELS = 6
 MAX_BATCH_PER_LAUNCH = 32
+MAX_FLOW_MAPS = 4    # CDP_MAX_FLOW_MAPS
 ABI_VERSION = 2
 
 _fp = POINTER(c_float)
@@ -73,6 +74,14 @@ SIGNATURES = {
     "cdp_pose_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "cdp_disp_to_depth_fwd": (c_int32, [c_void_p, c_size_t, c_float, c_float, c_void_p, c_void_p]),
     "cdp_disp_to_depth_bwd": (c_int32, [c_void_p, c_void_p, c_size_t, c_float, c_float, c_void_p, c_void_p]),
+    "cdp_flow_scratch_bytes": (c_size_t, [c_int32] * 5),
+    "cdp_flow_smooth_fwd": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_flow_sparsity_fwd": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                        c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_scale_fwd": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "cdp_warp_c2c_fwd": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                   c_void_p, ctypes.c_double, c_int32, c_int32, c_void_p, c_void_p]),
 }
 
 _lock = threading.Lock()
@@ -149,4 +158,4 @@ def profile_read() -> dict:
 
 
 __all__ = ["PhotoArgs", "SIGNATURES", "load", "check", "library_path", "NativeError",
-           "MAX_LEVELS", "MAX_BATCH_PER_LAUNCH", "c_uint8"]
+           "MAX_LEVELS", "MAX_BATCH_PER_LAUNCH", "MAX_FLOW_MAPS", "c_uint8"]

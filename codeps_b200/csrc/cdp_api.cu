@@ -685,3 +685,172 @@ extern "C" int cdp_disp_to_depth_bwd(const float* grad_depth, const float* depth
   CDP_LAUNCH_CHECK("cdp_disp_to_depth_bwd_kernel");
   return CDP_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// object-motion regularisers (cdp_flow.h): FlowSmoothnessLoss / FlowSparsityLoss
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cdp_block_sum(float v, float* red) {  // fixed order; result valid in thread 0
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float acc = 0.f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < nwarps; ++w) acc += red[w];
+  return acc;
+}
+
+__global__ void __launch_bounds__(CDP_FLOW_THREADS) cdp_flow_smooth_kernel(const __grid_constant__ CdpFlowParams p) {
+  __shared__ float red[CDP_FLOW_THREADS / 32];
+  const float v = cdp_flow_smooth_thread(p, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+  const float s = cdp_block_sum(v, red);
+  if (threadIdx.x == 0) p.part[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(CDP_FLOW_THREADS) cdp_flow_abs_kernel(const __grid_constant__ CdpFlowParams p) {
+  __shared__ float red[CDP_FLOW_THREADS / 32];
+  const float v = cdp_flow_abs_thread(p, blockIdx.x, blockIdx.y, threadIdx.x);
+  const float s = cdp_block_sum(v, red);
+  if (threadIdx.x == 0) p.part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(CDP_FLOW_THREADS) cdp_flow_sparsity_kernel(const __grid_constant__ CdpFlowParams p) {
+  __shared__ float red[CDP_FLOW_THREADS / 32];
+  __shared__ float mean_s;
+  if (threadIdx.x < 32) {  // every block re-derives its plane's mean from the pass-1 records (<= a few dozen)
+    double acc = cdp_lane_sum(p.part + (size_t)blockIdx.y * gridDim.x, gridDim.x, 1, threadIdx.x);
+    acc = cdp_warp_butterfly(acc);
+    if (threadIdx.x == 0) mean_s = (float)(acc / (double)((size_t)p.W * p.H));
+  }
+  __syncthreads();
+  const float v = cdp_flow_sparsity_thread(p, blockIdx.x, blockIdx.y, threadIdx.x, mean_s);
+  const float s = cdp_block_sum(v, red);
+  float* part2 = p.part + (size_t)gridDim.x * gridDim.y;
+  if (threadIdx.x == 0) part2[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+
+// loss = scale * sum(records), thread t sums records t, t+1024, ... (= cdp_flow_sum_records_host)
+__global__ void __launch_bounds__(1024) cdp_sum_records_kernel(const float* part, size_t count, double scale, float* loss) {
+  __shared__ double warp_sum[32];
+  double acc = 0.0;
+  for (size_t i = threadIdx.x; i < count; i += 1024) acc += (double)part[i];
+  acc = cdp_warp_butterfly(acc);
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+    for (int w = 0; w < 32; ++w) total += warp_sum[w];
+    loss[0] = (float)(total * scale);
+  }
+}
+
+__global__ void __launch_bounds__(256) cdp_scale_kernel(const float* in, const float* scalar, size_t n, float* out) {
+  const float s = __ldg(scalar);
+  const size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[n4 * 4 + threadIdx.x] = __ldg(in + n4 * 4 + threadIdx.x) * s;
+}
+
+extern "C" size_t cdp_flow_scratch_bytes(int32_t n_maps, int32_t planes, int32_t height, int32_t width, int32_t sparsity) {
+  return cdp_flow_records(n_maps, planes, height, width, sparsity != 0) * sizeof(float);
+}
+
+static int cdp_flow_common(const float* const* maps, int32_t n_maps, int32_t planes, int32_t height, int32_t width,
+                           int32_t wrap, bool sparsity, float* loss, float* unit_grad, void* scratch,
+                           size_t scratch_bytes, CdpFlowParams* p) {
+  CDP_REQUIRE(maps && loss && scratch, "null pointer");
+  CDP_REQUIRE(n_maps >= 1 && n_maps <= CDP_MAX_FLOW_MAPS, "n_maps %d outside [1, %d]", n_maps, CDP_MAX_FLOW_MAPS);
+  for (int i = 0; i < n_maps; ++i) CDP_REQUIRE(maps[i], "null map pointer");
+  CDP_REQUIRE(cdp_fill_flow_params(maps, n_maps, planes, height, width, wrap, sparsity, loss, unit_grad,
+                                   static_cast<float*>(scratch), p),
+              "invalid shape: %d planes of %dx%d%s", planes, width, height,
+              (!sparsity && !wrap) ? " (without wrap-around needs >= 2x2)" : "");
+  const size_t need = cdp_flow_records(n_maps, planes, height, width, sparsity) * sizeof(float);
+  if (scratch_bytes < need) return cdp_fail(CDP_ERR_WORKSPACE, "scratch too small: %zu < %zu", scratch_bytes, need);
+  CDP_REQUIRE((size_t)planes * n_maps <= 65535, "too many planes for one launch");
+  return CDP_OK;
+}
+
+extern "C" int cdp_flow_smooth_fwd(const float* const* maps, int32_t n_maps, int32_t planes, int32_t height,
+                                   int32_t width, int32_t wrap_around, float* loss, float* unit_grad, void* scratch,
+                                   size_t scratch_bytes, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CdpFlowParams p;
+  const int rc = cdp_flow_common(maps, n_maps, planes, height, width, wrap_around, false, loss, unit_grad, scratch,
+                                 scratch_bytes, &p);
+  if (rc != CDP_OK) return rc;
+  CDP_REQUIRE(p.blocks_y <= 65535, "image too tall for one launch");
+  dim3 grid(p.blocks_x, p.blocks_y, planes * n_maps);
+  cdp_flow_smooth_kernel<<<grid, CDP_FLOW_THREADS, 0, stream>>>(p);
+  CDP_LAUNCH_CHECK("cdp_flow_smooth_kernel");
+  const size_t count = (size_t)grid.x * grid.y * grid.z;
+  cdp_sum_records_kernel<<<1, 1024, 0, stream>>>(p.part, count, (double)p.inv_count, loss);
+  CDP_LAUNCH_CHECK("cdp_sum_records_kernel");
+  return CDP_OK;
+}
+
+extern "C" int cdp_flow_sparsity_fwd(const float* const* maps, int32_t n_maps, int32_t planes, int32_t height,
+                                     int32_t width, float* loss, float* unit_grad, void* scratch,
+                                     size_t scratch_bytes, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CdpFlowParams p;
+  const int rc = cdp_flow_common(maps, n_maps, planes, height, width, 1, true, loss, unit_grad, scratch,
+                                 scratch_bytes, &p);
+  if (rc != CDP_OK) return rc;
+  dim3 grid(p.blocks_x, planes * n_maps);
+  cdp_flow_abs_kernel<<<grid, CDP_FLOW_THREADS, 0, stream>>>(p);
+  CDP_LAUNCH_CHECK("cdp_flow_abs_kernel");
+  cdp_flow_sparsity_kernel<<<grid, CDP_FLOW_THREADS, 0, stream>>>(p);
+  CDP_LAUNCH_CHECK("cdp_flow_sparsity_kernel");
+  const size_t count = (size_t)grid.x * grid.y;
+  cdp_sum_records_kernel<<<1, 1024, 0, stream>>>(p.part + count, count, (double)p.inv_count, loss);
+  CDP_LAUNCH_CHECK("cdp_sum_records_kernel");
+  return CDP_OK;
+}
+
+extern "C" int cdp_scale_fwd(const float* in, const float* scalar, size_t count, float* out, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(in && scalar && out && count > 0, "null pointer or empty");
+  CDP_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "buffers must be 16-byte aligned");
+  cdp_scale_kernel<<<cdp_elementwise_grid((count + 3) / 4), 256, 0, stream>>>(in, scalar, count, out);
+  CDP_LAUNCH_CHECK("cdp_scale_kernel");
+  return CDP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// camera-to-camera warp (cdp_c2c.h): Mixup.warp_c2c
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) cdp_warp_c2c_kernel(const __grid_constant__ CdpC2cParams p) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < p.Ht * p.Wt) cdp_c2c_pixel<T>(p, blockIdx.y, pix);
+}
+
+extern "C" int cdp_warp_c2c_fwd(const void* src, int32_t src_is_f64, int32_t batch, int32_t channels, int32_t src_height,
+                                int32_t src_width, int32_t out_height, int32_t out_width, const double* K_src,
+                                const double* K_tgt, double depth_val, int32_t nearest, int32_t padding_zeros,
+                                double* out, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(batch > 0 && channels > 0 && src_height > 0 && src_width > 0 && out_height > 0 && out_width > 0,
+              "invalid shape");
+  CDP_REQUIRE((size_t)out_height * out_width < (1ull << 31) && (size_t)src_height * src_width < (1ull << 31),
+              "image too large");
+  CDP_REQUIRE(src && K_src && K_tgt && out, "null pointer");
+  for (int b0 = 0; b0 < batch; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+    const int nb = cdp_chunk_size(batch, b0);
+    CdpC2cParams p;
+    cdp_fill_c2c_params(&p, src, out, K_src, K_tgt, b0, nb, channels, src_height, src_width, out_height, out_width,
+                        depth_val, nearest != 0, padding_zeros != 0);
+    dim3 grid((out_height * out_width + 255) / 256, nb);
+    if (src_is_f64) cdp_warp_c2c_kernel<double><<<grid, 256, 0, stream>>>(p);
+    else cdp_warp_c2c_kernel<float><<<grid, 256, 0, stream>>>(p);
+    CDP_LAUNCH_CHECK("cdp_warp_c2c_kernel");
+  }
+  return CDP_OK;
+}

@@ -626,3 +626,13 @@ CDP_HD void cdp_pose_bwd_sample(const float* gM, const float* axisangle, const f
 
 CDP_HD float cdp_disp_to_depth(float disp, float min_disp, float span) { return 1.0f / (min_disp + span * disp); }
 CDP_HD float cdp_disp_to_depth_grad(float g_depth, float depth, float span) { return -g_depth * span * depth * depth; }
+
+// ==========================================================================================
+// 8. Object-motion regularisers (FlowSmoothnessLoss / FlowSparsityLoss): see cdp_flow.h
+// ==========================================================================================
+#include "cdp_flow.h"
+
+// ==========================================================================================
+// 9. Camera-to-camera warp at constant depth (Mixup.warp_c2c): see cdp_c2c.h
+// ==========================================================================================
+#include "cdp_c2c.h"

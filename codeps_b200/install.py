@@ -14,7 +14,9 @@ import importlib
 import sys
 
 from .camera import CameraModel
-from .losses import EdgeAwareSmoothnessLoss, ReconstructionLoss, SSIMLoss
+from .losses import (EdgeAwareSmoothnessLoss, FlowSmoothnessLoss, FlowSparsityLoss, ReconstructionLoss,
+                     SSIMLoss)
+from .mixup import warp_c2c
 from .warper import CoordinateWarper, ImageWarper
 
 _PATCHES = {
@@ -23,13 +25,18 @@ _PATCHES = {
     "misc": {"CameraModel": CameraModel, "ImageWarper": ImageWarper},
     "algos.depth": {"CameraModel": CameraModel, "ImageWarper": ImageWarper, "SSIMLoss": SSIMLoss,
                     "ReconstructionLoss": ReconstructionLoss,
-                    "EdgeAwareSmoothnessLoss": EdgeAwareSmoothnessLoss},
+                    "EdgeAwareSmoothnessLoss": EdgeAwareSmoothnessLoss,
+                    "FlowSmoothnessLoss": FlowSmoothnessLoss, "FlowSparsityLoss": FlowSparsityLoss},
     "algos": {"SSIMLoss": SSIMLoss, "ReconstructionLoss": ReconstructionLoss,
-              "EdgeAwareSmoothnessLoss": EdgeAwareSmoothnessLoss},
+              "EdgeAwareSmoothnessLoss": EdgeAwareSmoothnessLoss,
+              "FlowSmoothnessLoss": FlowSmoothnessLoss, "FlowSparsityLoss": FlowSparsityLoss},
     "codeps.model_setup": {"SSIMLoss": SSIMLoss, "ReconstructionLoss": ReconstructionLoss,
-                           "EdgeAwareSmoothnessLoss": EdgeAwareSmoothnessLoss},
+                           "EdgeAwareSmoothnessLoss": EdgeAwareSmoothnessLoss,
+                           "FlowSmoothnessLoss": FlowSmoothnessLoss, "FlowSparsityLoss": FlowSparsityLoss},
     "codeps.online_adap": {"CameraModel": CameraModel},
 }
+# static methods rebound on a class: (module, class) -> {name: function}
+_METHOD_PATCHES = {("datasets.mixup", "Mixup"): {"warp_c2c": warp_c2c}}
 _originals = {}
 
 
@@ -51,12 +58,31 @@ def install(import_missing: bool = True) -> list:
                 _originals.setdefault((mod_name, attr), getattr(mod, attr))
                 setattr(mod, attr, obj)
                 patched.append(f"{mod_name}.{attr}")
+    for (mod_name, cls_name), names in _METHOD_PATCHES.items():
+        mod = sys.modules.get(mod_name)
+        if mod is None and import_missing:
+            try:
+                mod = importlib.import_module(mod_name)
+            except Exception:
+                continue
+        cls = getattr(mod, cls_name, None) if mod is not None else None
+        if cls is None:
+            continue
+        for attr, fn in names.items():
+            if attr in cls.__dict__:
+                _originals.setdefault((mod_name, cls_name, attr), cls.__dict__[attr])
+                setattr(cls, attr, staticmethod(fn))
+                patched.append(f"{mod_name}.{cls_name}.{attr}")
     return patched
 
 
 def uninstall() -> None:
-    for (mod_name, attr), obj in _originals.items():
-        mod = sys.modules.get(mod_name)
-        if mod is not None:
-            setattr(mod, attr, obj)
+    for key, obj in _originals.items():
+        mod = sys.modules.get(key[0])
+        if mod is None:
+            continue
+        if len(key) == 3:
+            setattr(getattr(mod, key[1]), key[2], obj)
+        else:
+            setattr(mod, key[1], obj)
     _originals.clear()

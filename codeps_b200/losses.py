@@ -1,7 +1,8 @@
 """Drop-in loss classes of the self-supervised depth path, backed by the fused CUDA kernels.
 
 Names, constructor arguments and call signatures follow /root/reference/algos/depth.py:58-326
-(``EdgeAwareSmoothnessLoss``, ``SSIMLoss``, ``ReconstructionLoss``) so that
+(``EdgeAwareSmoothnessLoss``, ``SSIMLoss``, ``ReconstructionLoss``; ``:15-52`` for the two flow
+regularisers) so that
 ``codeps.model_setup.gen_models`` (/root/reference/codeps/model_setup.py:63-85) and ``DepthAlgo``
 (/root/reference/algos/depth.py:474-481) use them unchanged.
 """
@@ -16,6 +17,25 @@ from torch import Tensor
 from . import ops
 from .camera import CameraModel
 from .warper import ImageWarper
+
+
+class FlowSmoothnessLoss:
+    """Smoothness of the object-motion maps, mean sqrt(dx^2 + dy^2 + 1e-7) of the (wrap-around)
+    backward differences, averaged over the maps (/root/reference/algos/depth.py:15-34)."""
+
+    def __init__(self, wrap_around: bool = True):
+        self.wrap_around = wrap_around
+
+    def __call__(self, flow_maps: Tuple[Tensor, ...]) -> Tensor:
+        return ops.flow_smoothness_loss(flow_maps, self.wrap_around)
+
+
+class FlowSparsityLoss:
+    """Sparsity of the object-motion maps, mean 2 m sqrt(|f| / (m + 1e-7) + 1) with the detached
+    spatial mean m of |f| (/root/reference/algos/depth.py:37-52)."""
+
+    def __call__(self, flow_maps: Tuple[Tensor, ...]) -> Tensor:
+        return ops.flow_sparsity_loss(flow_maps)
 
 
 class EdgeAwareSmoothnessLoss:

@@ -246,6 +246,102 @@ def smoothness_loss(target_image: torch.Tensor, disparity: torch.Tensor) -> torc
     return _Smoothness.apply(disp, image)
 
 
+class _FlowLoss(torch.autograd.Function):
+    """cdp_flow_smooth_fwd / cdp_flow_sparsity_fwd; backward = cdp_scale_fwd of the unit gradients."""
+
+    @staticmethod
+    def forward(ctx, kind, wrap_around, *maps):
+        n = len(maps)
+        b, c, h, w = maps[0].shape
+        device = maps[0].device
+        lib = _lib_for(device)
+        need_grad = any(ctx.needs_input_grad[2:])
+        sparsity = kind == "sparsity"
+        scratch = _bytes(lib.cdp_flow_scratch_bytes(n, b * c, h, w, int(sparsity)), device)
+        unit = torch.empty((n, b, c, h, w), dtype=torch.float32, device=device) if need_grad else None
+        loss = torch.empty(1, dtype=torch.float32, device=device)
+        ptrs = (ctypes.c_void_p * n)(*[m.data_ptr() for m in maps])
+        with torch.cuda.device(device):
+            if sparsity:
+                check(lib.cdp_flow_sparsity_fwd(ptrs, n, b * c, h, w, _ptr(loss), _ptr(unit), _ptr(scratch),
+                                                scratch.numel(), _stream(device)), "cdp_flow_sparsity_fwd")
+            else:
+                check(lib.cdp_flow_smooth_fwd(ptrs, n, b * c, h, w, int(wrap_around), _ptr(loss), _ptr(unit),
+                                              _ptr(scratch), scratch.numel(), _stream(device)), "cdp_flow_smooth_fwd")
+        _LAUNCHES["count"] += 3 if sparsity else 2
+        ctx.unit = unit
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        unit = ctx.unit
+        device = unit.device
+        lib = _lib_for(device)
+        go = _require_cuda_f32(grad_loss.reshape(1), "grad_loss")
+        out = torch.empty_like(unit)
+        with torch.cuda.device(device):
+            check(lib.cdp_scale_fwd(_ptr(unit), _ptr(go), unit.numel(), _ptr(out), _stream(device)), "cdp_scale_fwd")
+        _LAUNCHES["count"] += 1
+        return (None, None) + tuple(out[i] if ctx.needs_input_grad[2 + i] else None for i in range(out.shape[0]))
+
+
+def _check_flow_maps(flow_maps) -> List[torch.Tensor]:
+    if isinstance(flow_maps, torch.Tensor):
+        raise TypeError("flow_maps must be a tuple of tensors (one per source frame), as in the reference")
+    maps = list(flow_maps)
+    if not 1 <= len(maps) <= _native.MAX_FLOW_MAPS:
+        raise ValueError(f"between 1 and {_native.MAX_FLOW_MAPS} flow maps are supported, got {len(maps)}")
+    first = _require_cuda_f32(maps[0], "flow_maps[0]", (None, None, None, None))
+    return [first] + [_require_cuda_f32(m, f"flow_maps[{i}]", tuple(first.shape)) for i, m in enumerate(maps[1:], 1)]
+
+
+def flow_smoothness_loss(flow_maps, wrap_around: bool = True) -> torch.Tensor:
+    """FlowSmoothnessLoss.__call__ (/root/reference/algos/depth.py:29-34)."""
+    maps = _check_flow_maps(flow_maps)
+    if not wrap_around and (maps[0].shape[2] < 2 or maps[0].shape[3] < 2):
+        raise ValueError("without wrap-around the maps must be at least 2x2")
+    return _FlowLoss.apply("smooth", bool(wrap_around), *maps)
+
+
+def flow_sparsity_loss(flow_maps) -> torch.Tensor:
+    """FlowSparsityLoss.__call__ (/root/reference/algos/depth.py:46-51)."""
+    return _FlowLoss.apply("sparsity", True, *_check_flow_maps(flow_maps))
+
+
+def warp_c2c(src: torch.Tensor, k_src: np.ndarray, k_tgt: np.ndarray, out_hw: Tuple[int, int],
+             depth_val: float = 1.0, interp_mode: str = "bilinear", padding_mode: str = "border") -> torch.Tensor:
+    """cdp_warp_c2c_fwd: [B,C,Hs,Ws] (fp32 or fp64, CUDA) -> fp64 [B,C,Ht,Wt]; k_* are [B,4] host
+    arrays (fx, fy, cx, cy) of the source / target cameras.  No gradient (as in the reference,
+    where the warp is a data augmentation on detached tensors)."""
+    if interp_mode not in ("bilinear", "nearest"):
+        raise NotImplementedError(f"interp_mode {interp_mode!r}: only 'bilinear' and 'nearest' are implemented")
+    if padding_mode not in ("border", "zeros"):
+        raise NotImplementedError(f"padding_mode {padding_mode!r}: only 'border' and 'zeros' are implemented")
+    if not isinstance(src, torch.Tensor) or not src.is_cuda:
+        raise RuntimeError("in_src must be a CUDA tensor; codeps_b200 runs on CUDA only (no CPU fallback)")
+    if src.dim() != 4:
+        raise ValueError(f"in_src must be [B,C,H,W], got {tuple(src.shape)}")
+    if src.dtype not in (torch.float32, torch.float64):
+        src = src.double()  # labels / masks: the reference converts with .double() too (mixup.py:226)
+    src = src.detach().contiguous()
+    b, c, hs, ws = src.shape
+    ks = np.ascontiguousarray(k_src, dtype=np.float64).reshape(-1, 4)
+    kt = np.ascontiguousarray(k_tgt, dtype=np.float64).reshape(-1, 4)
+    if ks.shape[0] != b or kt.shape[0] != b:
+        raise ValueError(f"need one source and one target camera per sample: {ks.shape[0]} / {kt.shape[0]} for batch {b}")
+    ht, wt = int(out_hw[0]), int(out_hw[1])
+    device = src.device
+    lib = _lib_for(device)
+    out = torch.empty((b, c, ht, wt), dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        check(lib.cdp_warp_c2c_fwd(_ptr(src), int(src.dtype == torch.float64), b, c, hs, ws, ht, wt,
+                                   ks.ctypes.data_as(ctypes.c_void_p), kt.ctypes.data_as(ctypes.c_void_p),
+                                   float(depth_val), int(interp_mode == "nearest"), int(padding_mode == "zeros"),
+                                   _ptr(out), _stream(device)), "cdp_warp_c2c_fwd")
+    _LAUNCHES["count"] += (b + _native.MAX_BATCH_PER_LAUNCH - 1) // _native.MAX_BATCH_PER_LAUNCH
+    return out
+
+
 class _WarpImage(torch.autograd.Function):
     """cdp_warp_image_fwd / cdp_warp_image_bwd."""
 

@@ -186,6 +186,47 @@ int cdp_disp_to_depth_fwd(const float* disp, size_t count, float min_depth, floa
 int cdp_disp_to_depth_bwd(const float* grad_depth, const float* depth, size_t count, float min_depth,
                           float max_depth, float* grad_disp, cdp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Regularisers of the object-motion maps: FlowSmoothnessLoss
+ * (algos/depth.py:15-34) and FlowSparsityLoss (algos/depth.py:37-52), called next to the
+ * reconstruction loss at algos/depth.py:483-485.
+ *
+ * maps: HOST array of n_maps (<= CDP_MAX_FLOW_MAPS) device pointers, each [planes, H, W] with
+ * planes = B * C.  loss: device float[1] = (1/n_maps) sum_maps mean(...).  unit_grad: null, or
+ * device [n_maps, planes, H, W] receiving d loss / d map (the losses are terminal scalars; backward
+ * is cdp_scale_fwd with the upstream scalar).  scratch: cdp_flow_scratch_bytes(...) bytes.
+ * ------------------------------------------------------------------------------------------- */
+#define CDP_MAX_FLOW_MAPS 4
+size_t cdp_flow_scratch_bytes(int32_t n_maps, int32_t planes, int32_t height, int32_t width,
+                              int32_t sparsity /* 0: smoothness, 1: sparsity */);
+/* mean sqrt((f - roll_x f)^2 + (f - roll_y f)^2 + 1e-7); wrap_around == 0 crops the first row and
+ * column first (algos/depth.py:20-27).  2 launches. */
+int cdp_flow_smooth_fwd(const float* const* maps, int32_t n_maps, int32_t planes, int32_t height,
+                        int32_t width, int32_t wrap_around, float* loss, float* unit_grad,
+                        void* scratch, size_t scratch_bytes, cdp_stream_t stream);
+/* mean 2 m sqrt(|f| / (m + 1e-7) + 1) with m = mean_{H,W} |f| per plane, detached
+ * (algos/depth.py:39-44).  3 launches. */
+int cdp_flow_sparsity_fwd(const float* const* maps, int32_t n_maps, int32_t planes, int32_t height,
+                          int32_t width, float* loss, float* unit_grad, void* scratch,
+                          size_t scratch_bytes, cdp_stream_t stream);
+/* out[i] = in[i] * scalar[0] (device scalar): backward of a terminal loss whose unit gradient was
+ * produced in the forward pass.  in / out 16-byte aligned. */
+int cdp_scale_fwd(const float* in, const float* scalar, size_t count, float* out, cdp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Camera-to-camera warp at constant depth: Mixup.warp_c2c
+ * (datasets/mixup.py:211-229) = viewing rays of the TARGET camera on its pixel grid
+ * (misc/image_warper.py:54-87, fp32), point at depth_val, projection with the SOURCE camera
+ * (datasets/mixup.py:29-66, fp64) and F.grid_sample(align_corners=True) of the source image in
+ * fp64.  src: device [B,C,Hs,Ws] float (src_is_f64 == 0) or double; out: device double
+ * [B,C,Ht,Wt]; K_src / K_tgt: HOST double [B,4] = fx, fy, cx, cy.  nearest: 0 bilinear, 1 nearest;
+ * padding_zeros: 0 "border", 1 "zeros".  No gradient.  1 launch per 32 samples.
+ * ------------------------------------------------------------------------------------------- */
+int cdp_warp_c2c_fwd(const void* src, int32_t src_is_f64, int32_t batch, int32_t channels,
+                     int32_t src_height, int32_t src_width, int32_t out_height, int32_t out_width,
+                     const double* K_src, const double* K_tgt, double depth_val, int32_t nearest,
+                     int32_t padding_zeros, double* out, cdp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -166,6 +166,62 @@ def heads_fixture(out_dir):
     print(f"heads -> {path} ({os.path.getsize(path) / 1e3:.1f} kB)")
 
 
+def c2c_fixture(ref_misc, out_dir):
+    """Outputs of the reference's Mixup.warp_c2c (datasets/mixup.py:211-229) for every mode its
+    callers use.  ``kornia`` (imported by datasets/mixup.py for an unrelated function) is absent
+    from this image and stubbed."""
+    kornia_contrib = types.ModuleType("kornia.contrib")
+    kornia_contrib.distance_transform = None
+    sys.modules.setdefault("kornia", types.ModuleType("kornia"))
+    sys.modules.setdefault("kornia.contrib", kornia_contrib)
+    from datasets.mixup import Mixup
+    gen = torch.Generator().manual_seed(55)
+    b, hs, ws, ht, wt = 2, 24, 40, 30, 52   # source and target images differ in size
+    img_src = torch.rand(b, 3, hs, ws, generator=gen)
+    lbl_src = torch.randint(0, 19, (b, hs, ws), generator=gen)      # [B,H,W] int64 label map
+    img_tgt = torch.rand(b, 3, ht, wt, generator=gen)
+    # intrinsics as CameraModel.from_tensor delivers them (np.float32), per sample different
+    k_src = torch.tensor([[45.3, 44.1, 19.7, 12.2], [38.9, 40.2, 21.4, 10.8]])
+    k_tgt = torch.tensor([[41.7, 43.9, 25.1, 15.6], [60.5, 58.3, 27.9, 13.3]])
+    cams_src = [ref_misc.CameraModel.from_tensor(ws, hs, k) for k in k_src]
+    cams_tgt = [ref_misc.CameraModel.from_tensor(wt, ht, k) for k in k_tgt]
+    blob = {"img_src": img_src.numpy(), "lbl_src": lbl_src.numpy(), "k_src": k_src.numpy(), "k_tgt": k_tgt.numpy(),
+            "out_hw": np.array([ht, wt])}
+    for interp in ("bilinear", "nearest"):
+        for pad in ("border", "zeros"):
+            blob[f"img_{interp}_{pad}"] = Mixup.warp_c2c(cams_src, cams_tgt, img_src, img_tgt, interp_mode=interp,
+                                                         padding_mode=pad).numpy()
+            blob[f"lbl_{interp}_{pad}"] = Mixup.warp_c2c(cams_src, cams_tgt, lbl_src, img_tgt, interp_mode=interp,
+                                                         padding_mode=pad).numpy()
+    blob["img_depth7"] = Mixup.warp_c2c(cams_src, cams_tgt, img_src, img_tgt, depth_val=7.5).numpy()
+    path = os.path.join(out_dir, "c2c.npz")
+    np.savez_compressed(path, **blob)
+    print(f"c2c -> {path} ({os.path.getsize(path) / 1e3:.1f} kB)")
+
+
+def flow_fixture(ref_depth, out_dir):
+    """Outputs of the reference's FlowSmoothnessLoss / FlowSparsityLoss (fp64 arbiter + fp32)."""
+    gen = torch.Generator().manual_seed(91)
+    maps = [0.05 * torch.randn(2, 3, 13, 22, generator=gen) for _ in range(2)]
+    maps[1][0, 1] = 0.0            # an all-zero plane: spatial mean 0, gradient 0
+    maps[0][1, 2, 3:6, 4:9] = 0.0  # exact zeros inside a plane: sign(0) = 0
+    blob = {"map0": maps[0].numpy(), "map1": maps[1].numpy()}
+    cases = {"smooth_wrap": lambda m: ref_depth.FlowSmoothnessLoss(True)(m),
+             "smooth_crop": lambda m: ref_depth.FlowSmoothnessLoss(False)(m),
+             "sparsity": lambda m: ref_depth.FlowSparsityLoss()(m)}
+    for name, fn in cases.items():
+        for dtype, tag in ((torch.float64, "64"), (torch.float32, "32")):
+            leaves = tuple(m.clone().to(dtype).requires_grad_(True) for m in maps)
+            loss = fn(leaves)
+            loss.backward()
+            blob[f"{name}_loss{tag}"] = loss.detach().numpy()
+            for i, leaf in enumerate(leaves):
+                blob[f"{name}_grad{i}_{tag}"] = leaf.grad.numpy()
+    path = os.path.join(out_dir, "flow.npz")
+    np.savez_compressed(path, **blob)
+    print(f"flow -> {path} ({os.path.getsize(path) / 1e3:.1f} kB)")
+
+
 CASES = {
     # name: (batch, W, H, intrinsics@WxH, num_scales, data seed, noise seed, kwargs)
     "city_near": (2, 96, 48, (106.06, 106.19, 51.42, 24.05), 5, 11, 1234, dict(depth_range="near")),
@@ -183,7 +239,9 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order for the committed numbers
     heads_fixture(out_dir)
-    if "--heads-only" in sys.argv:
+    flow_fixture(ref_depth, out_dir)
+    c2c_fixture(ref_misc, out_dir)
+    if "--heads-only" in sys.argv or "--small-only" in sys.argv:
         return
     for name, (b, w, h, k, scales, seed, noise_seed, kw) in CASES.items():
         batch = make_batch(b, w, h, k, seed=seed, **kw)

@@ -27,6 +27,7 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -281,3 +282,63 @@ def disp_to_depth(disp: torch.Tensor, min_depth: float = 0.1, max_depth: float =
     """DepthHead.disp_to_depth (/root/reference/models/depth_head.py:49-54)."""
     min_disp, max_disp = 1 / max_depth, 1 / min_depth
     return 1 / (min_disp + (max_disp - min_disp) * disp)
+
+
+def flow_smoothness_loss(flow_maps: Sequence[torch.Tensor], wrap_around: bool = True) -> torch.Tensor:
+    """FlowSmoothnessLoss.__call__ (/root/reference/algos/depth.py:15-34): per map the mean of
+    sqrt(dx^2 + dy^2 + 1e-7) over backward differences with wrap-around (cropped to [1:, 1:]
+    otherwise), averaged over the maps."""
+    total = 0
+    for f in flow_maps:
+        gx = f - torch.roll(f, shifts=1, dims=3)
+        gy = f - torch.roll(f, shifts=1, dims=2)
+        if not wrap_around:
+            gx, gy = gx[:, :, 1:, 1:], gy[:, :, 1:, 1:]
+        total = total + torch.sqrt(gx * gx + gy * gy + 1e-7).mean()
+    return total / len(flow_maps)
+
+
+def flow_sparsity_loss(flow_maps: Sequence[torch.Tensor]) -> torch.Tensor:
+    """FlowSparsityLoss.__call__ (/root/reference/algos/depth.py:37-52): per map
+    mean(2 m sqrt(|f| / (m + 1e-7) + 1)) with m = mean_{H,W} |f| detached, averaged over the maps."""
+    total = 0
+    for f in flow_maps:
+        a = f.abs()
+        m = a.mean(dim=(2, 3), keepdim=True).detach()
+        total = total + (2 * m * torch.sqrt(a / (m + 1e-7) + 1)).mean()
+    return total / len(flow_maps)
+
+
+def warp_c2c(k_src, k_tgt, in_src: torch.Tensor, out_hw: Tuple[int, int], depth_val: float = 1.0,
+             interp_mode: str = "bilinear", padding_mode: str = "border", ieee_sqrt: bool = False) -> torch.Tensor:
+    """Mixup.warp_c2c (/root/reference/datasets/mixup.py:211-229): rays of the target camera on
+    its fp32 pixel grid (misc/image_warper.py:62-87, misc/camera_model.py:52-71), point at
+    ``depth_val`` in fp64, projection with the source camera (mixup.py:29-66), fp64 grid_sample.
+    k_src / k_tgt: [B,4] (fx, fy, cx, cy) arrays.
+
+    ``ieee_sqrt``: torch's vectorised CPU ``sqrt`` is not correctly rounded for fp32 (about 0.4 % of
+    arguments come out 1 ulp low), CUDA's ``sqrtf`` and numpy's are.  The default reproduces the
+    reference as it runs on the CPU (and matches the committed fixture to 1e-14); ``True`` takes
+    the correctly rounded root, which is what the reference computes on a GPU and what the kernel
+    computes."""
+    if in_src.dim() == 3:
+        in_src = in_src.unsqueeze(1)
+    b, _, hs, ws = in_src.shape
+    ht, wt = out_hw
+    u = torch.arange(wt).expand(ht, wt).float()
+    v = torch.arange(ht).expand(wt, ht).t().float()
+    grids = []
+    for i in range(b):
+        fx, fy, cx, cy = (np.float32(x) for x in np.asarray(k_tgt)[i])
+        rx, ry = (u - cx) / fx, (v - cy) / fy
+        norm2 = rx**2 + ry**2 + 1.0
+        norm = torch.from_numpy(np.sqrt(norm2.numpy())) if ieee_sqrt else torch.sqrt(norm2)
+        rx, ry, rz = rx / norm, ry / norm, 1.0 / norm
+        scale = torch.full((ht, wt), float(depth_val), dtype=torch.float64) / rz.double().abs()
+        x3, y3, z3 = scale * rx.double(), scale * ry.double(), (scale * rz.double()).clamp(min=1e-5)
+        sfx, sfy, scx, scy = (float(x) for x in np.asarray(k_src)[i])
+        us, vs = (x3 / z3) * sfx + scx, (y3 / z3) * sfy + scy
+        grids.append(torch.stack([(us / (ws - 1) - 0.5) * 2, (vs / (hs - 1) - 0.5) * 2], dim=-1))
+    return F.grid_sample(in_src.double(), torch.stack(grids), mode=interp_mode, padding_mode=padding_mode,
+                         align_corners=True)
+

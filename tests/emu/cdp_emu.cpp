@@ -142,6 +142,65 @@ EMU_API int emu_smooth_bwd(const void* saved_, const float* grad_loss, int32_t B
   return CDP_OK;
 }
 
+// object-motion regularisers (cdp_flow.h): kind 0 = smoothness, 1 = sparsity
+EMU_API int emu_flow_loss(const float* const* maps, int32_t n_maps, int32_t planes, int32_t H, int32_t W,
+                          int32_t kind, int32_t wrap, float* loss, float* unit_grad) {
+  CdpFlowParams p;
+  const bool sparsity = kind != 0;
+  std::vector<float> part(cdp_flow_records(n_maps, planes, H, W, sparsity) + 1, 0.f);
+  if (!cdp_fill_flow_params(maps, n_maps, planes, H, W, wrap, sparsity, loss, unit_grad, part.data(), &p))
+    return CDP_ERR_INVALID;
+  const int nt = CDP_FLOW_THREADS, nz = planes * n_maps;
+  if (!sparsity) {
+    for (int bz = 0; bz < nz; ++bz)
+      for (int by = 0; by < p.blocks_y; ++by)
+        for (int bx = 0; bx < p.blocks_x; ++bx) {
+          float tot = 0.f;
+          for (int t = 0; t < nt; ++t) tot += cdp_flow_smooth_thread(p, bx, by, bz, t);
+          part[((size_t)bz * p.blocks_y + by) * p.blocks_x + bx] = tot;
+        }
+    const size_t count = (size_t)nz * p.blocks_y * p.blocks_x;
+    loss[0] = (float)(cdp_flow_sum_records_host(part.data(), count) * (double)p.inv_count);
+    return CDP_OK;
+  }
+  const size_t count = (size_t)nz * p.blocks_x;
+  for (int bz = 0; bz < nz; ++bz)
+    for (int bx = 0; bx < p.blocks_x; ++bx) {
+      float tot = 0.f;
+      for (int t = 0; t < nt; ++t) tot += cdp_flow_abs_thread(p, bx, bz, t);
+      part[(size_t)bz * p.blocks_x + bx] = tot;
+    }
+  for (int bz = 0; bz < nz; ++bz) {
+    double lanes[32];
+    for (int l = 0; l < 32; ++l) lanes[l] = cdp_lane_sum(part.data() + (size_t)bz * p.blocks_x, p.blocks_x, 1, l);
+    const float mean = cdp_flow_plane_mean(p, bz, lanes);
+    for (int bx = 0; bx < p.blocks_x; ++bx) {
+      float tot = 0.f;
+      for (int t = 0; t < nt; ++t) tot += cdp_flow_sparsity_thread(p, bx, bz, t, mean);
+      part[count + (size_t)bz * p.blocks_x + bx] = tot;
+    }
+  }
+  loss[0] = (float)(cdp_flow_sum_records_host(part.data() + count, count) * (double)p.inv_count);
+  return CDP_OK;
+}
+
+// camera-to-camera warp (cdp_c2c.h)
+EMU_API int emu_warp_c2c(const void* src, int32_t src_is_f64, int32_t B, int32_t C, int32_t Hs, int32_t Ws, int32_t Ht,
+                         int32_t Wt, const double* Ks, const double* Kt, double depth, int32_t nearest, int32_t zeros,
+                         double* out) {
+  for (int b0 = 0; b0 < B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+    const int nb = cdp_chunk_size(B, b0);
+    CdpC2cParams p;
+    cdp_fill_c2c_params(&p, src, out, Ks, Kt, b0, nb, C, Hs, Ws, Ht, Wt, depth, nearest, zeros);
+    for (int i = 0; i < nb; ++i)
+      for (int pix = 0; pix < Ht * Wt; ++pix) {
+        if (src_is_f64) cdp_c2c_pixel<double>(p, i, pix);
+        else cdp_c2c_pixel<float>(p, i, pix);
+      }
+  }
+  return CDP_OK;
+}
+
 EMU_API int emu_warp_grid_fwd(const float* depth, const float* pose, const float* motion, const float* K, int32_t B,
                               int32_t H, int32_t W, float* grid) {
   for (int b0 = 0; b0 < B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {

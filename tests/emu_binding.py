@@ -18,7 +18,7 @@ REPO = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "cdp_emu.cpp")
 LIB = os.path.join(HERE, "emu", "libcdp_emu.so")
 DEPS = [SRC] + [os.path.join(REPO, "codeps_b200", "csrc", n)
-                for n in ("cdp_common.h", "cdp_math.h", "cdp_kernels.h", "cdp_photo_tile.h", "cdp_plan.h")]
+                for n in ("cdp_common.h", "cdp_math.h", "cdp_kernels.h", "cdp_photo_tile.h", "cdp_plan.h", "cdp_flow.h", "cdp_c2c.h")]
 
 _lib = None
 
@@ -123,6 +123,42 @@ def smooth(image, disp, with_grad=True, grad_loss=1.0):
         gd = torch.zeros_like(disp)
         assert lib.emu_smooth_bwd(_p(saved), _p(go), c_int32(b), c_int32(h), c_int32(w), _p(gd)) == 0
         out["grad_disp"] = gd
+    return out
+
+
+def flow_loss(maps, kind, wrap_around=True):
+    """kind: "smooth" | "sparsity"; returns (loss, [unit gradient per map])."""
+    import ctypes
+    lib = load()
+    maps = [_f32(m) for m in maps]
+    n = len(maps)
+    b, c, h, w = maps[0].shape
+    ptrs = (ctypes.c_void_p * n)(*[m.data_ptr() for m in maps])
+    loss = torch.zeros(1)
+    unit = torch.zeros(n, b, c, h, w)
+    rc = lib.emu_flow_loss(ptrs, c_int32(n), c_int32(b * c), c_int32(h), c_int32(w),
+                           c_int32(1 if kind == "sparsity" else 0), c_int32(int(wrap_around)), _p(loss), _p(unit))
+    assert rc == 0, rc
+    return loss[0].clone(), [unit[i] for i in range(n)]
+
+
+def warp_c2c(src, k_src, k_tgt, out_hw, depth_val=1.0, interp_mode="bilinear", padding_mode="border"):
+    from ctypes import c_double
+    lib = load()
+    if src.dim() == 3:
+        src = src.unsqueeze(1)
+    if src.dtype not in (torch.float32, torch.float64):
+        src = src.double()
+    src = src.contiguous()
+    b, c, hs, ws = src.shape
+    ks = np.ascontiguousarray(k_src, dtype=np.float64)
+    kt = np.ascontiguousarray(k_tgt, dtype=np.float64)
+    out = torch.zeros(b, c, out_hw[0], out_hw[1], dtype=torch.float64)
+    rc = lib.emu_warp_c2c(_p(src), c_int32(int(src.dtype == torch.float64)), c_int32(b), c_int32(c), c_int32(hs),
+                          c_int32(ws), c_int32(out_hw[0]), c_int32(out_hw[1]), c_void_p(ks.ctypes.data),
+                          c_void_p(kt.ctypes.data), c_double(float(depth_val)), c_int32(int(interp_mode == "nearest")),
+                          c_int32(int(padding_mode == "zeros")), _p(out))
+    assert rc == 0, rc
     return out
 
 

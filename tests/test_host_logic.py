@@ -143,7 +143,8 @@ def test_product_package_never_imports_the_oracle_or_emulator():
 
 def test_install_rebinds_reference_names():
     """install() swaps the classes into (stand-ins for) the reference's modules."""
-    names = ["misc", "misc.camera_model", "misc.image_warper", "algos", "algos.depth", "codeps", "codeps.model_setup"]
+    names = ["misc", "misc.camera_model", "misc.image_warper", "algos", "algos.depth", "codeps", "codeps.model_setup",
+             "datasets", "datasets.mixup"]
     saved = {n: sys.modules.get(n) for n in names}
     try:
         for n in names:
@@ -154,13 +155,26 @@ def test_install_rebinds_reference_names():
         sys.modules["algos.depth"].ImageWarper = sentinel
         sys.modules["misc"].ImageWarper = sentinel
         sys.modules["codeps.model_setup"].EdgeAwareSmoothnessLoss = sentinel
+        sys.modules["algos.depth"].FlowSparsityLoss = sentinel
+
+        class Mixup:  # stand-in for datasets.mixup.Mixup with its static method
+            @staticmethod
+            def warp_c2c(*args, **kwargs):
+                return sentinel
+
+            def embed(self):
+                return self.warp_c2c()
+        sys.modules["datasets.mixup"].Mixup = Mixup
         patched = codeps_b200.install(import_missing=False)
+        assert "datasets.mixup.Mixup.warp_c2c" in patched and "algos.depth.FlowSparsityLoss" in patched
+        assert Mixup.warp_c2c is codeps_b200.warp_c2c and Mixup().warp_c2c is codeps_b200.warp_c2c
         assert "algos.depth.ReconstructionLoss" in patched and "misc.ImageWarper" in patched
         assert sys.modules["algos.depth"].ReconstructionLoss is codeps_b200.ReconstructionLoss
         assert sys.modules["codeps.model_setup"].EdgeAwareSmoothnessLoss is codeps_b200.EdgeAwareSmoothnessLoss
         assert not hasattr(sys.modules["misc"], "CameraModel")  # only existing names are rebound
         codeps_b200.uninstall()
         assert sys.modules["algos.depth"].ReconstructionLoss is sentinel
+        assert Mixup().embed() is sentinel
     finally:
         for n, m in saved.items():
             if m is None:
