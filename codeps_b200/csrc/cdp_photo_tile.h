@@ -25,6 +25,9 @@
 #ifndef CDP_OPT_DIRECT_DT
 #define CDP_OPT_DIRECT_DT 1  // phase C accumulates dL/dT without a per-pixel temporary
 #endif
+#ifndef CDP_OPT_PREFETCH_DEPTH
+#define CDP_OPT_PREFETCH_DEPTH 1  // phase A requests the next region pixel's depth one iteration ahead: -1 %
+#endif
 #ifndef CDP_STRIP
 #define CDP_STRIP 5  // pixels per thread strip in phases B1/B2
 #endif
@@ -109,13 +112,36 @@ CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int 
   const float* src0 = lv.src0 + (size_t)c.b * 3 * plane;
   const float* src1 = lv.src1 + (size_t)c.b * 3 * plane;
   const float* tgt = lv.tgt + (size_t)c.b * 3 * plane;
+#if CDP_OPT_PREFETCH_DEPTH
+  // the depth of the next region pixel is requested one iteration ahead: the loop body has two
+  // dependent global-memory round trips (depth -> sample position -> source taps) otherwise
+  float depth_next = 0.f;
+  {
+    const int ry = tid / Geo::RW, rx = tid - ry * Geo::RW;
+    const int px = c.x0 - Geo::HALO + rx, py = c.y0 - Geo::HALO + ry;
+    if (tid < Geo::RN && !(px < -1 || px > W || py < -1 || py > H))
+      depth_next = CDP_LDG(lv.depth + (size_t)c.b * plane + cdp_reflect(py, H) * W + cdp_reflect(px, W));
+  }
+#endif
   for (int idx = tid; idx < Geo::RN; idx += nthreads) {
     const int ry = idx / Geo::RW, rx = idx - ry * Geo::RW;
     const int px = c.x0 - Geo::HALO + rx, py = c.y0 - Geo::HALO + ry;
+#if CDP_OPT_PREFETCH_DEPTH
+    const float depth = depth_next;
+    {
+      const int nidx = idx + nthreads;
+      const int nry = nidx / Geo::RW, nrx = nidx - nry * Geo::RW;
+      const int npx = c.x0 - Geo::HALO + nrx, npy = c.y0 - Geo::HALO + nry;
+      if (nidx < Geo::RN && !(npx < -1 || npx > W || npy < -1 || npy > H))
+        depth_next = CDP_LDG(lv.depth + (size_t)c.b * plane + cdp_reflect(npy, H) * W + cdp_reflect(npx, W));
+    }
+#endif
     if (px < -1 || px > W || py < -1 || py > H) continue;  // never read
     const int u = cdp_reflect(px, W), v = cdp_reflect(py, H);
     const int pix = v * W + u;
+#if !CDP_OPT_PREFETCH_DEPTH
     const float depth = CDP_LDG(lv.depth + (size_t)c.b * plane + pix);
+#endif
     float m0[3], m1[3];
     if (M) {  // object-motion maps (make_sflow): added to the transformed point
 #pragma unroll
@@ -205,7 +231,7 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
   uint8_t* kplane = reinterpret_cast<uint8_t*>(sm + (size_t)Geo::NPLANES * Geo::RN);
   float centre[3];
   cdp_tile_centre(lv, c, centre);
-  const float a3 = p.alpha * (1.0f / 3.0f), b3 = (float)(1.0 - (double)p.alpha) * (1.0f / 3.0f);
+  const float a3 = p.w_ssim3, b3 = p.w_l13;
   for (int item = tid; item < Geo::NITEMS; item += nthreads) {
     const int strip = item / Geo::BW, bx = item - strip * Geo::BW;
     const int by0 = strip * CDP_STRIP;
@@ -407,8 +433,8 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
   const size_t plane = (size_t)W * H;
   const CdpCam cam = cdp_tile_cam(p, c);
   const uint8_t* kplane = reinterpret_cast<const uint8_t*>(sm + (size_t)Geo::NPLANES * Geo::RN);
-  const float w_ssim = p.alpha / 27.0f;  // alpha * (1/3 channels) * (1/9 window)
-  const float w_l1 = (float)(1.0 - (double)p.alpha) * (1.0f / 3.0f);
+  const float w_ssim = p.w_ssim27;  // alpha * (1/3 channels) * (1/9 window)
+  const float w_l1 = p.w_l13;
   for (int idx = tid; idx < CDP_TILE_X * CDP_TILE_Y; idx += nthreads) {
     const int ly = idx / CDP_TILE_X, lx = idx - ly * CDP_TILE_X;
     const int px = c.x0 + lx, py = c.y0 + ly;
