@@ -109,9 +109,6 @@ struct CdpPhotoParams {
   int32_t batch_begin;  // first sample handled by this launch
   int32_t blocks_per_image;
   float alpha;
-  // host-computed per-launch constants (kept out of the kernels' per-thread prologues)
-  float w_ssim3, w_l13;  // alpha / 3, (1 - alpha) / 3: channel means of the SSIM and L1 terms
-  float w_ssim27;        // alpha / 27: channel mean x 3x3 window mean (adjoint)
 };
 
 // ------------------------------------------------------------------------------------------

@@ -67,9 +67,6 @@ static inline void cdp_fill_photo_params(const CdpPlan& plan, const cdp_photo_ar
   kp->seed = a->noise_seed;
   kp->num_levels = plan.L; kp->batch_begin = b0; kp->blocks_per_image = plan.blocks_per_image;
   kp->alpha = a->alpha;
-  kp->w_ssim3 = a->alpha * (1.0f / 3.0f);
-  kp->w_l13 = (float)(1.0 - (double)a->alpha) * (1.0f / 3.0f);
-  kp->w_ssim27 = a->alpha / 27.0f;
 }
 
 static inline void cdp_fill_finalize_params(const CdpPlan& plan, const cdp_photo_args* a, CdpFinalizeParams* fp) {
