@@ -5,6 +5,7 @@ Drop-in replacements for the reference's hot-path classes (``CameraModel``, ``Im
 sm_100a CUDA kernels behind a C ABI (include/codeps_photo.h).  See DESIGN.md.
 """
 from .camera import CameraModel
+from .evaluator import DepthEvaluator
 from .heads import disp_to_depth, transformation_from_parameters
 from .install import install, uninstall
 from .losses import (EdgeAwareSmoothnessLoss, FlowSmoothnessLoss, FlowSparsityLoss, ReconstructionLoss,
@@ -13,5 +14,5 @@ from .mixup import warp_c2c
 from .warper import CoordinateWarper, ImageWarper
 
 __all__ = ["CameraModel", "ImageWarper", "CoordinateWarper", "SSIMLoss", "ReconstructionLoss",
-           "EdgeAwareSmoothnessLoss", "FlowSmoothnessLoss", "FlowSparsityLoss", "install", "uninstall", "transformation_from_parameters", "disp_to_depth", "warp_c2c"]
+           "EdgeAwareSmoothnessLoss", "FlowSmoothnessLoss", "FlowSparsityLoss", "install", "uninstall", "transformation_from_parameters", "disp_to_depth", "warp_c2c", "DepthEvaluator"]
 __version__ = "0.1.0"

@@ -80,6 +80,9 @@ SIGNATURES = {
     "cdp_flow_sparsity_fwd": (c_int32, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int32, c_void_p,
                                         c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_scale_fwd": (c_int32, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "cdp_depth_metrics_scratch_bytes": (c_size_t, [c_int32, c_int32]),
+    "cdp_depth_metrics_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int32, c_int32, c_int32, c_int32,
+                                        c_int32, c_float, c_float, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_warp_c2c_fwd": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                    c_void_p, ctypes.c_double, c_int32, c_int32, c_void_p, c_void_p]),
 }

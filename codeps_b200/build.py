@@ -17,7 +17,7 @@ REPO = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcodeps_photo.so")
 SOURCES = [os.path.join(CSRC, "cdp_api.cu")]
-HEADERS = [os.path.join(CSRC, n) for n in ("cdp_common.h", "cdp_math.h", "cdp_kernels.h", "cdp_photo_tile.h", "cdp_plan.h", "cdp_flow.h", "cdp_c2c.h")] + \
+HEADERS = [os.path.join(CSRC, n) for n in ("cdp_common.h", "cdp_math.h", "cdp_kernels.h", "cdp_photo_tile.h", "cdp_plan.h", "cdp_flow.h", "cdp_c2c.h", "cdp_metrics.h")] + \
           [os.path.join(REPO, "include", "codeps_photo.h")]
 
 NVCC_FLAGS = [

@@ -854,3 +854,182 @@ extern "C" int cdp_warp_c2c_fwd(const void* src, int32_t src_is_f64, int32_t bat
   }
   return CDP_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// depth metrics (cdp_metrics.h): DepthEvaluator.compute_depth_metrics
+// ------------------------------------------------------------------------------------------
+// warp-parallel form of cdp_metrics_scan: lane l owns bins [8l, 8l+8); all lanes return the result
+__device__ __forceinline__ void cdp_metrics_scan_warp(const uint32_t* hist256, uint32_t rank, int lane, uint32_t& bin,
+                                                      uint32_t& rank_out, uint32_t& total) {
+  uint32_t c[8], mine = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j] = hist256[lane * 8 + j]; mine += c[j]; }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
+  }
+  total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t excl = incl - mine;
+  const bool here = rank >= excl && rank < incl;
+  uint32_t b = 255, r = 0;
+  if (here) {
+    uint32_t acc = excl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (rank >= acc && rank < acc + c[j]) { b = lane * 8 + j; r = rank - acc; }
+      acc += c[j];
+    }
+  }
+  const uint32_t who = __ballot_sync(0xffffffffu, here);
+  const int src = who ? __ffs(who) - 1 : 0;
+  bin = __shfl_sync(0xffffffffu, b, src);
+  rank_out = __shfl_sync(0xffffffffu, r, src);
+  if (!who) { bin = 255; rank_out = 0; }
+}
+
+__device__ __forceinline__ void cdp_metrics_state_warp(const CdpMetricsParams& p, int unit, int arr, int passes, int lane,
+                                                       uint32_t& prefix, uint32_t& rank, uint32_t& count) {
+  uint32_t bin, r, total;
+  prefix = 0; rank = 0; count = 0;
+  for (int q = 0; q < passes; ++q) {
+    const uint32_t* h = cdp_metrics_hist(p, q, unit, arr);
+    if (q == 0) {
+      cdp_metrics_scan_warp(h, 0, lane, bin, r, total);  // total = number of valid elements
+      count = total;
+      rank = count ? (count - 1) / 2 : 0;
+    }
+    cdp_metrics_scan_warp(h, rank, lane, bin, r, total);
+    prefix |= bin << (24 - 8 * q);
+    rank = r;
+  }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(CDP_METRICS_THREADS) cdp_metrics_hist_kernel(const __grid_constant__ CdpMetricsParams p) {
+  __shared__ uint32_t h[CDP_METRICS_THREADS / 32][2][256];  // one private histogram pair per warp
+  __shared__ uint32_t prefix_s[2];
+  const int unit = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (CDP_METRICS_THREADS / 32) * 2 * 256; i += blockDim.x) (&h[0][0][0])[i] = 0;
+  if (PASS > 0 && warp < 2) {
+    uint32_t prefix, rank, count;
+    cdp_metrics_state_warp(p, unit, warp, PASS, lane, prefix, rank, count);
+    if (lane == 0) prefix_s[warp] = prefix;
+  }
+  __syncthreads();
+  const uint32_t pre_g = PASS > 0 ? prefix_s[0] : 0, pre_p = PASS > 0 ? prefix_s[1] : 0;
+  const int base = blockIdx.x * CDP_METRICS_CHUNK;
+#pragma unroll 4
+  for (int k = 0; k < CDP_METRICS_PER_THREAD; ++k) {
+    const int i = base + k * CDP_METRICS_THREADS + threadIdx.x;
+    float g;
+    if (i < p.n && cdp_metrics_valid(p, unit, i, g)) {
+      const uint32_t kg = cdp_metrics_key(g), kp = cdp_metrics_key(__ldg(p.pred + (size_t)unit * p.n + i));
+      if (cdp_metrics_match(kg, pre_g, PASS)) atomicAdd(&h[warp][0][(kg >> (24 - 8 * PASS)) & 255u], 1u);
+      if (cdp_metrics_match(kp, pre_p, PASS)) atomicAdd(&h[warp][1][(kp >> (24 - 8 * PASS)) & 255u], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t* out = p.hist + (((size_t)PASS * p.units + unit) * 2) * 256;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < CDP_METRICS_THREADS / 32; ++w) s += (&h[w][0][0])[i];
+    if (s) atomicAdd(out + i, s);  // integer counters: exact and order-independent
+  }
+}
+
+__global__ void __launch_bounds__(CDP_METRICS_THREADS) cdp_metrics_stats_kernel(const __grid_constant__ CdpMetricsParams p) {
+  __shared__ float red[(CDP_METRICS_THREADS / 32) * CDP_METRICS_NSTATS];
+  __shared__ float med_s[2];
+  const int unit = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < 2) {
+    uint32_t prefix, rank, count;
+    cdp_metrics_state_warp(p, unit, warp, CDP_METRICS_PASSES, lane, prefix, rank, count);
+    if (lane == 0) med_s[warp] = cdp_metrics_unkey(prefix);
+  }
+  __syncthreads();
+  const float ratio = p.use_gt_scale ? med_s[0] / med_s[1] : 1.0f;  // gt.median() / pred.median()
+  float acc[CDP_METRICS_NSTATS];
+#pragma unroll
+  for (int j = 0; j < CDP_METRICS_NSTATS; ++j) acc[j] = 0.f;
+  const int base = blockIdx.x * CDP_METRICS_CHUNK;
+#pragma unroll 2
+  for (int k = 0; k < CDP_METRICS_PER_THREAD; ++k) {
+    const int i = base + k * CDP_METRICS_THREADS + threadIdx.x;
+    float g;
+    if (i < p.n && cdp_metrics_valid(p, unit, i, g))
+      cdp_metrics_element(p, g, __ldg(p.pred + (size_t)unit * p.n + i), ratio, acc);
+  }
+  float* rec = p.part + ((size_t)unit * p.blocks + blockIdx.x) * CDP_METRICS_REC;
+  cdp_block_reduce_store(acc, red, rec);
+}
+
+// one warp per unit (fixed order), thread 0 averages the units in index order
+__global__ void __launch_bounds__(1024) cdp_metrics_finalize_kernel(const __grid_constant__ CdpMetricsParams p) {
+  __shared__ double unit_stats[32][CDP_METRICS_NSTATS];
+  __shared__ int unit_ok[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  double total[CDP_METRICS_NSTATS];
+  for (int j = 0; j < CDP_METRICS_NSTATS; ++j) total[j] = 0.0;
+  int with_gt = 0;
+  for (int u0 = 0; u0 < p.units; u0 += nwarps) {
+    const int u = u0 + warp;
+    if (u < p.units) {
+      double sums[CDP_METRICS_NSTATS];
+      for (int j = 0; j < CDP_METRICS_NSTATS; ++j)
+        sums[j] = cdp_warp_butterfly(cdp_lane_sum(p.part + (size_t)u * p.blocks * CDP_METRICS_REC + j, p.blocks,
+                                                  CDP_METRICS_REC, lane));
+      uint32_t bin, r, count;
+      cdp_metrics_scan_warp(cdp_metrics_hist(p, 0, u, 0), 0, lane, bin, r, count);
+      if (lane == 0) {
+        double out[CDP_METRICS_NSTATS];
+        unit_ok[warp] = cdp_metrics_unit_stats(sums, count, out) ? 1 : 0;
+        for (int j = 0; j < CDP_METRICS_NSTATS; ++j) unit_stats[warp][j] = out[j];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int w = 0; w < nwarps && u0 + w < p.units; ++w) {
+        with_gt += unit_ok[w];
+        for (int j = 0; j < CDP_METRICS_NSTATS; ++j) total[j] += unit_ok[w] ? unit_stats[w][j] : (double)NAN;
+      }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < CDP_METRICS_NSTATS; ++j) p.out[j] = (float)(total[j] / (double)p.units);
+    p.out[CDP_METRICS_NSTATS] = (float)with_gt;
+  }
+}
+
+extern "C" size_t cdp_depth_metrics_scratch_bytes(int32_t units, int32_t count) {
+  return cdp_metrics_scratch_total(units, count);
+}
+
+extern "C" int cdp_depth_metrics_fwd(const float* depth_gt, const float* depth_pred, const int64_t* labels,
+                                     int64_t class_id, int32_t units, int32_t count, int32_t height, int32_t width,
+                                     int32_t garg_crop, float min_depth, float max_depth, int32_t use_gt_scale,
+                                     float* out, void* scratch, size_t scratch_bytes, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDP_REQUIRE(depth_gt && depth_pred && out && scratch, "null pointer");
+  CDP_REQUIRE(units >= 1 && units <= 65535 && count >= 1, "invalid shape: %d units of %d elements", units, count);
+  CdpMetricsParams p;
+  CDP_REQUIRE(cdp_fill_metrics_params(&p, depth_gt, depth_pred, labels, class_id, units, count, width, height, garg_crop,
+                                      min_depth, max_depth, use_gt_scale, scratch, out),
+              "invalid arguments (depth range, or crop without height*width == count)");
+  const size_t need = cdp_metrics_scratch_total(units, count);
+  if (scratch_bytes < need) return cdp_fail(CDP_ERR_WORKSPACE, "scratch too small: %zu < %zu", scratch_bytes, need);
+  CDP_CUDA(cudaMemsetAsync(p.hist, 0, cdp_metrics_hist_bytes(units), stream));
+  dim3 grid(p.blocks, units);
+  cdp_metrics_hist_kernel<0><<<grid, CDP_METRICS_THREADS, 0, stream>>>(p);
+  cdp_metrics_hist_kernel<1><<<grid, CDP_METRICS_THREADS, 0, stream>>>(p);
+  cdp_metrics_hist_kernel<2><<<grid, CDP_METRICS_THREADS, 0, stream>>>(p);
+  cdp_metrics_hist_kernel<3><<<grid, CDP_METRICS_THREADS, 0, stream>>>(p);
+  CDP_LAUNCH_CHECK("cdp_metrics_hist_kernel");
+  cdp_metrics_stats_kernel<<<grid, CDP_METRICS_THREADS, 0, stream>>>(p);
+  CDP_LAUNCH_CHECK("cdp_metrics_stats_kernel");
+  cdp_metrics_finalize_kernel<<<1, 1024, 0, stream>>>(p);
+  CDP_LAUNCH_CHECK("cdp_metrics_finalize_kernel");
+  return CDP_OK;
+}

@@ -636,3 +636,8 @@ CDP_HD float cdp_disp_to_depth_grad(float g_depth, float depth, float span) { re
 // 9. Camera-to-camera warp at constant depth (Mixup.warp_c2c): see cdp_c2c.h
 // ==========================================================================================
 #include "cdp_c2c.h"
+
+// ==========================================================================================
+// 10. Depth metrics (DepthEvaluator.compute_depth_metrics): see cdp_metrics.h
+// ==========================================================================================
+#include "cdp_metrics.h"

@@ -16,6 +16,7 @@ import sys
 from .camera import CameraModel
 from .losses import (EdgeAwareSmoothnessLoss, FlowSmoothnessLoss, FlowSparsityLoss, ReconstructionLoss,
                      SSIMLoss)
+from .evaluator import DepthEvaluator
 from .mixup import warp_c2c
 from .warper import CoordinateWarper, ImageWarper
 
@@ -26,14 +27,18 @@ _PATCHES = {
     "algos.depth": {"CameraModel": CameraModel, "ImageWarper": ImageWarper, "SSIMLoss": SSIMLoss,
                     "ReconstructionLoss": ReconstructionLoss,
                     "EdgeAwareSmoothnessLoss": EdgeAwareSmoothnessLoss,
-                    "FlowSmoothnessLoss": FlowSmoothnessLoss, "FlowSparsityLoss": FlowSparsityLoss},
+                    "FlowSmoothnessLoss": FlowSmoothnessLoss, "FlowSparsityLoss": FlowSparsityLoss,
+                    "DepthEvaluator": DepthEvaluator},
     "algos": {"SSIMLoss": SSIMLoss, "ReconstructionLoss": ReconstructionLoss,
               "EdgeAwareSmoothnessLoss": EdgeAwareSmoothnessLoss,
               "FlowSmoothnessLoss": FlowSmoothnessLoss, "FlowSparsityLoss": FlowSparsityLoss},
     "codeps.model_setup": {"SSIMLoss": SSIMLoss, "ReconstructionLoss": ReconstructionLoss,
                            "EdgeAwareSmoothnessLoss": EdgeAwareSmoothnessLoss,
-                           "FlowSmoothnessLoss": FlowSmoothnessLoss, "FlowSparsityLoss": FlowSparsityLoss},
+                           "FlowSmoothnessLoss": FlowSmoothnessLoss, "FlowSparsityLoss": FlowSparsityLoss,
+                           "DepthEvaluator": DepthEvaluator},
     "codeps.online_adap": {"CameraModel": CameraModel},
+    "eval.depth": {"DepthEvaluator": DepthEvaluator},
+    "eval": {"DepthEvaluator": DepthEvaluator},
 }
 # static methods rebound on a class: (module, class) -> {name: function}
 _METHOD_PATCHES = {("datasets.mixup", "Mixup"): {"warp_c2c": warp_c2c}}

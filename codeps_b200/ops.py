@@ -308,6 +308,38 @@ def flow_sparsity_loss(flow_maps) -> torch.Tensor:
     return _FlowLoss.apply("sparsity", True, *_check_flow_maps(flow_maps))
 
 
+def depth_metrics(depth_gt: torch.Tensor, depth_pred: torch.Tensor, min_depth: float, max_depth: float,
+                  use_gt_scale: bool, garg_crop: bool = False, labels: Optional[torch.Tensor] = None,
+                  class_id: int = 0) -> torch.Tensor:
+    """cdp_depth_metrics_fwd.  depth_gt / depth_pred: [B,1,H,W] fp32 CUDA.  Without ``labels`` every
+    image is a unit and the result is the batch mean; with ``labels`` ([B,1,H,W] int64) the whole
+    batch restricted to ``class_id`` is one unit.  Returns a device tensor of 8 floats: d_a1, d_a2,
+    d_a3, d_rmse, d_rmse_log, d_abs_rel, d_sq_rel, number of units with ground truth."""
+    gt = _require_cuda_f32(depth_gt, "depth_gt", (None, 1, None, None))
+    b, _, h, w = gt.shape
+    pred = _require_cuda_f32(depth_pred.detach(), "depth_pred", (b, 1, h, w))
+    device = gt.device
+    if labels is not None:
+        if not labels.is_cuda or labels.dtype != torch.int64 or tuple(labels.shape) != (b, 1, h, w):
+            raise ValueError("labels must be an int64 CUDA tensor of shape [B,1,H,W]")
+        labels = labels.contiguous()
+        units, count = 1, b * h * w
+        if garg_crop:
+            raise NotImplementedError("the per-class metrics of the reference do not apply the Garg crop")
+    else:
+        units, count = b, h * w
+    lib = _lib_for(device)
+    scratch = _bytes(lib.cdp_depth_metrics_scratch_bytes(units, count), device)
+    out = torch.empty(8, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(lib.cdp_depth_metrics_fwd(_ptr(gt), _ptr(pred), _ptr(labels), int(class_id), units, count, h, w,
+                                        int(garg_crop), float(min_depth), float(max_depth), int(use_gt_scale),
+                                        _ptr(out), _ptr(scratch), scratch.numel(), _stream(device)),
+              "cdp_depth_metrics_fwd")
+    _LAUNCHES["count"] += 6
+    return out
+
+
 def warp_c2c(src: torch.Tensor, k_src: np.ndarray, k_tgt: np.ndarray, out_hw: Tuple[int, int],
              depth_val: float = 1.0, interp_mode: str = "bilinear", padding_mode: str = "border") -> torch.Tensor:
     """cdp_warp_c2c_fwd: [B,C,Hs,Ws] (fp32 or fp64, CUDA) -> fp64 [B,C,Ht,Wt]; k_* are [B,4] host

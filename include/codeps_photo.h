@@ -227,6 +227,28 @@ int cdp_warp_c2c_fwd(const void* src, int32_t src_is_f64, int32_t batch, int32_t
                      const double* K_src, const double* K_tgt, double depth_val, int32_t nearest,
                      int32_t padding_zeros, double* out, cdp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Depth metrics: DepthEvaluator.compute_depth_metrics
+ * (eval/depth.py:21-70, statistics :109-133), called inside DepthAlgo.training
+ * (algos/depth.py:468-469), and the per-class variant (eval/depth.py:72-106).
+ *
+ * A unit is one image (units = B, count = H*W) or the whole batch restricted to one class
+ * (units = 1, count = B*H*W, labels + class_id).  Per unit over the elements with depth_gt > 0
+ * (and inside the Garg crop when garg_crop != 0, which needs height * width == count): optional
+ * median scaling pred *= median(gt) / median(pred) (lower median, as torch.median), clamp of both
+ * to [min_depth, max_depth], then d_a1, d_a2, d_a3, d_rmse, d_rmse_log, d_abs_rel, d_sq_rel;
+ * out[0..6] = mean of the unit values, out[7] = number of units that had ground truth (a unit
+ * without any makes the means NaN; the reference raises there).  No host synchronisation.
+ * depth_gt / depth_pred: device float [units, count]; labels: device int64 [units, count] or null;
+ * out: device float[8]; scratch: cdp_depth_metrics_scratch_bytes(units, count) bytes.
+ * 1 memset + 6 launches.
+ * ------------------------------------------------------------------------------------------- */
+size_t cdp_depth_metrics_scratch_bytes(int32_t units, int32_t count);
+int cdp_depth_metrics_fwd(const float* depth_gt, const float* depth_pred, const int64_t* labels,
+                          int64_t class_id, int32_t units, int32_t count, int32_t height, int32_t width,
+                          int32_t garg_crop, float min_depth, float max_depth, int32_t use_gt_scale,
+                          float* out, void* scratch, size_t scratch_bytes, cdp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

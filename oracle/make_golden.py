@@ -199,6 +199,35 @@ def c2c_fixture(ref_misc, out_dir):
     print(f"c2c -> {path} ({os.path.getsize(path) / 1e3:.1f} kB)")
 
 
+def metrics_fixture(out_dir):
+    """Outputs of the reference's DepthEvaluator (eval/depth.py) on seeded sparse ground truth."""
+    from eval.depth import DepthEvaluator
+    gen = torch.Generator().manual_seed(63)
+    b, h, w = 3, 37, 61
+    pred = 0.5 + 60 * torch.rand(b, 1, h, w, generator=gen)**2
+    gt = pred[:, 0] * (1.3 + 0.25 * torch.randn(b, h, w, generator=gen))      # off-scale by ~1.3
+    gt[torch.rand(b, h, w, generator=gen) < 0.6] = 0.0                         # sparse (LiDAR-like), VOID = 0
+    gt[1, :20] = 0.0
+    gt = gt.clamp(min=0.0)
+    sem = torch.randint(0, 5, (b, h, w), generator=gen)
+    sem[torch.rand(b, h, w, generator=gen) < 0.1] = 255
+    sem[sem == 3] = 2
+    gt[sem == 4] = 0.0                                                         # a class without ground truth
+    blob = {"gt": gt.numpy(), "pred": pred.numpy(), "sem": sem.numpy()}
+    configs = {"scaled": (True, (0.1, 80.0), False), "raw": (False, (1.0, 50.0), False),
+               "garg": (True, (0.001, 80.0), True)}
+    for name, (scale, rng, garg) in configs.items():
+        ev = DepthEvaluator(scale, rng, garg)
+        for k, v in ev.compute_depth_metrics(gt.clone(), pred.clone()).items():
+            blob[f"{name}_{k}"] = v.numpy()
+        if not garg:
+            for k, v in ev.compute_depth_metrics_per_class(gt.clone(), pred.clone(), sem.clone()).items():
+                blob[f"{name}_class_{k}"] = v.numpy()
+    path = os.path.join(out_dir, "metrics.npz")
+    np.savez_compressed(path, **blob)
+    print(f"metrics -> {path} ({os.path.getsize(path) / 1e3:.1f} kB)")
+
+
 def flow_fixture(ref_depth, out_dir):
     """Outputs of the reference's FlowSmoothnessLoss / FlowSparsityLoss (fp64 arbiter + fp32)."""
     gen = torch.Generator().manual_seed(91)
@@ -241,6 +270,7 @@ def main():
     heads_fixture(out_dir)
     flow_fixture(ref_depth, out_dir)
     c2c_fixture(ref_misc, out_dir)
+    metrics_fixture(out_dir)
     if "--heads-only" in sys.argv or "--small-only" in sys.argv:
         return
     for name, (b, w, h, k, scales, seed, noise_seed, kw) in CASES.items():

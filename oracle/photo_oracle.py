@@ -342,3 +342,58 @@ def warp_c2c(k_src, k_tgt, in_src: torch.Tensor, out_hw: Tuple[int, int], depth_
     return F.grid_sample(in_src.double(), torch.stack(grids), mode=interp_mode, padding_mode=padding_mode,
                          align_corners=True)
 
+
+DEPTH_STAT_KEYS = ("d_a1", "d_a2", "d_a3", "d_rmse", "d_rmse_log", "d_abs_rel", "d_sq_rel")
+
+
+def _depth_stats(gt: torch.Tensor, pred: torch.Tensor):
+    """DepthEvaluator._compute_depth_stats (/root/reference/eval/depth.py:108-133)."""
+    thresh = torch.max(gt / pred, pred / gt)
+    return {"d_a1": (thresh < 1.25).float().mean(), "d_a2": (thresh < 1.25**2).float().mean(),
+            "d_a3": (thresh < 1.25**3).float().mean(), "d_rmse": torch.sqrt(((gt - pred)**2).mean()),
+            "d_rmse_log": torch.sqrt(((torch.log(gt) - torch.log(pred))**2).mean()),
+            "d_abs_rel": torch.mean(torch.abs(gt - pred) / gt), "d_sq_rel": torch.mean((gt - pred)**2 / gt)}
+
+
+def depth_metrics(depth_gt: torch.Tensor, depth_pred: torch.Tensor, depth_range: Tuple[float, float],
+                  use_gt_scale: bool, garg_crop: bool = False):
+    """DepthEvaluator.compute_depth_metrics (/root/reference/eval/depth.py:21-70): per image over
+    gt > 0 (and the Garg crop), median scaling, clamp, statistics; mean over the batch."""
+    if depth_gt.dim() == 3:
+        depth_gt = depth_gt.unsqueeze(1)
+    mask = depth_gt > 0
+    if garg_crop:
+        h, w = depth_gt.shape[2:]
+        crop = torch.zeros_like(mask)
+        crop[:, :, int(0.4080 * h):int(0.9891 * h), int(0.0354 * w):int(0.9638 * w)] = 1
+        mask = mask & crop
+    total = {}
+    for b in range(depth_gt.shape[0]):
+        gt, pred = depth_gt[b][mask[b]], depth_pred[b][mask[b]]
+        if use_gt_scale:
+            pred = pred * (gt.median() / pred.median())
+        gt, pred = gt.clamp(depth_range[0], depth_range[1]), pred.clamp(depth_range[0], depth_range[1])
+        for k, v in _depth_stats(gt, pred).items():
+            total[k] = total.get(k, 0) + v
+    return {k: v / depth_gt.shape[0] for k, v in total.items()}
+
+
+def depth_metrics_per_class(depth_gt, depth_pred, semantic_gt, depth_range, use_gt_scale: bool):
+    """DepthEvaluator.compute_depth_metrics_per_class (/root/reference/eval/depth.py:72-106)."""
+    depth_gt, semantic_gt = depth_gt.unsqueeze(1), semantic_gt.unsqueeze(1)
+    out = {}
+    for c in torch.unique(semantic_gt):
+        if c == 255:
+            continue
+        gt, pred = depth_gt[semantic_gt == c], depth_pred[semantic_gt == c]
+        valid = gt > 0
+        if not valid.any():
+            continue
+        gt, pred = gt[valid], pred[valid]
+        if use_gt_scale:
+            pred = pred * (gt.median() / pred.median())
+        gt, pred = gt.clamp(depth_range[0], depth_range[1]), pred.clamp(depth_range[0], depth_range[1])
+        for k, v in _depth_stats(gt, pred).items():
+            out[f"{k}_c{int(c)}"] = v
+    return out
+

@@ -184,6 +184,56 @@ EMU_API int emu_flow_loss(const float* const* maps, int32_t n_maps, int32_t plan
   return CDP_OK;
 }
 
+// depth metrics (cdp_metrics.h): sequential form of the four histogram passes, the statistics
+// pass and the finalize step
+EMU_API int emu_depth_metrics(const float* gt, const float* pred, const int64_t* labels, int64_t class_id, int32_t units,
+                              int32_t n, int32_t H, int32_t W, int32_t garg, float lo, float hi, int32_t use_gt_scale,
+                              float* out) {
+  std::vector<unsigned char> scratch(cdp_metrics_scratch_total(units, n), 0);
+  CdpMetricsParams p;
+  if (!cdp_fill_metrics_params(&p, gt, pred, labels, class_id, units, n, W, H, garg, lo, hi, use_gt_scale,
+                               scratch.data(), out))
+    return CDP_ERR_INVALID;
+  for (int pass = 0; pass < CDP_METRICS_PASSES; ++pass)
+    for (int u = 0; u < units; ++u) {
+      uint32_t pre[2] = {0, 0}, rank, count = pass ? cdp_metrics_count(p, u) : 0;
+      for (int arr = 0; arr < 2 && pass; ++arr) cdp_metrics_state(p, u, arr, pass, count, pre[arr], rank);
+      uint32_t* h = p.hist + (((size_t)pass * units + u) * 2) * 256;
+      for (int i = 0; i < n; ++i) {
+        float g;
+        if (!cdp_metrics_valid(p, u, i, g)) continue;
+        const uint32_t kg = cdp_metrics_key(g), kp = cdp_metrics_key(pred[(size_t)u * n + i]);
+        if (cdp_metrics_match(kg, pre[0], pass)) ++h[(kg >> (24 - 8 * pass)) & 255u];
+        if (cdp_metrics_match(kp, pre[1], pass)) ++h[256 + ((kp >> (24 - 8 * pass)) & 255u)];
+      }
+    }
+  double total[CDP_METRICS_NSTATS] = {0, 0, 0, 0, 0, 0, 0};
+  int with_gt = 0;
+  for (int u = 0; u < units; ++u) {
+    const uint32_t count = cdp_metrics_count(p, u);
+    uint32_t kg, kp, rank;
+    cdp_metrics_state(p, u, 0, CDP_METRICS_PASSES, count, kg, rank);
+    cdp_metrics_state(p, u, 1, CDP_METRICS_PASSES, count, kp, rank);
+    const float ratio = use_gt_scale ? cdp_metrics_unkey(kg) / cdp_metrics_unkey(kp) : 1.0f;
+    double sums[CDP_METRICS_NSTATS] = {0, 0, 0, 0, 0, 0, 0};
+    for (int blk = 0; blk < p.blocks; ++blk) {  // per-block fp32 records, fp64 combine
+      float acc[CDP_METRICS_NSTATS] = {0, 0, 0, 0, 0, 0, 0};
+      for (int i = blk * CDP_METRICS_CHUNK; i < n && i < (blk + 1) * CDP_METRICS_CHUNK; ++i) {
+        float g;
+        if (cdp_metrics_valid(p, u, i, g)) cdp_metrics_element(p, g, pred[(size_t)u * n + i], ratio, acc);
+      }
+      for (int j = 0; j < CDP_METRICS_NSTATS; ++j) sums[j] += acc[j];
+    }
+    double st[CDP_METRICS_NSTATS];
+    const bool ok = cdp_metrics_unit_stats(sums, count, st);
+    with_gt += ok;
+    for (int j = 0; j < CDP_METRICS_NSTATS; ++j) total[j] += ok ? st[j] : (double)NAN;
+  }
+  for (int j = 0; j < CDP_METRICS_NSTATS; ++j) out[j] = (float)(total[j] / units);
+  out[CDP_METRICS_NSTATS] = (float)with_gt;
+  return CDP_OK;
+}
+
 // camera-to-camera warp (cdp_c2c.h)
 EMU_API int emu_warp_c2c(const void* src, int32_t src_is_f64, int32_t B, int32_t C, int32_t Hs, int32_t Ws, int32_t Ht,
                          int32_t Wt, const double* Ks, const double* Kt, double depth, int32_t nearest, int32_t zeros,

@@ -18,7 +18,7 @@ REPO = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "cdp_emu.cpp")
 LIB = os.path.join(HERE, "emu", "libcdp_emu.so")
 DEPS = [SRC] + [os.path.join(REPO, "codeps_b200", "csrc", n)
-                for n in ("cdp_common.h", "cdp_math.h", "cdp_kernels.h", "cdp_photo_tile.h", "cdp_plan.h", "cdp_flow.h", "cdp_c2c.h")]
+                for n in ("cdp_common.h", "cdp_math.h", "cdp_kernels.h", "cdp_photo_tile.h", "cdp_plan.h", "cdp_flow.h", "cdp_c2c.h", "cdp_metrics.h")]
 
 _lib = None
 
@@ -140,6 +140,23 @@ def flow_loss(maps, kind, wrap_around=True):
                            c_int32(1 if kind == "sparsity" else 0), c_int32(int(wrap_around)), _p(loss), _p(unit))
     assert rc == 0, rc
     return loss[0].clone(), [unit[i] for i in range(n)]
+
+
+def depth_metrics(gt, pred, lo, hi, use_gt_scale, garg_crop=False, labels=None, class_id=0):
+    """gt / pred [B,1,H,W]; returns the 8 output floats (7 statistics + units with ground truth)."""
+    from ctypes import c_int64
+    lib = load()
+    gt, pred = _f32(gt), _f32(pred)
+    b, _, h, w = gt.shape
+    units, n = (1, b * h * w) if labels is not None else (b, h * w)
+    if labels is not None:
+        labels = labels.to(torch.int64).contiguous()
+    out = torch.zeros(8)
+    rc = lib.emu_depth_metrics(_p(gt), _p(pred), _p(labels), c_int64(int(class_id)), c_int32(units), c_int32(n),
+                               c_int32(h), c_int32(w), c_int32(int(garg_crop)), c_float(lo), c_float(hi),
+                               c_int32(int(use_gt_scale)), _p(out))
+    assert rc == 0, rc
+    return out
 
 
 def warp_c2c(src, k_src, k_tgt, out_hw, depth_val=1.0, interp_mode="bilinear", padding_mode="border"):

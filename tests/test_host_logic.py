@@ -144,7 +144,7 @@ def test_product_package_never_imports_the_oracle_or_emulator():
 def test_install_rebinds_reference_names():
     """install() swaps the classes into (stand-ins for) the reference's modules."""
     names = ["misc", "misc.camera_model", "misc.image_warper", "algos", "algos.depth", "codeps", "codeps.model_setup",
-             "datasets", "datasets.mixup"]
+             "datasets", "datasets.mixup", "eval", "eval.depth"]
     saved = {n: sys.modules.get(n) for n in names}
     try:
         for n in names:
@@ -156,6 +156,7 @@ def test_install_rebinds_reference_names():
         sys.modules["misc"].ImageWarper = sentinel
         sys.modules["codeps.model_setup"].EdgeAwareSmoothnessLoss = sentinel
         sys.modules["algos.depth"].FlowSparsityLoss = sentinel
+        sys.modules["eval.depth"].DepthEvaluator = sentinel
 
         class Mixup:  # stand-in for datasets.mixup.Mixup with its static method
             @staticmethod
@@ -167,6 +168,7 @@ def test_install_rebinds_reference_names():
         sys.modules["datasets.mixup"].Mixup = Mixup
         patched = codeps_b200.install(import_missing=False)
         assert "datasets.mixup.Mixup.warp_c2c" in patched and "algos.depth.FlowSparsityLoss" in patched
+        assert sys.modules["eval.depth"].DepthEvaluator is codeps_b200.DepthEvaluator
         assert Mixup.warp_c2c is codeps_b200.warp_c2c and Mixup().warp_c2c is codeps_b200.warp_c2c
         assert "algos.depth.ReconstructionLoss" in patched and "misc.ImageWarper" in patched
         assert sys.modules["algos.depth"].ReconstructionLoss is codeps_b200.ReconstructionLoss
