@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cityscapes_b8")
     ap.add_argument("--noise", choices=("torch", "fused"), default="torch")
+    ap.add_argument("--intrinsics", choices=("host", "device"), default="host",
+                    help="host: CameraModel objects hold host values (kernel parameter space); device: lazy "
+                         "CameraModel.from_tensor of CUDA rows, the kernels read the calibration from HBM")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -222,6 +225,9 @@ def main():
                  for i in range(INPUT_SETS)]
     dev_sets = [hs.to(dev) for hs in host_sets]
     cams = [hs.camera_models() for hs in host_sets]
+    if args.intrinsics == "device":
+        k_dev = [hs.intrinsics.to(dev) for hs in host_sets]
+        cams = [[codeps_b200.CameraModel.from_tensor(w, h, k[i]) for i in range(batch)] for k in k_dev]
     resident_bytes = sum(hs.nbytes() for hs in host_sets)
 
     recon_fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), NUM_SCALES, dev, noise=args.noise)
@@ -423,7 +429,7 @@ def main():
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "per_gpu_batch": batch,
-                       "global_batch": batch * n_gpus, "num_scales": NUM_SCALES, "noise": args.noise,
+                       "global_batch": batch * n_gpus, "num_scales": NUM_SCALES, "noise": args.noise, "intrinsics": args.intrinsics,
                        "timed_with": "cuda_graph_replay" if use_graph else "eager_launches",
                        "l2": f"{INPUT_SETS} rotating input sets, {resident_bytes / 1e6:.0f} MB resident > 126 MB L2",
                        "loss_weights": [RECON_WEIGHT, SMOOTH_WEIGHT]},

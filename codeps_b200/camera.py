@@ -6,6 +6,11 @@ method names, so callers such as ``CodepsNet.forward``
 (/root/reference/codeps/online_adap.py:95-100) keep working.  Everything here is
 host-side Python; the per-pixel math lives in the CUDA kernels, which receive
 the four intrinsics by value (kernel parameter space = constant bank).
+
+``from_tensor`` of a CUDA tensor is lazy: the object keeps the device tensor and reads it back
+only when somebody asks for ``.intrinsics`` on the host.  ``ReconstructionLoss`` hands the device
+values straight to its kernels, so the per-sample host synchronisation of the reference
+(/root/reference/misc/camera_model.py:27) disappears from the training step.
 """
 from __future__ import annotations
 
@@ -30,7 +35,28 @@ class CameraModel:
             else:
                 assert value >= 0, f"{name} < 0 is not allowed"
         self.image_size = {"width": img_width, "height": img_height}
-        self.intrinsics = OrderedDict(zip(_KEYS, (fx, fy, cx, cy)))
+        self._intrinsics = OrderedDict(zip(_KEYS, (fx, fy, cx, cy)))
+        self._device_intrinsics = None  # CUDA tensor [4] when built lazily by from_tensor
+
+    @property
+    def intrinsics(self) -> OrderedDict:
+        """fx, fy, cx, cy on the host (read back from the device on first use if built lazily)."""
+        if self._intrinsics is None:
+            k = self._device_intrinsics.cpu().numpy()
+            for name, value in zip(_KEYS, k):
+                assert value >= 0, f"{name} < 0 is not allowed"
+            self._intrinsics = OrderedDict(zip(_KEYS, (k[0], k[1], k[2], k[3])))
+        return self._intrinsics
+
+    @intrinsics.setter
+    def intrinsics(self, value) -> None:
+        self._intrinsics = value
+        self._device_intrinsics = None
+
+    @property
+    def device_intrinsics(self):
+        """The CUDA tensor [4] this model was built from (None for host-built models)."""
+        return self._device_intrinsics
 
     # ------------------------------------------------------------------ conversions
     def to_tensor(self) -> torch.Tensor:
@@ -38,9 +64,20 @@ class CameraModel:
 
     @classmethod
     def from_tensor(cls, img_width: int, img_height: int, intrinsics: torch.Tensor) -> "CameraModel":
-        # camera_model.py:26-29 -- one D2H sync per sample; values stay numpy float32 scalars so
-        # that later scaling happens in the same precision as in the reference.
-        k = intrinsics.detach().cpu().numpy()
+        # camera_model.py:26-29.  The reference reads the four values back right here (one D2H
+        # sync per sample); for a CUDA fp32 tensor that read-back is deferred until the host values
+        # are actually asked for.  Values stay numpy float32 scalars so that later scaling happens in
+        # the same precision as in the reference.
+        t = intrinsics.detach()
+        if t.is_cuda and t.dtype == torch.float32 and t.dim() == 1 and t.numel() == 4:
+            assert img_width > 0, "img_width <= 0 is not allowed"
+            assert img_height > 0, "img_height <= 0 is not allowed"
+            cam = cls.__new__(cls)
+            cam.image_size = {"width": img_width, "height": img_height}
+            cam._intrinsics = None
+            cam._device_intrinsics = t
+            return cam
+        k = t.cpu().numpy()
         return cls(img_width, img_height, k[0], k[1], k[2], k[3])
 
     def as_tuple(self) -> Tuple[float, float, float, float]:

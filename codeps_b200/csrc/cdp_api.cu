@@ -166,6 +166,11 @@ __global__ void __launch_bounds__(256) cdp_pyramid_fwd_kernel(const __grid_const
   cdp_pyramid_fwd_item(p, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
+__global__ void cdp_k_table_kernel(const __grid_constant__ CdpKTableParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.batch_count * p.L) cdp_k_table_entry(p, i / p.batch_count, i % p.batch_count);
+}
+
 template <bool G, bool M>
 __global__ void __launch_bounds__(CDP_PHOTO_THREADS, CDP_PHOTO_MIN_CTAS)
 cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p) {
@@ -359,7 +364,8 @@ extern "C" size_t cdp_photo_saved_bytes(int32_t batch, int32_t height, int32_t w
 static int cdp_batch_chunks(int32_t batch) { return (batch + CDP_MAX_BATCH_PER_LAUNCH - 1) / CDP_MAX_BATCH_PER_LAUNCH; }
 
 extern "C" int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels) {
-  return (num_levels > 1 ? 1 : 0) + cdp_batch_chunks(batch) + 1;
+  // pyramid, intrinsics table (per 32 samples), tile kernel, reduction
+  return (num_levels > 1 ? 1 : 0) + cdp_batch_chunks(batch) + 1 + 1;
 }
 extern "C" int cdp_photo_bwd_launches(int32_t, int32_t, int32_t with_motion) { return with_motion ? 3 : 1; }
 
@@ -371,7 +377,10 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   CDP_REQUIRE(cdp_make_plan(a->batch, a->height, a->width, a->num_levels, &plan, a->motion0 != nullptr),
               "invalid shape: batch %d, %dx%d, %d levels (every level needs >= 2x2 pixels, at most %d levels)",
               a->batch, a->width, a->height, a->num_levels, CDP_MAX_LEVELS);
-  CDP_REQUIRE(a->intrinsics_host && a->target && a->source0 && a->source1 && a->depth && a->pose0 && a->pose1 && a->loss,
+  CDP_REQUIRE(a->batch <= 65535, "batch %d exceeds the grid limit of one launch", a->batch);
+  CDP_REQUIRE((a->intrinsics_host != nullptr) != (a->intrinsics_dev != nullptr),
+              "exactly one of intrinsics_host / intrinsics_dev must be set");
+  CDP_REQUIRE(a->target && a->source0 && a->source1 && a->depth && a->pose0 && a->pose1 && a->loss,
               "null tensor pointer");
   CDP_REQUIRE(a->scratch != nullptr, "scratch is null");
   if (a->scratch_bytes < plan.scratch_floats * sizeof(float))
@@ -400,15 +409,25 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   const size_t smem = G ? CdpTileGeom<true>::SMEM_BYTES : CdpTileGeom<false>::SMEM_BYTES;
   static unsigned long long smem_done[4] = {0ull, 0ull, 0ull, 0ull};
   const bool M = plan.has_motion != 0;
-  void (*photo_kernel)(const CdpPhotoParams) =
-      G ? (M ? cdp_photo_kernel<true, true> : cdp_photo_kernel<true, false>)
-        : (M ? cdp_photo_kernel<false, true> : cdp_photo_kernel<false, false>);
-  CDP_CUDA(cdp_allow_smem(photo_kernel, smem, &smem_done[(G ? 2 : 0) + (M ? 1 : 0)]));
+  typedef void (*PhotoKernel)(const CdpPhotoParams);
+  static const PhotoKernel kernels[4] = {cdp_photo_kernel<false, false>, cdp_photo_kernel<false, true>,
+                                         cdp_photo_kernel<true, false>, cdp_photo_kernel<true, true>};
+  const int which = (G ? 2 : 0) + (M ? 1 : 0);
+  const PhotoKernel photo_kernel = kernels[which];
+  CDP_CUDA(cdp_allow_smem(photo_kernel, smem, &smem_done[which]));
+  // per-level intrinsics table: host values travel by value (<= 32 samples per launch), device
+  // values are rescaled per level
   for (int b0 = 0; b0 < plan.B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
     const int nb = cdp_chunk_size(plan.B, b0);
+    CdpKTableParams tp;
+    cdp_fill_k_table_params(plan, a, b0, nb, &tp);
+    cdp_k_table_kernel<<<(nb * plan.L + 127) / 128, 128, 0, stream>>>(tp);
+    CDP_LAUNCH_CHECK("cdp_k_table_kernel");
+  }
+  {
     CdpPhotoParams kp;
-    cdp_fill_photo_params(plan, a, b0, nb, &kp);
-    dim3 grid(plan.blocks_per_image, nb);
+    cdp_fill_photo_params(plan, a, 0, plan.B, &kp);
+    dim3 grid(plan.blocks_per_image, plan.B);
     {
       ProfScope prof_(CDP_KERNEL_PHOTO, stream);
       photo_kernel<<<grid, CDP_PHOTO_THREADS, smem, stream>>>(kp);

@@ -52,7 +52,7 @@ struct CdpTileGeom {
 };
 
 struct CdpTileCtx {
-  int lvl, b, b_local, x0, y0;  // level, sample (global / within launch), tile origin
+  int lvl, b, x0, y0;  // level, sample, tile origin
 };
 
 CDP_HD CdpTileCtx cdp_tile_ctx(const CdpPhotoParams& p, int bx, int by) {
@@ -64,14 +64,29 @@ CDP_HD CdpTileCtx cdp_tile_ctx(const CdpPhotoParams& p, int bx, int by) {
   const int ty = tile / p.lv[s].tiles_x;
   c.x0 = (tile - ty * p.lv[s].tiles_x) * CDP_TILE_X;
   c.y0 = ty * CDP_TILE_Y;
-  c.b_local = by;
   c.b = p.batch_begin + by;
   return c;
 }
 
 CDP_HD CdpCam cdp_tile_cam(const CdpPhotoParams& p, const CdpTileCtx& c) {
-  return cdp_make_cam(p.K[c.lvl][c.b_local][0], p.K[c.lvl][c.b_local][1], p.K[c.lvl][c.b_local][2],
-                      p.K[c.lvl][c.b_local][3]);
+  // per-level intrinsics table (rows are 16-byte aligned)
+  const float4 k = CDP_LDG(reinterpret_cast<const float4*>(p.K_tab) + (size_t)c.lvl * p.batch_total + c.b);
+  return cdp_make_cam(k.x, k.y, k.z, k.w);
+}
+
+// Entry (level s, sample b) of the per-level intrinsics table: the scaling of
+// CameraModel.get_scaled_model_image_size (misc/camera_model.py:36-41) -- a python float ratio of
+// the two image sizes that meets the fp32 calibration value, i.e. rounded to fp32 before the product.
+CDP_HD void cdp_k_table_entry(const CdpKTableParams& p, int s, int b_local) {
+  const int b = p.batch_begin + b_local;
+  float* o = p.K_tab + ((size_t)s * p.B + b) * 4;
+  if (p.K_full) {
+    const float* k = p.K_full + (size_t)b * 4;
+    o[0] = CDP_MUL(CDP_LDG(k + 0), p.su[s]); o[1] = CDP_MUL(CDP_LDG(k + 1), p.sv[s]);
+    o[2] = CDP_MUL(CDP_LDG(k + 2), p.su[s]); o[3] = CDP_MUL(CDP_LDG(k + 3), p.sv[s]);
+  } else {
+    for (int j = 0; j < 4; ++j) o[j] = p.K[s][b_local][j];
+  }
 }
 
 // Per-tile, per-channel constant subtracted from every staged image value (target value at the

@@ -59,14 +59,31 @@ static inline void cdp_fill_photo_params(const CdpPlan& plan, const cdp_photo_ar
     lv.block_begin = plan.block_begin[s];
     // mean over B*H_s*W_s, / 2^s, / num_levels (algos/depth.py:325-326)
     lv.weight = (float)(1.0 / ((double)plan.B * plan.Hs[s] * plan.Ws[s] * (double)(1 << s) * plan.L));
-    for (int i = 0; i < nb; ++i)
-      for (int j = 0; j < 4; ++j) kp->K[s][i][j] = a->intrinsics_host[((size_t)s * plan.B + b0 + i) * 4 + j];
   }
+  kp->K_tab = scratch + plan.off_ktab;
+  kp->batch_total = plan.B;
   kp->pose0 = a->pose0; kp->pose1 = a->pose1;
   kp->partials = scratch + plan.off_partials;
   kp->seed = a->noise_seed;
   kp->num_levels = plan.L; kp->batch_begin = b0; kp->blocks_per_image = plan.blocks_per_image;
   kp->alpha = a->alpha;
+}
+
+// parameters of the intrinsics-table kernel for samples [b0, b0 + nb)
+static inline void cdp_fill_k_table_params(const CdpPlan& plan, const cdp_photo_args* a, int b0, int nb,
+                                           CdpKTableParams* tp) {
+  memset(tp, 0, sizeof(*tp));
+  tp->K_full = a->intrinsics_host ? nullptr : a->intrinsics_dev;
+  tp->K_tab = static_cast<float*>(a->scratch) + plan.off_ktab;
+  tp->B = plan.B; tp->L = plan.L; tp->batch_begin = b0; tp->batch_count = nb;
+  for (int s = 0; s < plan.L; ++s) {
+    // scale of CameraModel.get_scaled_model_image_size: python float ratio, rounded to fp32 on use
+    tp->su[s] = (float)((double)plan.Ws[s] / (double)plan.W);
+    tp->sv[s] = (float)((double)plan.Hs[s] / (double)plan.H);
+    if (a->intrinsics_host)
+      for (int i = 0; i < nb; ++i)
+        for (int j = 0; j < 4; ++j) tp->K[s][i][j] = a->intrinsics_host[((size_t)s * plan.B + b0 + i) * 4 + j];
+  }
 }
 
 static inline void cdp_fill_finalize_params(const CdpPlan& plan, const cdp_photo_args* a, CdpFinalizeParams* fp) {

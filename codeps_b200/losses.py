@@ -107,6 +107,23 @@ class ReconstructionLoss:
         self.last_argmin: List[Tensor] = []
         self._k_cache = {}
 
+    def _device_intrinsics(self, camera_models: List[CameraModel], device) -> Optional[Tensor]:
+        """[B,4] CUDA tensor of full-resolution intrinsics if every camera model was built lazily
+        from a CUDA tensor (CameraModel.from_tensor) for this loss's image size, else None.  Rows of
+        one contiguous [B,4] tensor (the usual in_data["camera_model"][i]) are used in place."""
+        rows = [getattr(cam, "device_intrinsics", None) for cam in camera_models]
+        if not rows or any(r is None or r.device != device for r in rows):
+            return None
+        if any(cam.image_size["width"] != self.scaled_width[0] or cam.image_size["height"] != self.scaled_height[0]
+               for cam in camera_models):
+            return None
+        base = rows[0]
+        step = 4 * base.element_size()
+        if all(r.is_contiguous() and r.data_ptr() == base.data_ptr() + i * step and
+               r.untyped_storage().data_ptr() == base.untyped_storage().data_ptr() for i, r in enumerate(rows)):
+            return torch.as_strided(base, (len(rows), 4), (4, 1))
+        return torch.stack(rows)
+
     def _level_intrinsics(self, camera_models: List[CameraModel]) -> np.ndarray:
         """[num_scales, B, 4]: CameraModel.get_scaled_model_image_size per level, as at
         depth.py:273-276 (cached per distinct camera)."""
@@ -142,8 +159,11 @@ class ReconstructionLoss:
             noise = [torch.randn((b, 2, self.scaled_height[s], self.scaled_width[s]), device=depth_map.device)
                      for s in range(self.num_scales)]
         self._calls += 1
+        intrinsics = self._device_intrinsics(camera_models, depth_map.device)
+        if intrinsics is None:
+            intrinsics = self._level_intrinsics(camera_models)
         loss, self.last_argmin = ops.photometric_loss(
-            self._level_intrinsics(camera_models), images, depth_map, poses, noise, self.num_scales,
+            intrinsics, images, depth_map, poses, noise, self.num_scales,
             self.alpha, seed=self.seed + self._calls, motions=object_motion_maps)
         return loss
 

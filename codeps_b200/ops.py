@@ -112,7 +112,10 @@ class _PhotometricLoss(torch.autograd.Function):
         a = PhotoArgs()
         a.batch, a.height, a.width, a.num_levels = b, h, w, num_levels
         a.alpha, a.with_grad = float(alpha), int(need_grad)
-        a.intrinsics_host = intrinsics.ctypes.data
+        if isinstance(intrinsics, torch.Tensor):
+            a.intrinsics_dev = intrinsics.data_ptr()
+        else:
+            a.intrinsics_host = intrinsics.ctypes.data
         a.target, a.source0, a.source1 = target.data_ptr(), source0.data_ptr(), source1.data_ptr()
         a.depth, a.pose0, a.pose1 = depth.data_ptr(), pose0.data_ptr(), pose1.data_ptr()
         for s in range(num_levels):
@@ -167,7 +170,9 @@ def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], dep
                      ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     """Multi-scale min-reprojection loss with identity auto-mask.
 
-    intrinsics: float32 array [num_levels, B, 4] (fx, fy, cx, cy per level and sample).
+    intrinsics: float32 array [num_levels, B, 4] (fx, fy, cx, cy per level and sample), or a CUDA
+    float32 tensor [B, 4] with the full-resolution values (rescaled per level inside the kernel; no
+    host copy of the calibration is needed then).
     noise: per level [B,2,H_s,W_s] standard-normal tie-break draws, or None to use the kernel's
     counter-based generator with ``seed``.  Returns (loss, per-level argmin maps)."""
     target = _require_cuda_f32(images[0], "images[0]", (None, 3, None, None))
@@ -181,9 +186,14 @@ def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], dep
                     ("poses[0]", pose0), ("poses[1]", pose1)):
         if t.device != target.device:
             raise RuntimeError(f"{name} is on {t.device}, images[0] on {target.device}")
-    intrinsics = np.ascontiguousarray(intrinsics, dtype=np.float32)
-    if intrinsics.shape != (num_levels, b, 4):
-        raise ValueError(f"intrinsics has shape {intrinsics.shape}, expected {(num_levels, b, 4)}")
+    if isinstance(intrinsics, torch.Tensor):
+        intrinsics = _require_cuda_f32(intrinsics.detach(), "intrinsics", (b, 4))
+        if intrinsics.device != target.device:
+            raise RuntimeError(f"intrinsics is on {intrinsics.device}, images[0] on {target.device}")
+    else:
+        intrinsics = np.ascontiguousarray(intrinsics, dtype=np.float32)
+        if intrinsics.shape != (num_levels, b, 4):
+            raise ValueError(f"intrinsics has shape {intrinsics.shape}, expected {(num_levels, b, 4)}")
     if not 1 <= num_levels <= _native.MAX_LEVELS:
         raise ValueError(f"num_levels must be in [1, {_native.MAX_LEVELS}], got {num_levels}")
     if noise is not None:

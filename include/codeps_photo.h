@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CDP_ABI_VERSION 2
+#define CDP_ABI_VERSION 3
 #define CDP_MAX_LEVELS 6           /* pyramid levels per call (reference uses 5) */
 #define CDP_MAX_BATCH_PER_LAUNCH 32 /* intrinsics travel in kernel-parameter (constant) space */
 
@@ -109,6 +109,12 @@ typedef struct cdp_photo_args {
    * misc/image_warper.py:133-134).  Both or neither. */
   const float* motion0;
   const float* motion1;
+  /* Alternative to intrinsics_host (exactly one of the two is set): DEVICE [batch][4] = fx,fy,cx,cy
+   * at full resolution, e.g. the batch's "camera_model" tensor as the data loader delivers it
+   * (codeps/online_adap.py:95-100).  The kernels rescale per level themselves (same arithmetic as
+   * misc/camera_model.py:36-41), so the per-sample CameraModel.from_tensor read-back
+   * (misc/camera_model.py:27, one host synchronisation per sample) is not needed. */
+  const float* intrinsics_dev;
 } cdp_photo_args;
 
 size_t cdp_photo_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels,

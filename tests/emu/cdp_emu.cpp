@@ -63,15 +63,24 @@ EMU_API int emu_photo_fwd(const cdp_photo_args* a) {
     for (int b = 0; b < plan.B; ++b)
       for (int i = 0; i < pp.begin[plan.L]; ++i) cdp_pyramid_fwd_item(pp, b, i);
   }
-  for (int b0 = 0; b0 < plan.B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+  for (int b0 = 0; b0 < plan.B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {  // per-level intrinsics table
     const int nb = cdp_chunk_size(plan.B, b0);
+    CdpKTableParams tp;
+    cdp_fill_k_table_params(plan, a, b0, nb, &tp);
+    for (int i = 0; i < nb * plan.L; ++i) cdp_k_table_entry(tp, i / nb, i % nb);
+  }
+  {
     CdpPhotoParams kp;
-    cdp_fill_photo_params(plan, a, b0, nb, &kp);
-    for (int by = 0; by < nb; ++by)
+    cdp_fill_photo_params(plan, a, 0, plan.B, &kp);
+    for (int by = 0; by < plan.B; ++by)
       for (int bx = 0; bx < plan.blocks_per_image; ++bx) {
-        const bool m = plan.has_motion != 0;
-        if (a->with_grad) { if (m) emu_photo_block<true, true>(kp, bx, by); else emu_photo_block<true, false>(kp, bx, by); }
-        else { if (m) emu_photo_block<false, true>(kp, bx, by); else emu_photo_block<false, false>(kp, bx, by); }
+        const int which = (a->with_grad ? 2 : 0) + (plan.has_motion ? 1 : 0);
+        switch (which) {
+          case 0: emu_photo_block<false, false>(kp, bx, by); break;
+          case 1: emu_photo_block<false, true>(kp, bx, by); break;
+          case 2: emu_photo_block<true, false>(kp, bx, by); break;
+          default: emu_photo_block<true, true>(kp, bx, by); break;
+        }
       }
   }
   CdpFinalizeParams fp;

@@ -63,14 +63,20 @@ def resize_tables(h, w, levels):
 
 
 def photo(level_intrinsics, images, depth, poses, noise, num_scales, alpha=0.85, with_grad=True,
-          grad_loss=1.0, seed=0, motions=None):
-    """Run emu_photo_fwd (+ emu_photo_bwd).  level_intrinsics: [L,B,4] float32."""
+          grad_loss=1.0, seed=0, motions=None, full_res_intrinsics=None):
+    """Run emu_photo_fwd (+ emu_photo_bwd).  level_intrinsics: [L,B,4] float32, or None with
+    full_res_intrinsics [B,4] to exercise the "intrinsics from device memory" instantiation."""
     lib = load()
     b, _, h, w = depth.shape
     tgt, s0, s1 = (_f32(i) for i in images)
     depth, p0, p1 = _f32(depth), _f32(poses[0]), _f32(poses[1])
-    k = np.ascontiguousarray(level_intrinsics, dtype=np.float32)
-    assert k.shape == (num_scales, b, 4)
+    if full_res_intrinsics is not None:
+        assert level_intrinsics is None
+        k = np.ascontiguousarray(full_res_intrinsics, dtype=np.float32)
+        assert k.shape == (b, 4)
+    else:
+        k = np.ascontiguousarray(level_intrinsics, dtype=np.float32)
+        assert k.shape == (num_scales, b, 4)
     tables = resize_tables(h, w, num_scales)
     hm = int(motions is not None)
     mo = [_f32(m) for m in motions] if motions is not None else None
@@ -82,7 +88,10 @@ def photo(level_intrinsics, images, depth, poses, noise, num_scales, alpha=0.85,
     a = PhotoArgs()
     a.batch, a.height, a.width, a.num_levels = b, h, w, num_scales
     a.alpha, a.with_grad = alpha, int(with_grad)
-    a.intrinsics_host = k.ctypes.data
+    if full_res_intrinsics is not None:
+        a.intrinsics_dev = k.ctypes.data
+    else:
+        a.intrinsics_host = k.ctypes.data
     a.target, a.source0, a.source1, a.depth = tgt.data_ptr(), s0.data_ptr(), s1.data_ptr(), depth.data_ptr()
     a.pose0, a.pose1 = p0.data_ptr(), p1.data_ptr()
     for s in range(num_scales):

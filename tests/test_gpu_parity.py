@@ -340,3 +340,42 @@ def test_fused_loss_with_object_motion(cuda_device):
         assert_grad_close_masked(mo[k].grad, ref["grad_motion"][k], mask.expand(-1, 3, -1, -1), f"dL/d motion{k}",
                                  max_masked_frac=0.05)
         assert_grad_close(poses[k].grad, ref["grad_pose"][k], f"dL/dT{k}")
+
+
+@pytest.mark.gpu
+def test_lazy_camera_models_skip_the_host_read_back(cuda_device):
+    """CameraModel.from_tensor of CUDA rows (codeps/online_adap.py:95-100) stays on the device:
+    the loss gets the calibration through cdp_photo_args.intrinsics_dev, the result equals the
+    host-intrinsics path bit for bit, and no host copy of the intrinsics is ever made."""
+    import codeps_b200
+    from codeps_b200.synthetic import make_preset_batch
+    dev = cuda_device
+    tb = make_preset_batch("kitti360", 3, seed=12, flip_every_other=True).to(dev)
+    h, w = tb.height, tb.width
+    k_dev = tb.intrinsics.to(dev)                       # in_data["camera_model"]: [B,4] on the GPU
+    lazy = [codeps_b200.CameraModel.from_tensor(w, h, k_dev[i]) for i in range(3)]
+    host = tb.camera_models()
+    assert all(c.device_intrinsics is not None and c._intrinsics is None for c in lazy)
+    results = []
+    for cams in (lazy, host):
+        torch.manual_seed(21)
+        fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), 5, dev)
+        depth = tb.depth.clone().requires_grad_(True)
+        poses = [p.clone().requires_grad_(True) for p in tb.poses]
+        loss = fn(cams, tb.images, depth, poses)
+        loss.backward()
+        results.append((loss.detach(), depth.grad, poses[0].grad, poses[1].grad, fn.last_argmin))
+    assert all(c._intrinsics is None for c in lazy), "the loss must not read the intrinsics back to the host"
+    a, b = results
+    assert float(a[0]) == float(b[0])
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert all(torch.equal(x, y) for x, y in zip(a[4], b[4]))
+    # rows of one [B,4] tensor are used in place; unrelated tensors are stacked
+    fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), 5, dev)
+    assert fn._device_intrinsics(lazy, dev).data_ptr() == k_dev.data_ptr()
+    scattered = [codeps_b200.CameraModel.from_tensor(w, h, k_dev[i].clone()) for i in range(3)]
+    assert torch.equal(fn._device_intrinsics(scattered, dev), k_dev)
+    assert fn._device_intrinsics(host, dev) is None
+    # host values are still available on demand (one read-back), e.g. for the stand-alone warper
+    assert abs(float(lazy[1].intrinsics["fx"]) - float(tb.intrinsics[1, 0])) == 0.0
+    assert lazy[1].get_scaled_model_image_size(w // 2, h // 2).image_size == {"width": w // 2, "height": h // 2}
