@@ -69,7 +69,11 @@ def profiled_kernel(workload: str, kernel_substr: str):
     kernel for this workload: DRAM traffic per launch, issue-slot utilisation, L2 hit rate."""
     import glob
     best = None
-    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "*_ncu.json"))):
+    import re
+
+    def natural(path):  # r01_9_... before r01_11_...
+        return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", os.path.basename(path))]
+    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "*_ncu.json")), key=natural):
         try:
             with open(path) as f:
                 blob = json.load(f)
@@ -313,7 +317,7 @@ def main():
     with ClockSampler(local_rank) as clocks:
         elapsed_ms, last = timed(run_step, args.steps)
     value = n_gpus * batch * args.steps / (elapsed_ms * 1e-3)
-    recon_val, smooth_val = float(last[0]), float(last[1])
+    recon_val, smooth_val = float(last[0].detach()), float(last[1].detach())
 
     # ---- eager pass with per-kernel CUDA events (same K steps) -> dominant-kernel duration
     _native.profile_enable(True)
