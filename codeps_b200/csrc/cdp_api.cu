@@ -200,10 +200,12 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p) {
 }
 
 __global__ void __launch_bounds__(CDP_FINALIZE_THREADS) cdp_finalize_kernel(const CdpFinalizeParams p) {
-  __shared__ double sm[2048];
+  __shared__ double sm[2048 + 32];
   cdp_finalize_phase_a(p, blockIdx.x, threadIdx.x, sm);
   __syncthreads();
   cdp_finalize_phase_b(p, blockIdx.x, threadIdx.x, sm);
+  __syncthreads();
+  cdp_finalize_phase_c(p, blockIdx.x, threadIdx.x, sm);
 }
 
 __device__ __forceinline__ double cdp_warp_butterfly(double v) {  // same order as cdp_butterfly_host
@@ -235,25 +237,27 @@ __global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_main_kernel(con
   cdp_block_reduce_store(v, sm, p.part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4);
 }
 
-// one warp per image (fixed order), then thread 0 combines the images in index order
+// four warps per image (one per accumulated quantity, fixed order inside each), then one thread
+// per image derives its scalars and thread 0 combines the images in index order
 __global__ void __launch_bounds__(1024) cdp_smooth_finalize_kernel(const CdpSmoothParams p) {
-  __shared__ double contrib[32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  __shared__ double sums[8][4];
+  __shared__ double contrib[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = p.tiles_x * p.tiles_y;
   double loss = 0.0;
-  for (int b0 = 0; b0 < p.B; b0 += nwarps) {
-    const int b = b0 + warp;
+  for (int b0 = 0; b0 < p.B; b0 += 8) {  // 32 warps = 8 images x 4 quantities per round
+    const int b = b0 + (warp >> 2), q = warp & 3;
     if (b < p.B) {
-      const float* rec = p.part + (size_t)b * nb * 4;
-      const double s0 = cdp_warp_butterfly(cdp_lane_sum(rec + 0, nb, 4, lane));
-      const double s1 = cdp_warp_butterfly(cdp_lane_sum(rec + 1, nb, 4, lane));
-      const double s2 = cdp_warp_butterfly(cdp_lane_sum(rec + 2, nb, 4, lane));
-      const double s3 = cdp_warp_butterfly(cdp_lane_sum(rec + 3, nb, 4, lane));
-      if (lane == 0) contrib[warp] = cdp_smooth_finalize_image(p, b, s0, s1, s2, s3);
+      const double s = cdp_warp_butterfly(cdp_lane_sum(p.part + (size_t)b * nb * 4 + q, nb, 4, lane));
+      if (lane == 0) sums[warp >> 2][q] = s;
     }
     __syncthreads();
+    if (threadIdx.x < 8 && b0 + threadIdx.x < p.B)
+      contrib[threadIdx.x] = cdp_smooth_finalize_image(p, b0 + threadIdx.x, sums[threadIdx.x][0], sums[threadIdx.x][1],
+                                                       sums[threadIdx.x][2], sums[threadIdx.x][3]);
+    __syncthreads();
     if (threadIdx.x == 0)
-      for (int w = 0; w < nwarps && b0 + w < p.B; ++w) loss += contrib[w];
+      for (int w = 0; w < 8 && b0 + w < p.B; ++w) loss += contrib[w];
     __syncthreads();
   }
   if (threadIdx.x == 0) p.loss[0] = (float)loss;

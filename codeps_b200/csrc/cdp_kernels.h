@@ -108,16 +108,25 @@ CDP_HD void cdp_finalize_phase_a(const CdpFinalizeParams& p, int b, int tid, dou
     sm[1024 + tid] = lacc;
   }
 }
-// step 2: combine in index order; threads 0..31 own one pose-gradient column, thread 32 of block 0
-// the loss
-CDP_HD void cdp_finalize_phase_b(const CdpFinalizeParams& p, int b, int tid, const double* sm) {
+// step 2: combine in index order; threads 0..31 own one pose-gradient column, threads 32..63 of
+// block 0 each fold 32 consecutive loss sums (sm needs 2048 + 32 doubles)
+CDP_HD void cdp_finalize_phase_b(const CdpFinalizeParams& p, int b, int tid, double* sm) {
   if (tid < 32) {
     double acc = 0.0;
     for (int r = 0; r < 32; ++r) acc += sm[r * 32 + tid];
     if (p.pose_unit) p.pose_unit[((size_t)(tid >> 4) * p.B + b) * 16 + (tid & 15)] = (float)acc;
-  } else if (tid == 32 && b == 0) {
+  } else if (tid < 64 && b == 0) {
     double acc = 0.0;
-    for (int i = 0; i < CDP_FINALIZE_THREADS; ++i) acc += sm[1024 + i];
+    for (int i = 0; i < 32; ++i) acc += sm[1024 + (tid - 32) * 32 + i];
+    sm[2048 + tid - 32] = acc;
+  }
+}
+// step 3: thread 0 of block 0 adds the 32 group sums (a 32 + 32 deep chain of fp64 additions
+// instead of 1024: the serial version cost 8 us)
+CDP_HD void cdp_finalize_phase_c(const CdpFinalizeParams& p, int b, int tid, const double* sm) {
+  if (tid == 0 && b == 0) {
+    double acc = 0.0;
+    for (int i = 0; i < 32; ++i) acc += sm[2048 + i];
     p.loss[0] = (float)acc;
   }
 }

@@ -85,10 +85,11 @@ EMU_API int emu_photo_fwd(const cdp_photo_args* a) {
   }
   CdpFinalizeParams fp;
   cdp_fill_finalize_params(plan, a, &fp);
-  std::vector<double> sm(2048);
+  std::vector<double> sm(2048 + 32);
   for (int b = 0; b < fp.B; ++b) {
     for (int t = 0; t < CDP_FINALIZE_THREADS; ++t) cdp_finalize_phase_a(fp, b, t, sm.data());
     for (int t = 0; t < CDP_FINALIZE_THREADS; ++t) cdp_finalize_phase_b(fp, b, t, sm.data());
+    for (int t = 0; t < CDP_FINALIZE_THREADS; ++t) cdp_finalize_phase_c(fp, b, t, sm.data());
   }
   return CDP_OK;
 }
