@@ -281,7 +281,7 @@ def test_error_behaviour(cuda_device):
         codeps_b200.EdgeAwareSmoothnessLoss()(tb.images[0], tb.disp)
 
 
-@pytest.mark.parametrize("w,h,scales", [(32, 32, 5), (40, 18, 4), (34, 66, 3)])
+@pytest.mark.parametrize("w,h,scales", [(32, 32, 5), (40, 18, 4), (34, 66, 3), (64, 64, 6), (48, 40, 1)])
 def test_tiny_and_ragged_sizes(w, h, scales, cuda_device):
     """Coarsest level down to 2x2 (reflection padding of a 2-pixel axis), sizes that are not
     multiples of the tile, single-tile images."""
@@ -379,3 +379,42 @@ def test_lazy_camera_models_skip_the_host_read_back(cuda_device):
     # host values are still available on demand (one read-back), e.g. for the stand-alone warper
     assert abs(float(lazy[1].intrinsics["fx"]) - float(tb.intrinsics[1, 0])) == 0.0
     assert lazy[1].get_scaled_model_image_size(w // 2, h // 2).image_size == {"width": w // 2, "height": h // 2}
+
+
+@pytest.mark.gpu
+def test_full_size_gradient_is_the_derivative_of_the_loss(cuda_device):
+    """Oracle-independent check at BASELINE size: along smooth directions the hand-written
+    backward equals the central difference of the CUDA forward (the loss is continuous and
+    piecewise smooth; pixels that switch candidate / tap cell inside the step only add O(eps))."""
+    dev = cuda_device
+    tb = make_preset_batch("cityscapes", 4, seed=23)
+    w, h, scales = tb.width, tb.height, 5
+    noise = [n.to(dev) for n in po.draw_noise(4, w, h, scales, seed=4)]
+    images = tuple(i.to(dev) for i in tb.images)
+    loss_fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), scales, dev)
+    k_levels = loss_fn._level_intrinsics(tb.camera_models())
+
+    def loss_of(depth, poses, grad=False):
+        depth = depth.to(dev).requires_grad_(grad)
+        poses = [p.to(dev).requires_grad_(grad) for p in poses]
+        recon, _ = ops.photometric_loss(k_levels, images, depth, poses, noise, scales, 0.85)
+        if not grad:
+            return float(recon.detach().double())
+        recon.backward()
+        return float(recon.detach().double()), depth.grad.double().cpu(), [p.grad.double().cpu() for p in poses]
+
+    base, g_depth, g_pose = loss_of(tb.depth, tb.poses, grad=True)
+    # (1) all depths scaled by (1 + eps):  dL/d eps = sum(dL/d depth * depth)
+    eps = 2e-3
+    fd = (loss_of(tb.depth * (1 + eps), tb.poses) - loss_of(tb.depth * (1 - eps), tb.poses)) / (2 * eps)
+    an = float((g_depth * tb.depth.double()).sum())
+    assert abs(fd - an) <= 0.03 * abs(an) + 1e-7, (fd, an, base)
+    # (2) forward translation of the t+1 pose by eps (metres):  dL/d eps = sum_b dL/dT1[b][2,3]
+    eps = 2e-4
+    def moved(sign):
+        p1 = tb.poses[1].clone()
+        p1[:, 2, 3] += sign * eps
+        return [tb.poses[0], p1]
+    fd = (loss_of(tb.depth, moved(+1)) - loss_of(tb.depth, moved(-1))) / (2 * eps)
+    an = float(g_pose[1][:, 2, 3].sum())
+    assert abs(fd - an) <= 0.03 * abs(an) + 1e-6, (fd, an, base)

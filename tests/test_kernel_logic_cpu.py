@@ -111,7 +111,7 @@ def test_emulated_object_motion_warp():
     assert_grad_close(gm, mo.grad, "motion warp dL/d motion")
 
 
-@pytest.mark.parametrize("w,h,scales", [(32, 32, 5), (40, 18, 4), (34, 66, 3)])
+@pytest.mark.parametrize("w,h,scales", [(32, 32, 5), (40, 18, 4), (34, 66, 3), (64, 64, 6), (48, 40, 1)])
 def test_emulated_tiny_and_ragged_sizes(w, h, scales):
     """Coarsest level down to 2x2 (reflection padding of a 2-pixel axis), sizes that are not
     multiples of the tile, single-tile images."""
