@@ -225,6 +225,13 @@ __global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_consta
     for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
 }
 
+__global__ void __launch_bounds__(256) cdp_depth_grad_quad_kernel(const __grid_constant__ CdpDepthGradParams p) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x < p.W) cdp_depth_grad_quad_exact(p, blockIdx.z, blockIdx.y, x);
+  if (p.scale_pose && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
+}
+
 __global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_main_kernel(const CdpSmoothParams p) {
   __shared__ float sm[CDP_SMOOTH_SMEM_FLOATS];
   float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -447,6 +454,19 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   return CDP_OK;
 }
 
+// adjoint of the pyramid: four pixels per thread where the layout allows it, else one
+static void cdp_launch_depth_grad(const CdpDepthGradParams& p, cudaStream_t stream) {
+  if (cdp_depth_grad_quad_ok(p)) {
+    const int threads = p.W / 4 >= 256 ? 256 : (p.W / 4 >= 128 ? 128 : 64);
+    dim3 grid((p.W / 4 + threads - 1) / threads, p.H, p.B);
+    cdp_depth_grad_quad_kernel<<<grid, threads, 0, stream>>>(p);
+    return;
+  }
+  dim3 grid((p.W + 255) / 256, p.H, p.B);
+  if (cdp_depth_grad_all_exact(p)) cdp_depth_grad_kernel<true><<<grid, 256, 0, stream>>>(p);
+  else cdp_depth_grad_kernel<false><<<grid, 256, 0, stream>>>(p);
+}
+
 extern "C" int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32_t num_levels, const void* saved_,
                              size_t saved_bytes, const void* resize_tables, const float* grad_loss,
                              float* grad_depth, float* grad_pose0, float* grad_pose1, int32_t with_motion,
@@ -460,11 +480,9 @@ extern "C" int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32
   if (saved_bytes < plan.saved_floats * sizeof(float)) return cdp_fail(CDP_ERR_WORKSPACE, "saved too small");
   CdpDepthGradParams p;
   cdp_fill_depth_grad_params(plan, saved_, resize_tables, grad_loss, grad_depth, grad_pose0, grad_pose1, &p);
-  dim3 grid((plan.W + 255) / 256, plan.H, plan.B);
   {
     ProfScope prof_(CDP_KERNEL_DEPTH_GRAD, stream);
-    if (cdp_depth_grad_all_exact(p)) cdp_depth_grad_kernel<true><<<grid, 256, 0, stream>>>(p);
-    else cdp_depth_grad_kernel<false><<<grid, 256, 0, stream>>>(p);
+    cdp_launch_depth_grad(p, stream);
   }
   CDP_LAUNCH_CHECK("cdp_depth_grad_kernel");
   if (with_motion) {
@@ -472,10 +490,8 @@ extern "C" int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32
     for (int k = 0; k < 2; ++k) {
       CdpDepthGradParams pm;
       cdp_fill_motion_grad_params(plan, saved_, resize_tables, grad_loss, k, outs[k], &pm);
-      dim3 gm((plan.W + 255) / 256, plan.H, 3 * plan.B);
       ProfScope prof_(CDP_KERNEL_DEPTH_GRAD, stream);
-      if (cdp_depth_grad_all_exact(pm)) cdp_depth_grad_kernel<true><<<gm, 256, 0, stream>>>(pm);
-      else cdp_depth_grad_kernel<false><<<gm, 256, 0, stream>>>(pm);
+      cdp_launch_depth_grad(pm, stream);
       CDP_LAUNCH_CHECK("cdp_depth_grad_kernel (motion)");
     }
   }

@@ -215,6 +215,48 @@ CDP_HD void cdp_depth_grad_px_exact(const CdpDepthGradParams& p, int b, int y, i
   p.grad_depth[(size_t)b * W * p.H + pix] = CDP_LDG(p.grad_loss) * acc;
 }
 
+// Four consecutive pixels x..x+3 (x % 4 == 0) of row y in one thread, for exact power-of-two
+// pyramids with W % 4 == 0 and 16-byte aligned rows: one 16-byte load of G_0, one 8-byte load of
+// G_1 (every position is a middle position of its 2x2 block), at most one scalar load per coarser
+// level (the middle columns of a 2^s block are positions 2^(s-1)-1 and 2^(s-1): pixels 1,2 of the
+// quad for s = 2, pixel 3 or pixel 0 of one quad each for s >= 3).  Same per-pixel accumulation
+// order as cdp_depth_grad_px_exact, so results are bit-identical.
+CDP_HD void cdp_depth_grad_quad_exact(const CdpDepthGradParams& p, int b, int y, int x) {
+  const int W = p.W;
+  const size_t o0 = (size_t)b * W * p.H + (size_t)y * W + x;
+  float4 a = CDP_LDG(reinterpret_cast<const float4*>(p.gdepth[0] + o0));
+  if (p.L > 1) {
+    const float2 g = CDP_LDG(reinterpret_cast<const float2*>(p.gdepth[1] + (size_t)b * p.Ws[1] * p.Hs[1] +
+                                                             (size_t)(y >> 1) * p.Ws[1] + (x >> 1)));
+    a.x += 0.25f * g.x; a.y += 0.25f * g.x; a.z += 0.25f * g.y; a.w += 0.25f * g.y;
+  }
+#pragma unroll
+  for (int s = 2; s < CDP_MAX_LEVELS; ++s) {
+    if (s >= p.L) break;
+    const int r = 1 << s, half = r >> 1;
+    if ((unsigned)((y & (r - 1)) - (half - 1)) >= 2u) continue;  // not a middle row (uniform per block)
+    const int m = x & (r - 1);  // position of the quad's first pixel inside its block
+    if (s > 2 && m != half - 4 && m != half) continue;
+    const float g = 0.25f * CDP_LDG(p.gdepth[s] + (size_t)b * p.Ws[s] * p.Hs[s] + (size_t)(y >> s) * p.Ws[s] + (x >> s));
+    if (s == 2) { a.y += g; a.z += g; }
+    else if (m == half) a.x += g;
+    else a.w += g;
+  }
+  const float go = CDP_LDG(p.grad_loss);
+  a.x *= go; a.y *= go; a.z *= go; a.w *= go;
+  *reinterpret_cast<float4*>(p.grad_depth + o0) = a;
+}
+
+// the quad form applies: exact pyramid, rows of every used level keep the vector loads aligned
+CDP_HD bool cdp_depth_grad_quad_ok(const CdpDepthGradParams& p) {
+  if ((p.W & 3) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p.gdepth[0]) & 15) != 0 || (reinterpret_cast<uintptr_t>(p.grad_depth) & 15) != 0) return false;
+  if (p.L > 1 && (reinterpret_cast<uintptr_t>(p.gdepth[1]) & 7) != 0) return false;
+  for (int s = 1; s < p.L; ++s)
+    if (!p.exact_x[s] || !p.exact_y[s]) return false;
+  return true;
+}
+
 CDP_HD bool cdp_depth_grad_all_exact(const CdpDepthGradParams& p) {
   for (int s = 1; s < p.L; ++s)
     if (!p.exact_x[s] || !p.exact_y[s]) return false;
@@ -222,9 +264,14 @@ CDP_HD bool cdp_depth_grad_all_exact(const CdpDepthGradParams& p) {
 }
 
 CDP_HD void cdp_depth_grad_pixel(const CdpDepthGradParams& p, int b, int pix) {
-  const int y = pix / p.W;
-  if (cdp_depth_grad_all_exact(p)) cdp_depth_grad_px_exact(p, b, y, pix - y * p.W);
-  else cdp_depth_grad_px(p, b, y, pix - y * p.W);
+  const int y = pix / p.W, x = pix - y * p.W;
+  if (cdp_depth_grad_quad_ok(p)) {
+    if ((x & 3) == 0) cdp_depth_grad_quad_exact(p, b, y, x);
+  } else if (cdp_depth_grad_all_exact(p)) {
+    cdp_depth_grad_px_exact(p, b, y, x);
+  } else {
+    cdp_depth_grad_px(p, b, y, x);
+  }
 }
 
 CDP_HD void cdp_pose_grad_scale(const CdpDepthGradParams& p, int i) {  // i in [0, 2*B*16)
