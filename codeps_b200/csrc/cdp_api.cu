@@ -244,6 +244,13 @@ __global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_main_kernel(con
   cdp_block_reduce_store(v, sm, p.part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4);
 }
 
+__global__ void __launch_bounds__(CDP_SMOOTH_Q_THREADS) cdp_smooth_quad_kernel(const CdpSmoothParams p) {
+  __shared__ float red[(CDP_SMOOTH_Q_THREADS / 32) * 4];
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  cdp_smooth_quad_thread(p, blockIdx.z, blockIdx.x, blockIdx.y, threadIdx.x, v);
+  cdp_block_reduce_store(v, red, p.part + (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 4);
+}
+
 // four warps per image (one per accumulated quantity, fixed order inside each), then one thread
 // per image derives its scalars and thread 0 combines the images in index order
 __global__ void __launch_bounds__(1024) cdp_smooth_finalize_kernel(const CdpSmoothParams p) {
@@ -516,8 +523,15 @@ extern "C" int cdp_smooth_fwd(const float* image, const float* disp, int32_t bat
   float* saved = static_cast<float*>(saved_);
   CdpSmoothParams p;
   cdp_fill_smooth_params(image, disp, batch, height, width, with_grad, loss, saved, &p);
-  dim3 grid(p.tiles_x * p.tiles_y, batch);
-  { ProfScope prof_(CDP_KERNEL_SMOOTH_MAIN, stream); cdp_smooth_main_kernel<<<grid, CDP_SMOOTH_THREADS, 0, stream>>>(p); }
+  if (cdp_smooth_quad_ok(p)) {
+    dim3 grid(p.tiles_x, p.tiles_y, batch);
+    ProfScope prof_(CDP_KERNEL_SMOOTH_MAIN, stream);
+    cdp_smooth_quad_kernel<<<grid, CDP_SMOOTH_Q_THREADS, 0, stream>>>(p);
+  } else {
+    dim3 grid(p.tiles_x * p.tiles_y, batch);
+    ProfScope prof_(CDP_KERNEL_SMOOTH_MAIN, stream);
+    cdp_smooth_main_kernel<<<grid, CDP_SMOOTH_THREADS, 0, stream>>>(p);
+  }
   CDP_LAUNCH_CHECK("cdp_smooth_main_kernel");
   { ProfScope prof_(CDP_KERNEL_SMOOTH_FINALIZE, stream); cdp_smooth_finalize_kernel<<<1, 1024, 0, stream>>>(p); }
   CDP_LAUNCH_CHECK("cdp_smooth_finalize_kernel");

@@ -395,6 +395,128 @@ CDP_HD void cdp_smooth_phase_grad(const CdpSmoothParams& p, int b, int tile, int
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Row-walk form of the same pass for W % 4 == 0 and 16-byte aligned planes: a thread owns four
+// consecutive pixels and walks CDP_SMOOTH_Q_ROWS rows down, the previous row and the pending
+// gradient terms stay in registers, the two neighbours of the quad come from two scalar loads
+// (L1 hits: they are the neighbouring threads' quads).  No shared memory, ~5x fewer instructions
+// than the staged tile form above, which remains the general path.
+// ------------------------------------------------------------------------------------------
+#ifndef CDP_SMOOTH_Q_THREADS
+#define CDP_SMOOTH_Q_THREADS 128
+#endif
+#ifndef CDP_SMOOTH_Q_ROWS
+#define CDP_SMOOTH_Q_ROWS 16
+#endif
+
+struct CdpSmoothRow {  // positions x-1 .. x+4 of one row: image channels and disparity
+  float c[4][6];
+};
+
+CDP_HD void cdp_smooth_load_row(const CdpSmoothParams& p, int b, int y, int x, CdpSmoothRow& r) {
+  const size_t plane = (size_t)p.H * p.W;
+  const size_t o = (size_t)y * p.W + x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float* src = k < 3 ? p.image + ((size_t)b * 3 + k) * plane : p.disp + (size_t)b * plane;
+    const float4 v = CDP_LDG(reinterpret_cast<const float4*>(src + o));
+    r.c[k][1] = v.x; r.c[k][2] = v.y; r.c[k][3] = v.z; r.c[k][4] = v.w;
+    r.c[k][0] = x > 0 ? CDP_LDG(src + o - 1) : 0.f;
+    r.c[k][5] = x + 4 < p.W ? CDP_LDG(src + o + 4) : 0.f;
+  }
+}
+
+// signed edge weight sign(d(p) - d(q)) exp(-mean_c |I(p) - I(q)|) and the edge's loss term
+CDP_HD float cdp_smooth_edge(float r0, float g0, float b0, float d0, float r1, float g1, float b1, float d1,
+                             float& loss_term) {
+  const float s = fabsf(r0 - r1) + fabsf(g0 - g1) + fabsf(b0 - b1);
+  const float e = cdp_exp(-(s * (1.0f / 3.0f)));
+  const float diff = d0 - d1;
+  loss_term = fabsf(diff) * e;
+  return cdp_sign(diff) * e;
+}
+
+// thread `tid` of block (bx, by) of image b; acc = {sum disp, sum x-edge loss, sum y-edge loss, sum g*disp}
+CDP_HD void cdp_smooth_quad_thread(const CdpSmoothParams& p, int b, int bx, int by, int tid, float acc[4]) {
+  const int x = (bx * CDP_SMOOTH_Q_THREADS + tid) * 4;
+  if (x >= p.W) return;
+  const int y0 = by * CDP_SMOOTH_Q_ROWS, y1 = y0 + CDP_SMOOTH_Q_ROWS < p.H ? y0 + CDP_SMOOTH_Q_ROWS : p.H;
+  const float cx = 1.0f / ((float)p.B * (float)p.H * (float)(p.W - 1));
+  const float cy = 1.0f / ((float)p.B * (float)(p.H - 1) * (float)p.W);
+  float prev[4][4];       // row t-1, the quad's own pixels
+  float xpart[4], hy1[4], hy2[4];  // row t-1: cx (hx(x) - hx(x-1)); hy of rows t-1 and t-2
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { xpart[i] = 0.f; hy1[i] = 0.f; hy2[i] = 0.f; prev[0][i] = prev[1][i] = prev[2][i] = prev[3][i] = 0.f; }
+  const int t0 = y0 > 0 ? y0 - 1 : 0;
+  CdpSmoothRow cur, nxt;
+  cdp_smooth_load_row(p, b, t0, x, nxt);
+  for (int t = t0; t <= y1; ++t) {  // row t is in registers; row t-1 is completed
+    cur = nxt;
+    if (t + 1 <= y1 && t + 1 < p.H) cdp_smooth_load_row(p, b, t + 1, x, nxt);  // requested one row ahead
+    float xp[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool have = t < p.H;
+    if (have) {
+      if (t >= y0 && t < y1) {  // x edges of an owned row: positions (x-1|x) .. (x+3|x+4)
+        float hx[5], lt;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const bool edge = x + i - 1 >= 0 && x + i < p.W;
+          hx[i] = 0.f;
+          if (edge) {
+            hx[i] = cdp_smooth_edge(cur.c[0][i], cur.c[1][i], cur.c[2][i], cur.c[3][i], cur.c[0][i + 1], cur.c[1][i + 1],
+                                    cur.c[2][i + 1], cur.c[3][i + 1], lt);
+            if (i >= 1) acc[1] += lt;  // the edge (x-1|x) is owned by the quad to the left
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xp[i] = cx * (hx[i + 1] - hx[i]);
+      }
+    }
+    // y edges (t-1 | t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hy2[i] = hy1[i];
+    if (have && t > t0) {
+      float lt;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        hy1[i] = cdp_smooth_edge(prev[0][i], prev[1][i], prev[2][i], prev[3][i], cur.c[0][i + 1], cur.c[1][i + 1],
+                                 cur.c[2][i + 1], cur.c[3][i + 1], lt);
+        if (t - 1 >= y0) acc[2] += lt;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hy1[i] = 0.f;  // no row below the last image row / nothing above the first loaded row
+    }
+    // complete row t-1
+    if (t - 1 >= y0 && t - 1 < y1 && t > t0) {
+      float4 g;
+      float gv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        gv[i] = xpart[i] + cy * (hy1[i] - hy2[i]);
+        acc[0] += prev[3][i];
+        acc[3] += gv[i] * prev[3][i];
+      }
+      if (p.with_grad) {
+        g.x = gv[0]; g.y = gv[1]; g.z = gv[2]; g.w = gv[3];
+        *reinterpret_cast<float4*>(p.g + (size_t)b * p.H * p.W + (size_t)(t - 1) * p.W + x) = g;
+      }
+    }
+    if (have) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xpart[i] = xp[i];
+        prev[0][i] = cur.c[0][i + 1]; prev[1][i] = cur.c[1][i + 1]; prev[2][i] = cur.c[2][i + 1]; prev[3][i] = cur.c[3][i + 1];
+      }
+    }
+  }
+}
+
+CDP_HD bool cdp_smooth_quad_ok(const CdpSmoothParams& p) {
+  return (p.W & 3) == 0 && (reinterpret_cast<uintptr_t>(p.image) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.disp) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(p.g) & 15) == 0;
+}
+
 // Fixed-order combination of per-block records that one warp can evaluate in parallel: lane l sums
 // records l, l+32, ...; lanes are combined by a butterfly (cdp_butterfly_host = same order).
 CDP_HD double cdp_lane_sum(const float* part, int count, int stride, int lane) {

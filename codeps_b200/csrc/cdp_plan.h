@@ -143,9 +143,13 @@ static inline CdpSmoothLayout cdp_smooth_layout(int32_t B, int32_t H, int32_t W)
   CdpSmoothLayout l;
   l.tiles_x = (W + CDP_SMOOTH_TX - 1) / CDP_SMOOTH_TX;
   l.tiles_y = (H + CDP_SMOOTH_TY - 1) / CDP_SMOOTH_TY;
+  // the row-walk kernel (W % 4 == 0) has its own block grid; the record area fits either
+  const size_t qx = ((size_t)(W + 3) / 4 + CDP_SMOOTH_Q_THREADS - 1) / CDP_SMOOTH_Q_THREADS;
+  const size_t qy = ((size_t)H + CDP_SMOOTH_Q_ROWS - 1) / CDP_SMOOTH_Q_ROWS;
+  const size_t tiles = (size_t)l.tiles_x * l.tiles_y > qx * qy ? (size_t)l.tiles_x * l.tiles_y : qx * qy;
   size_t o = 0;
   l.g = o; o += cdp_align_floats((size_t)B * H * W);
-  l.part = o; o += cdp_align_floats((size_t)B * l.tiles_x * l.tiles_y * 4);
+  l.part = o; o += cdp_align_floats((size_t)B * tiles * 4);
   l.scal = o; o += cdp_align_floats((size_t)B * 2);
   l.total = o;
   return l;
@@ -158,6 +162,10 @@ static inline void cdp_fill_smooth_params(const float* image, const float* disp,
   p->scal = saved + l.scal; p->loss = loss;
   p->B = B; p->H = H; p->W = W; p->with_grad = with_grad;
   p->tiles_x = l.tiles_x; p->tiles_y = l.tiles_y;
+  if (cdp_smooth_quad_ok(*p)) {  // block grid of the row-walk kernel
+    p->tiles_x = (W / 4 + CDP_SMOOTH_Q_THREADS - 1) / CDP_SMOOTH_Q_THREADS;
+    p->tiles_y = (H + CDP_SMOOTH_Q_ROWS - 1) / CDP_SMOOTH_Q_ROWS;
+  }
 }
 
 static inline void cdp_fill_warp_params(CdpWarpParams* p, const float* src, int C, const float* depth,

@@ -125,6 +125,21 @@ EMU_API int emu_smooth_fwd(const float* image, const float* disp, int32_t B, int
   CdpSmoothParams p;
   cdp_fill_smooth_params(image, disp, B, H, W, with_grad, loss, static_cast<float*>(saved), &p);
   const int nt = CDP_SMOOTH_THREADS, nb = p.tiles_x * p.tiles_y;
+  if (cdp_smooth_quad_ok(p)) {  // row-walk kernel
+    for (int b = 0; b < B; ++b)
+      for (int by = 0; by < p.tiles_y; ++by)
+        for (int bx = 0; bx < p.tiles_x; ++bx) {
+          float tot[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int t = 0; t < CDP_SMOOTH_Q_THREADS; ++t) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            cdp_smooth_quad_thread(p, b, bx, by, t, v);
+            for (int j = 0; j < 4; ++j) tot[j] += v[j];
+          }
+          for (int j = 0; j < 4; ++j) p.part[(((size_t)b * p.tiles_y + by) * p.tiles_x + bx) * 4 + j] = tot[j];
+        }
+    cdp_smooth_finalize(p);
+    return CDP_OK;
+  }
   std::vector<float> sm(CDP_SMOOTH_SMEM_FLOATS);
   for (int b = 0; b < B; ++b)
     for (int tile = 0; tile < nb; ++tile) {
