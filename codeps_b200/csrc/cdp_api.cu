@@ -395,6 +395,8 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   CDP_REQUIRE(cdp_make_plan(a->batch, a->height, a->width, a->num_levels, &plan, a->motion0 != nullptr),
               "invalid shape: batch %d, %dx%d, %d levels (every level needs >= 2x2 pixels, at most %d levels)",
               a->batch, a->width, a->height, a->num_levels, CDP_MAX_LEVELS);
+  CDP_REQUIRE((reinterpret_cast<uintptr_t>(a->pose0) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->pose1) & 15) == 0,
+              "pose0 / pose1 must be 16-byte aligned");
   CDP_REQUIRE(a->batch <= 65535, "batch %d exceeds the grid limit of one launch", a->batch);
   CDP_REQUIRE((a->intrinsics_host != nullptr) != (a->intrinsics_dev != nullptr),
               "exactly one of intrinsics_host / intrinsics_dev must be set");

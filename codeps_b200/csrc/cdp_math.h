@@ -85,6 +85,15 @@ CDP_HD void cdp_load_pose(const float* T, CdpPose& o) {
   for (int i = 0; i < 16; ++i) o.d[i] = CDP_LDG(T + i);
   o.d[0] -= 1.0f; o.d[5] -= 1.0f; o.d[10] -= 1.0f;
 }
+// same for a 16-byte aligned matrix: four 16-byte loads instead of sixteen scalar ones
+CDP_HD void cdp_load_pose_aligned(const float* T, CdpPose& o) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float4 v = CDP_LDG(reinterpret_cast<const float4*>(T) + r);
+    o.d[4 * r + 0] = v.x; o.d[4 * r + 1] = v.y; o.d[4 * r + 2] = v.z; o.d[4 * r + 3] = v.w;
+  }
+  o.d[0] -= 1.0f; o.d[5] -= 1.0f; o.d[10] -= 1.0f;
+}
 
 // ------------------------------------------------------------------------------------------
 // Warp of one pixel: CameraModel.get_viewing_ray + _ImageToPointcloud (misc/camera_model.py:52-71,

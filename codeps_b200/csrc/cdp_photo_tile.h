@@ -120,8 +120,8 @@ CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int 
   const size_t plane = (size_t)W * H;
   const CdpCam cam = cdp_tile_cam(p, c);
   CdpPose T[2];
-  cdp_load_pose(p.pose0 + (size_t)c.b * 16, T[0]);
-  cdp_load_pose(p.pose1 + (size_t)c.b * 16, T[1]);
+  cdp_load_pose_aligned(p.pose0 + (size_t)c.b * 16, T[0]);  // cdp_photo_fwd requires 16-byte aligned poses
+  cdp_load_pose_aligned(p.pose1 + (size_t)c.b * 16, T[1]);
   float centre[3];
   cdp_tile_centre(lv, c, centre);
   const float* src0 = lv.src0 + (size_t)c.b * 3 * plane;
@@ -540,7 +540,7 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
 #endif
         // (the source loop is rolled to keep the code small: no register arrays indexed by k)
         CdpPose T;
-        cdp_load_pose((k == 0 ? p.pose0 : p.pose1) + (size_t)c.b * 16, T);
+        cdp_load_pose_aligned((k == 0 ? p.pose0 : p.pose1) + (size_t)c.b * 16, T);
         const float* srck = (k == 0 ? lv.src0 : lv.src1) + (size_t)c.b * 3 * plane;
         float mo[3], gmo[3];
         const float* motk = k == 0 ? lv.mot0 : lv.mot1;

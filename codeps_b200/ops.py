@@ -182,6 +182,10 @@ def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], dep
     depth = _require_cuda_f32(depth, "depth_map", (b, 1, h, w))
     pose0 = _require_cuda_f32(poses[0], "poses[0]", (b, 4, 4))
     pose1 = _require_cuda_f32(poses[1], "poses[1]", (b, 4, 4))
+    if pose0.data_ptr() % 16:  # the kernels read the matrices with 16-byte loads
+        pose0 = pose0.clone()
+    if pose1.data_ptr() % 16:
+        pose1 = pose1.clone()
     for name, t in (("images[1]", source0), ("images[2]", source1), ("depth_map", depth),
                     ("poses[0]", pose0), ("poses[1]", pose1)):
         if t.device != target.device:

@@ -90,8 +90,8 @@ typedef struct cdp_photo_args {
   const float* source0; /* [B,3,H,W] frame t-1 */
   const float* source1; /* [B,3,H,W] frame t+1 */
   const float* depth;   /* [B,1,H,W] */
-  const float* pose0;   /* [B,4,4] t -> t-1 */
-  const float* pose1;   /* [B,4,4] t -> t+1 */
+  const float* pose0;   /* [B,4,4] t -> t-1, 16-byte aligned */
+  const float* pose1;   /* [B,4,4] t -> t+1, 16-byte aligned */
   /* Tie-break noise (algos/depth.py:316-318).  noise[s] = [B,2,H_s,W_s] standard normal draws
    * (the library multiplies by 1e-5), or all NULL to use the built-in counter-based generator
    * seeded with noise_seed. */
