@@ -11,7 +11,12 @@ but it is importable in the build container.  ``oracle/make_golden.py`` runs the
 itself* (imported from /root/reference) on seeded inputs and commits its outputs under
 ``tests/golden/``; ``tests/test_oracle_golden.py`` requires this oracle to reproduce them
 (bit-for-bit on the argmin, to float rounding on values).  So: parity pinned against
-outputs of the reference run in the build container.
+outputs of the reference run in the build container.  The restatements of the neighbouring
+rows are pinned the same way: ``transformation_from_parameters`` /
+``disp_to_depth`` by ``heads.npz`` (tests/test_heads.py), ``flow_smoothness_loss`` /
+``flow_sparsity_loss`` by ``flow.npz`` (tests/test_flow_losses.py), ``warp_c2c`` by ``c2c.npz``
+(tests/test_warp_c2c.py), ``depth_metrics[_per_class]`` by ``metrics.npz``
+(tests/test_depth_metrics.py) -- each generated from the reference's own class.
 
 The arithmetic all lives in PyTorch ATen ops (reference pins torch==1.12.1,
 /root/reference/requirements.txt:1; validated here with torch 2.11): ``upsample_bilinear2d``
