@@ -306,7 +306,11 @@ def _check_flow_maps(flow_maps) -> List[torch.Tensor]:
     if not 1 <= len(maps) <= _native.MAX_FLOW_MAPS:
         raise ValueError(f"between 1 and {_native.MAX_FLOW_MAPS} flow maps are supported, got {len(maps)}")
     first = _require_cuda_f32(maps[0], "flow_maps[0]", (None, None, None, None))
-    return [first] + [_require_cuda_f32(m, f"flow_maps[{i}]", tuple(first.shape)) for i, m in enumerate(maps[1:], 1)]
+    out = [first] + [_require_cuda_f32(m, f"flow_maps[{i}]", tuple(first.shape)) for i, m in enumerate(maps[1:], 1)]
+    for i, m in enumerate(out):
+        if m.device != first.device:
+            raise RuntimeError(f"flow_maps[{i}] is on {m.device}, flow_maps[0] on {first.device}")
+    return out
 
 
 def flow_smoothness_loss(flow_maps, wrap_around: bool = True) -> torch.Tensor:
