@@ -162,7 +162,13 @@ __device__ __forceinline__ void cdp_block_reduce_store_wide(const float (&v)[N],
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cdp_pyramid_fwd_kernel(const __grid_constant__ CdpPyrParams p) {
+// kt.batch_count > 0: the first block also writes the per-level intrinsics table (saves the
+// separate cdp_k_table_kernel launch when the whole batch fits one parameter block)
+__global__ void __launch_bounds__(256) cdp_pyramid_fwd_kernel(const __grid_constant__ CdpPyrParams p,
+                                                              const __grid_constant__ CdpKTableParams kt) {
+  if (blockIdx.x == 0 && blockIdx.y == 0)
+    for (int i = threadIdx.x; i < kt.batch_count * kt.L; i += blockDim.x)
+      cdp_k_table_entry(kt, i / kt.batch_count, i % kt.batch_count);
   cdp_pyramid_fwd_item(p, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
@@ -382,8 +388,9 @@ extern "C" size_t cdp_photo_saved_bytes(int32_t batch, int32_t height, int32_t w
 static int cdp_batch_chunks(int32_t batch) { return (batch + CDP_MAX_BATCH_PER_LAUNCH - 1) / CDP_MAX_BATCH_PER_LAUNCH; }
 
 extern "C" int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels) {
-  // pyramid, intrinsics table (per 32 samples), tile kernel, reduction
-  return (num_levels > 1 ? 1 : 0) + cdp_batch_chunks(batch) + 1 + 1;
+  // pyramid (+ intrinsics table), or intrinsics table kernels per 32 samples; tile kernel; reduction
+  const bool table_in_pyramid = num_levels > 1 && batch <= CDP_MAX_BATCH_PER_LAUNCH;
+  return (num_levels > 1 ? 1 : 0) + (table_in_pyramid ? 0 : cdp_batch_chunks(batch)) + 1 + 1;
 }
 extern "C" int cdp_photo_bwd_launches(int32_t, int32_t, int32_t with_motion) { return with_motion ? 3 : 1; }
 
@@ -416,12 +423,17 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   for (int s = 0; s < plan.L; ++s) { any_noise |= a->noise[s] != nullptr; all_noise &= a->noise[s] != nullptr; }
   CDP_REQUIRE(!any_noise || all_noise, "noise must be given for every level or for none");
 
+  // the per-level intrinsics table rides along with the pyramid launch when there is one and the
+  // whole batch fits its parameter block; otherwise cdp_k_table_kernel writes it (step 2)
+  const bool table_in_pyramid = plan.L > 1 && plan.B <= CDP_MAX_BATCH_PER_LAUNCH;
   // 1. pyramid
   if (plan.L > 1) {
     CdpPyrParams pp;
     cdp_fill_pyr_params(plan, a, &pp);
     dim3 grid((pp.begin[plan.L] + 255) / 256, plan.B);
-    { ProfScope prof_(CDP_KERNEL_PYRAMID, stream); cdp_pyramid_fwd_kernel<<<grid, 256, 0, stream>>>(pp); }
+    CdpKTableParams tp;
+    cdp_fill_k_table_params(plan, a, 0, table_in_pyramid ? plan.B : 0, &tp);
+    { ProfScope prof_(CDP_KERNEL_PYRAMID, stream); cdp_pyramid_fwd_kernel<<<grid, 256, 0, stream>>>(pp, tp); }
     CDP_LAUNCH_CHECK("cdp_pyramid_fwd_kernel");
   }
 
@@ -437,7 +449,7 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   CDP_CUDA(cdp_allow_smem(photo_kernel, smem, &smem_done[which]));
   // per-level intrinsics table: host values travel by value (<= 32 samples per launch), device
   // values are rescaled per level
-  for (int b0 = 0; b0 < plan.B; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
+  for (int b0 = 0; b0 < plan.B && !table_in_pyramid; b0 += CDP_MAX_BATCH_PER_LAUNCH) {
     const int nb = cdp_chunk_size(plan.B, b0);
     CdpKTableParams tp;
     cdp_fill_k_table_params(plan, a, b0, nb, &tp);
