@@ -253,7 +253,10 @@ __global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_main_kernel(con
   cdp_block_reduce_store(v, sm, p.part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4);
 }
 
-__global__ void __launch_bounds__(CDP_SMOOTH_Q_THREADS) cdp_smooth_quad_kernel(const CdpSmoothParams p) {
+#ifndef CDP_SMOOTH_Q_MIN_BLOCKS
+#define CDP_SMOOTH_Q_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(CDP_SMOOTH_Q_THREADS, CDP_SMOOTH_Q_MIN_BLOCKS) cdp_smooth_quad_kernel(const CdpSmoothParams p) {
   __shared__ float red[(CDP_SMOOTH_Q_THREADS / 32) * 4];
   float v[4] = {0.f, 0.f, 0.f, 0.f};
   cdp_smooth_quad_thread(p, blockIdx.z, blockIdx.x, blockIdx.y, threadIdx.x, v);
