@@ -418,3 +418,53 @@ def test_full_size_gradient_is_the_derivative_of_the_loss(cuda_device):
     fd = (loss_of(tb.depth, moved(+1)) - loss_of(tb.depth, moved(-1))) / (2 * eps)
     an = float(g_pose[1][:, 2, 3].sum())
     assert abs(fd - an) <= 0.03 * abs(an) + 1e-6, (fd, an, base)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_capture_and_replay(cuda_device):
+    """The whole step (both losses, forward + backward, tie-break randn included) can be captured
+    into a CUDA graph from the public classes and replayed on new data in place -- how bench.py
+    times it; the replay must equal an eager evaluation of the same inputs bit for bit."""
+    dev = cuda_device
+    a = make_preset_batch("semkitti", 2, seed=31).to(dev)
+    b = make_preset_batch("semkitti", 2, seed=32).to(dev)
+    w, h = a.width, a.height
+    recon_fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), 5, dev, noise="fused", seed=3)
+    smooth_fn = codeps_b200.EdgeAwareSmoothnessLoss()
+    cams = a.camera_models()
+    static = dict(images=[i.clone() for i in a.images], depth=a.depth.clone(), disp=a.disp.clone(),
+                  poses=[p.clone() for p in a.poses])
+
+    def step():
+        depth, disp = static["depth"].detach().requires_grad_(True), static["disp"].detach().requires_grad_(True)
+        poses = [p.detach().requires_grad_(True) for p in static["poses"]]
+        recon_fn._calls = 0  # same fused-noise seed on every call
+        recon = recon_fn(cams, static["images"], depth, poses)
+        smooth = smooth_fn(static["images"][0], disp)
+        grads = torch.autograd.grad([recon, smooth], [depth, disp] + poses)
+        return (recon, smooth) + tuple(grads)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = step()
+    for batch in (b, a):
+        for dst, src in zip(static["images"], batch.images):
+            dst.copy_(src)
+        static["depth"].copy_(batch.depth)
+        static["disp"].copy_(batch.disp)
+        for dst, src in zip(static["poses"], batch.poses):
+            dst.copy_(src)
+        graph.replay()
+        torch.cuda.synchronize()
+        replayed = [o.clone() for o in outs]
+        eager = step()
+        torch.cuda.synchronize()
+        for r, e in zip(replayed, eager):
+            assert torch.equal(r, e)
