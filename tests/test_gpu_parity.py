@@ -468,3 +468,30 @@ def test_cuda_graph_capture_and_replay(cuda_device):
         torch.cuda.synchronize()
         for r, e in zip(replayed, eager):
             assert torch.equal(r, e)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["behind_camera", "general_last_row"])
+def test_degenerate_and_general_poses(case, cuda_device):
+    """Points behind the camera after the transform (z clamp, zero gradient through it) and a
+    general 4x4 matrix with a projective last row: the literal-formula branch of the warp."""
+    g = Golden("city_near")
+    inp = g.inputs()
+    poses = [p.clone() for p in inp["poses"]]
+    if case == "behind_camera":
+        poses[0][:, 2, 3] -= 1.4 * float(inp["depth"].median())
+        poses[1][0, 2, 3] -= 0.9 * float(inp["depth"].median())
+    else:
+        poses[0][:, 3, :] = torch.tensor([0.02, -0.03, 0.05, 1.1])
+        poses[1][:, 3, :] = torch.tensor([-0.01, 0.015, -0.04, 0.93])
+    inp = dict(inp, poses=poses)
+    out = run_cuda(inp, g.width, g.height, g.num_scales, cuda_device, inp["noise"])
+    free = po.loss_and_grads(inp["intrinsics"], inp["images"], inp["depth"], inp["disp"], poses, inp["noise"],
+                             g.num_scales, dtype=torch.float64)
+    assert_loss_close(out["recon"], free["recon"], f"recon {case}")
+    for s in range(g.num_scales):
+        top2 = torch.sort(free["candidates"][s], dim=1).values[:, :2]
+        decided = (top2[:, 1] - top2[:, 0]) > 1e-6
+        assert not ((out["argmin"][s] != free["argmin"][s]) & decided).any(), f"level {s}"
+    print(check_photo_grads(out, inp, g.num_scales, case, max_masked_frac=0.5, pose_rtol=1e-3))
+    assert torch.isfinite(out["grad_depth"]).all() and all(torch.isfinite(p).all() for p in out["grad_pose"])

@@ -179,3 +179,35 @@ def test_emulated_device_intrinsics_path_is_identical(w, h, scales):
         assert torch.equal(host["argmin"][s], dev["argmin"][s])
     assert torch.equal(host["grad_depth"], dev["grad_depth"])
     assert torch.equal(host["grad_pose"][0], dev["grad_pose"][0]) and torch.equal(host["grad_pose"][1], dev["grad_pose"][1])
+
+
+@pytest.mark.parametrize("case", ["behind_camera", "general_last_row"])
+def test_emulated_degenerate_and_general_poses(case):
+    """The literal-formula branch of the warp (cdp_warp_point, `regular == false`):
+    points that land behind the camera after the transform (z clamped to 1e-5, zero gradient
+    through the clamp, misc/image_warper.py:32) and a general 4x4 matrix whose last row is not
+    (0,0,0,1) (homogeneous divide by Q_w, misc/image_warper.py:137-138), as a badly initialised
+    pose network produces them."""
+    from helpers import check_photo_grads
+    g = Golden("city_near")
+    inp = g.inputs()
+    poses = [p.clone() for p in inp["poses"]]
+    if case == "behind_camera":
+        poses[0][:, 2, 3] -= 1.4 * float(inp["depth"].median())   # t_z pushes the nearer half behind the camera
+        poses[1][0, 2, 3] -= 0.9 * float(inp["depth"].median())
+    else:
+        poses[0][:, 3, :] = torch.tensor([0.02, -0.03, 0.05, 1.1])
+        poses[1][:, 3, :] = torch.tensor([-0.01, 0.015, -0.04, 0.93])
+    inp = dict(inp, poses=poses)
+    out = emu.photo(level_tables(g), inp["images"], inp["depth"], poses, inp["noise"], g.num_scales)
+    free = po.loss_and_grads(inp["intrinsics"], inp["images"], inp["depth"], inp["disp"], poses, inp["noise"],
+                             g.num_scales, dtype=torch.float64)
+    if case == "behind_camera":  # the case must actually exercise the clamp
+        pts = inp["depth"].double() * 1.0 + poses[0][:, 2, 3].double().view(-1, 1, 1, 1)
+        assert (pts < 1e-5).float().mean() > 0.2
+    assert_loss_close(out["recon"], free["recon"], f"recon {case}")
+    for s in range(g.num_scales):
+        top2 = torch.sort(free["candidates"][s], dim=1).values[:, :2]
+        decided = (top2[:, 1] - top2[:, 0]) > 1e-6
+        assert not ((out["argmin"][s] != free["argmin"][s]) & decided).any(), f"level {s}"
+    print(check_photo_grads(out, inp, g.num_scales, case, max_masked_frac=0.5, pose_rtol=1e-3))
