@@ -495,3 +495,29 @@ def test_degenerate_and_general_poses(case, cuda_device):
         assert not ((out["argmin"][s] != free["argmin"][s]) & decided).any(), f"level {s}"
     print(check_photo_grads(out, inp, g.num_scales, case, max_masked_frac=0.5, pose_rtol=1e-3))
     assert torch.isfinite(out["grad_depth"]).all() and all(torch.isfinite(p).all() for p in out["grad_pose"])
+
+
+@pytest.mark.gpu
+def test_batch_64_equals_mean_of_its_chunks(cuda_device):
+    """BASELINE config 5 shape (SemKITTI 1280x384) with the whole global batch of 64 on one GPU:
+    the loss is the mean of the eight 8-sample chunk losses and every gradient is the chunk
+    gradient / 8 (samples are independent; also exercises > 32 samples in one tile launch and
+    index arithmetic beyond 2^27 elements)."""
+    dev = cuda_device
+    tb = make_preset_batch("semkitti", 8, seed=41, flip_every_other=True)
+    rep = lambda t: t.repeat(8, *([1] * (t.dim() - 1)))
+    w, h, scales = tb.width, tb.height, 5
+    big = dict(images=tuple(rep(i) for i in tb.images), depth=rep(tb.depth), disp=rep(tb.disp),
+               poses=tuple(rep(p) for p in tb.poses), intrinsics=np.tile(tb.intrinsics.numpy(), (8, 1)))
+    small = dict(images=tb.images, depth=tb.depth, disp=tb.disp, poses=tb.poses, intrinsics=tb.intrinsics.numpy())
+    noise8 = po.draw_noise(8, w, h, scales, seed=13)
+    out64 = run_cuda(big, w, h, scales, dev, [rep(n) for n in noise8])
+    out8 = run_cuda(small, w, h, scales, dev, noise8)
+    assert abs(float(out64["recon"]) - float(out8["recon"])) <= 2e-6 * abs(float(out8["recon"]))
+    assert abs(float(out64["smooth"]) - float(out8["smooth"])) <= 2e-6 * abs(float(out8["smooth"]))
+    for c in (0, 3, 7):
+        sl = slice(8 * c, 8 * c + 8)
+        assert torch.equal(out64["argmin"][0][sl], out8["argmin"][0])
+        assert rel_err(out64["grad_depth"][sl] * 8, out8["grad_depth"]) < 1e-6
+        assert rel_err(out64["grad_disp"][sl] * 8, out8["grad_disp"]) < 1e-5
+        assert rel_err(out64["grad_pose"][0][sl] * 8, out8["grad_pose"][0]) < 1e-5
