@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_consta
 
 __global__ void __launch_bounds__(256) cdp_depth_grad_quad_kernel(const __grid_constant__ CdpDepthGradParams p) {
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (x < p.W) cdp_depth_grad_quad_exact(p, blockIdx.z, blockIdx.y, x);
+  if (x < p.W) cdp_depth_grad_quad(p, blockIdx.z, blockIdx.y, x);
   if (p.scale_pose && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
 }

@@ -162,6 +162,34 @@ CDP_HD void cdp_inv_taps(bool exact, const CdpResizeInv* table, int i, int s, in
   }
 }
 
+// contribution of level s to full-resolution pixel (x, y): (resize_s^T G_s)(x, y), table or exact taps per axis
+CDP_HD float cdp_depth_grad_level(const CdpDepthGradParams& p, int b, int y, int x, int s) {
+  int xa, xb, ya, yb;
+  float wxa, wxb, wya, wyb;
+  cdp_inv_taps(p.exact_y[s] != 0, p.inv_y[s], y, s, ya, yb, wya, wyb);
+  if (ya < 0 && yb < 0) return 0.f;
+  cdp_inv_taps(p.exact_x[s] != 0, p.inv_x[s], x, s, xa, xb, wxa, wxb);
+  if (xa < 0 && xb < 0) return 0.f;
+  const int ws = p.Ws[s];
+  const float* g = p.gdepth[s] + (size_t)b * ws * p.Hs[s];
+  float t = 0.f;
+  if (ya >= 0) {
+    const float* r = g + ya * ws;
+    float u = 0.f;
+    if (xa >= 0) u = wxa * CDP_LDG(r + xa);
+    if (xb >= 0) u += wxb * CDP_LDG(r + xb);
+    t = wya * u;
+  }
+  if (yb >= 0) {
+    const float* r = g + yb * ws;
+    float u = 0.f;
+    if (xa >= 0) u = wxa * CDP_LDG(r + xa);
+    if (xb >= 0) u += wxb * CDP_LDG(r + xb);
+    t += wyb * u;
+  }
+  return t;
+}
+
 // dL/d depth at full-resolution pixel (x, y) = grad_loss * (G_0 + sum_s resize_s^T G_s)
 CDP_HD void cdp_depth_grad_px(const CdpDepthGradParams& p, int b, int y, int x) {
   const int W = p.W, pix = y * W + x;
@@ -169,30 +197,7 @@ CDP_HD void cdp_depth_grad_px(const CdpDepthGradParams& p, int b, int y, int x) 
 #pragma unroll
   for (int s = 1; s < CDP_MAX_LEVELS; ++s) {
     if (s >= p.L) break;
-    int xa, xb, ya, yb;
-    float wxa, wxb, wya, wyb;
-    cdp_inv_taps(p.exact_y[s] != 0, p.inv_y[s], y, s, ya, yb, wya, wyb);
-    if (ya < 0 && yb < 0) continue;
-    cdp_inv_taps(p.exact_x[s] != 0, p.inv_x[s], x, s, xa, xb, wxa, wxb);
-    if (xa < 0 && xb < 0) continue;
-    const int ws = p.Ws[s];
-    const float* g = p.gdepth[s] + (size_t)b * ws * p.Hs[s];
-    float t = 0.f;
-    if (ya >= 0) {
-      const float* r = g + ya * ws;
-      float u = 0.f;
-      if (xa >= 0) u = wxa * CDP_LDG(r + xa);
-      if (xb >= 0) u += wxb * CDP_LDG(r + xb);
-      t = wya * u;
-    }
-    if (yb >= 0) {
-      const float* r = g + yb * ws;
-      float u = 0.f;
-      if (xa >= 0) u = wxa * CDP_LDG(r + xa);
-      if (xb >= 0) u += wxb * CDP_LDG(r + xb);
-      t += wyb * u;
-    }
-    acc += t;
+    acc += cdp_depth_grad_level(p, b, y, x, s);
   }
   p.grad_depth[(size_t)b * W * p.H + pix] = CDP_LDG(p.grad_loss) * acc;
 }
@@ -215,24 +220,34 @@ CDP_HD void cdp_depth_grad_px_exact(const CdpDepthGradParams& p, int b, int y, i
   p.grad_depth[(size_t)b * W * p.H + pix] = CDP_LDG(p.grad_loss) * acc;
 }
 
-// Four consecutive pixels x..x+3 (x % 4 == 0) of row y in one thread, for exact power-of-two
-// pyramids with W % 4 == 0 and 16-byte aligned rows: one 16-byte load of G_0, one 8-byte load of
-// G_1 (every position is a middle position of its 2x2 block), at most one scalar load per coarser
-// level (the middle columns of a 2^s block are positions 2^(s-1)-1 and 2^(s-1): pixels 1,2 of the
-// quad for s = 2, pixel 3 or pixel 0 of one quad each for s >= 3).  Same per-pixel accumulation
-// order as cdp_depth_grad_px_exact, so results are bit-identical.
-CDP_HD void cdp_depth_grad_quad_exact(const CdpDepthGradParams& p, int b, int y, int x) {
+// Four consecutive pixels x..x+3 (x % 4 == 0) of row y in one thread, for W % 4 == 0 and 16-byte
+// aligned rows: one 16-byte load of G_0 and one 16-byte store.  Levels that halve both axes
+// exactly s times take the short path -- one 8-byte load of G_1 (every position is a middle
+// position of its 2x2 block), at most one scalar load per coarser level (the middle columns of a
+// 2^s block are positions 2^(s-1)-1 and 2^(s-1): pixels 1,2 of the quad for s = 2, pixel 3 or
+// pixel 0 of one quad each for s >= 3); other levels (e.g. 376 -> 23 rows at level 4 of KITTI-360)
+// go through the transposed tap tables per pixel.  Same per-pixel accumulation order and values
+// as cdp_depth_grad_px, so results are bit-identical.
+CDP_HD void cdp_depth_grad_quad(const CdpDepthGradParams& p, int b, int y, int x) {
   const int W = p.W;
   const size_t o0 = (size_t)b * W * p.H + (size_t)y * W + x;
   float4 a = CDP_LDG(reinterpret_cast<const float4*>(p.gdepth[0] + o0));
-  if (p.L > 1) {
-    const float2 g = CDP_LDG(reinterpret_cast<const float2*>(p.gdepth[1] + (size_t)b * p.Ws[1] * p.Hs[1] +
-                                                             (size_t)(y >> 1) * p.Ws[1] + (x >> 1)));
-    a.x += 0.25f * g.x; a.y += 0.25f * g.x; a.z += 0.25f * g.y; a.w += 0.25f * g.y;
-  }
 #pragma unroll
-  for (int s = 2; s < CDP_MAX_LEVELS; ++s) {
+  for (int s = 1; s < CDP_MAX_LEVELS; ++s) {
     if (s >= p.L) break;
+    if (!(p.exact_x[s] && p.exact_y[s])) {
+      a.x += cdp_depth_grad_level(p, b, y, x, s);
+      a.y += cdp_depth_grad_level(p, b, y, x + 1, s);
+      a.z += cdp_depth_grad_level(p, b, y, x + 2, s);
+      a.w += cdp_depth_grad_level(p, b, y, x + 3, s);
+      continue;
+    }
+    if (s == 1) {
+      const float2 g = CDP_LDG(reinterpret_cast<const float2*>(p.gdepth[1] + (size_t)b * p.Ws[1] * p.Hs[1] +
+                                                               (size_t)(y >> 1) * p.Ws[1] + (x >> 1)));
+      a.x += 0.25f * g.x; a.y += 0.25f * g.x; a.z += 0.25f * g.y; a.w += 0.25f * g.y;
+      continue;
+    }
     const int r = 1 << s, half = r >> 1;
     if ((unsigned)((y & (r - 1)) - (half - 1)) >= 2u) continue;  // not a middle row (uniform per block)
     const int m = x & (r - 1);  // position of the quad's first pixel inside its block
@@ -247,13 +262,11 @@ CDP_HD void cdp_depth_grad_quad_exact(const CdpDepthGradParams& p, int b, int y,
   *reinterpret_cast<float4*>(p.grad_depth + o0) = a;
 }
 
-// the quad form applies: exact pyramid, rows of every used level keep the vector loads aligned
+// the quad form applies: rows of level 0 (and of an exact level 1) keep the vector accesses aligned
 CDP_HD bool cdp_depth_grad_quad_ok(const CdpDepthGradParams& p) {
   if ((p.W & 3) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p.gdepth[0]) & 15) != 0 || (reinterpret_cast<uintptr_t>(p.grad_depth) & 15) != 0) return false;
-  if (p.L > 1 && (reinterpret_cast<uintptr_t>(p.gdepth[1]) & 7) != 0) return false;
-  for (int s = 1; s < p.L; ++s)
-    if (!p.exact_x[s] || !p.exact_y[s]) return false;
+  if (p.L > 1 && p.exact_x[1] && p.exact_y[1] && (reinterpret_cast<uintptr_t>(p.gdepth[1]) & 7) != 0) return false;
   return true;
 }
 
@@ -266,7 +279,7 @@ CDP_HD bool cdp_depth_grad_all_exact(const CdpDepthGradParams& p) {
 CDP_HD void cdp_depth_grad_pixel(const CdpDepthGradParams& p, int b, int pix) {
   const int y = pix / p.W, x = pix - y * p.W;
   if (cdp_depth_grad_quad_ok(p)) {
-    if ((x & 3) == 0) cdp_depth_grad_quad_exact(p, b, y, x);
+    if ((x & 3) == 0) cdp_depth_grad_quad(p, b, y, x);
   } else if (cdp_depth_grad_all_exact(p)) {
     cdp_depth_grad_px_exact(p, b, y, x);
   } else {
