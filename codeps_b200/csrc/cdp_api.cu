@@ -234,9 +234,10 @@ __global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_consta
     for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
 }
 
+template <bool ALL_EXACT>
 __global__ void __launch_bounds__(256) cdp_depth_grad_quad_kernel(const __grid_constant__ CdpDepthGradParams p) {
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (x < p.W) cdp_depth_grad_quad(p, blockIdx.z, blockIdx.y, x);
+  if (x < p.W) cdp_depth_grad_quad<ALL_EXACT>(p, blockIdx.z, blockIdx.y, x);
   if (p.scale_pose && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
     for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
 }
@@ -486,7 +487,8 @@ static void cdp_launch_depth_grad(const CdpDepthGradParams& p, cudaStream_t stre
   if (cdp_depth_grad_quad_ok(p)) {
     const int threads = p.W / 4 >= 256 ? 256 : (p.W / 4 >= 128 ? 128 : 64);
     dim3 grid((p.W / 4 + threads - 1) / threads, p.H, p.B);
-    cdp_depth_grad_quad_kernel<<<grid, threads, 0, stream>>>(p);
+    if (cdp_depth_grad_all_exact(p)) cdp_depth_grad_quad_kernel<true><<<grid, threads, 0, stream>>>(p);
+    else cdp_depth_grad_quad_kernel<false><<<grid, threads, 0, stream>>>(p);
     return;
   }
   dim3 grid((p.W + 255) / 256, p.H, p.B);

@@ -228,6 +228,8 @@ CDP_HD void cdp_depth_grad_px_exact(const CdpDepthGradParams& p, int b, int y, i
 // pixel 0 of one quad each for s >= 3); other levels (e.g. 376 -> 23 rows at level 4 of KITTI-360)
 // go through the transposed tap tables per pixel.  Same per-pixel accumulation order and values
 // as cdp_depth_grad_px, so results are bit-identical.
+// ALL_EXACT: every level is exact on both axes (no table path compiled in)
+template <bool ALL_EXACT>
 CDP_HD void cdp_depth_grad_quad(const CdpDepthGradParams& p, int b, int y, int x) {
   const int W = p.W;
   const size_t o0 = (size_t)b * W * p.H + (size_t)y * W + x;
@@ -235,7 +237,7 @@ CDP_HD void cdp_depth_grad_quad(const CdpDepthGradParams& p, int b, int y, int x
 #pragma unroll
   for (int s = 1; s < CDP_MAX_LEVELS; ++s) {
     if (s >= p.L) break;
-    if (!(p.exact_x[s] && p.exact_y[s])) {
+    if (!ALL_EXACT && !(p.exact_x[s] && p.exact_y[s])) {
       a.x += cdp_depth_grad_level(p, b, y, x, s);
       a.y += cdp_depth_grad_level(p, b, y, x + 1, s);
       a.z += cdp_depth_grad_level(p, b, y, x + 2, s);
@@ -279,7 +281,9 @@ CDP_HD bool cdp_depth_grad_all_exact(const CdpDepthGradParams& p) {
 CDP_HD void cdp_depth_grad_pixel(const CdpDepthGradParams& p, int b, int pix) {
   const int y = pix / p.W, x = pix - y * p.W;
   if (cdp_depth_grad_quad_ok(p)) {
-    if ((x & 3) == 0) cdp_depth_grad_quad(p, b, y, x);
+    if ((x & 3) != 0) return;
+    if (cdp_depth_grad_all_exact(p)) cdp_depth_grad_quad<true>(p, b, y, x);
+    else cdp_depth_grad_quad<false>(p, b, y, x);
   } else if (cdp_depth_grad_all_exact(p)) {
     cdp_depth_grad_px_exact(p, b, y, x);
   } else {
