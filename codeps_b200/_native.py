@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_size_t, c_uint8, c_uin
 MAX_LEVELS = 6
 MAX_BATCH_PER_LAUNCH = 32
 MAX_FLOW_MAPS = 4    # CDP_MAX_FLOW_MAPS
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _fp = POINTER(c_float)
 
@@ -35,6 +35,7 @@ class PhotoArgs(ctypes.Structure):
         ("saved", c_void_p), ("saved_bytes", c_size_t),
         ("motion0", c_void_p), ("motion1", c_void_p),
         ("intrinsics_dev", c_void_p),
+        ("noise_ready", c_void_p),
     ]
 
 

@@ -463,6 +463,7 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
     cdp_k_table_kernel<<<(nb * plan.L + 127) / 128, 128, 0, stream>>>(tp);
     CDP_LAUNCH_CHECK("cdp_k_table_kernel");
   }
+  if (a->noise_ready) CDP_CUDA(cudaStreamWaitEvent(stream, static_cast<cudaEvent_t>(a->noise_ready), 0));
   {
     CdpPhotoParams kp;
     cdp_fill_photo_params(plan, a, 0, plan.B, &kp);

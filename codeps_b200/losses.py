@@ -154,18 +154,43 @@ class ReconstructionLoss:
             raise ValueError(f"images are {w}x{h} but this loss was built for "
                              f"{self.scaled_width[0]}x{self.scaled_height[0]}")
         b = images[0].shape[0]
-        noise = None
-        if self.noise == "torch":
+        noise, noise_event = None, None
+        if self.noise == "torch" and not depth_map.is_cuda:
             noise = [torch.randn((b, 2, self.scaled_height[s], self.scaled_width[s]), device=depth_map.device)
-                     for s in range(self.num_scales)]
+                     for s in range(self.num_scales)]  # rejected below with the "CUDA only" error
+        elif self.noise == "torch":
+            # drawn on a side stream so that the five randn kernels overlap the pyramid kernel (both
+            # are independent and memory-bound); same generator, same call order, same values
+            device = depth_map.device
+            current = torch.cuda.current_stream(device)
+            side = self._side_stream(device)
+            side.wait_stream(current)
+            with torch.cuda.stream(side):
+                noise = [torch.randn((b, 2, self.scaled_height[s], self.scaled_width[s]), device=device)
+                         for s in range(self.num_scales)]
+                noise_event = torch.cuda.Event()
+                noise_event.record(side)
+            for n in noise:
+                n.record_stream(current)
         self._calls += 1
         intrinsics = self._device_intrinsics(camera_models, depth_map.device)
         if intrinsics is None:
             intrinsics = self._level_intrinsics(camera_models)
         loss, self.last_argmin = ops.photometric_loss(
             intrinsics, images, depth_map, poses, noise, self.num_scales,
-            self.alpha, seed=self.seed + self._calls, motions=object_motion_maps)
+            self.alpha, seed=self.seed + self._calls, motions=object_motion_maps, noise_event=noise_event)
         return loss
+
+    _side_streams = {}
+
+    @classmethod
+    def _side_stream(cls, device) -> "torch.cuda.Stream":
+        """One auxiliary stream per device for the tie-break noise (shared by all loss objects)."""
+        key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        stream = cls._side_streams.get(key)
+        if stream is None:
+            stream = cls._side_streams[key] = torch.cuda.Stream(device=key)
+        return stream
 
     def auto_mask(self, level: int = 0) -> Tensor:
         """Boolean [B,H_s,W_s]: True where the last call auto-masked the pixel (identity won)."""

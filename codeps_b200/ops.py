@@ -97,7 +97,7 @@ class _PhotometricLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, depth, pose0, pose1, motion0, motion1, target, source0, source1, intrinsics, noise, seed,
-                num_levels, alpha, state):
+                num_levels, alpha, state, noise_event=None):
         b, _, h, w = target.shape
         device = target.device
         lib = _lib_for(device)
@@ -122,6 +122,8 @@ class _PhotometricLoss(torch.autograd.Function):
             a.noise[s] = noise[s].data_ptr() if noise is not None else None
             a.argmin[s] = argmin[s].data_ptr()
         a.noise_seed = int(seed)
+        if noise_event is not None:  # the noise was produced on another stream
+            a.noise_ready = noise_event.cuda_event
         a.resize_tables = tables.data_ptr()
         a.loss = loss.data_ptr()
         a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
@@ -160,13 +162,14 @@ class _PhotometricLoss(torch.autograd.Function):
                                     _ptr(go), _ptr(grad_depth), _ptr(grad_pose0), _ptr(grad_pose1),
                                     int(ctx.has_motion), _ptr(gm0), _ptr(gm1), _stream(device)), "cdp_photo_bwd")
         _LAUNCHES["count"] += lib.cdp_photo_bwd_launches(b, num_levels, int(ctx.has_motion))
-        return (grad_depth, grad_pose0, grad_pose1, gm0, gm1) + (None,) * 9
+        return (grad_depth, grad_pose0, grad_pose1, gm0, gm1) + (None,) * 10
 
 
 def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], depth: torch.Tensor,
                      poses: Sequence[torch.Tensor], noise: Optional[Sequence[torch.Tensor]],
                      num_levels: int, alpha: float = 0.85, seed: int = 0,
-                     motions: Optional[Sequence[torch.Tensor]] = None
+                     motions: Optional[Sequence[torch.Tensor]] = None,
+                     noise_event: Optional[torch.cuda.Event] = None
                      ) -> Tuple[torch.Tensor, List[torch.Tensor]]:
     """Multi-scale min-reprojection loss with identity auto-mask.
 
@@ -174,7 +177,10 @@ def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], dep
     float32 tensor [B, 4] with the full-resolution values (rescaled per level inside the kernel; no
     host copy of the calibration is needed then).
     noise: per level [B,2,H_s,W_s] standard-normal tie-break draws, or None to use the kernel's
-    counter-based generator with ``seed``.  Returns (loss, per-level argmin maps)."""
+    counter-based generator with ``seed``.  ``noise_event``: event recorded after the noise was
+    written on another stream; the library makes the current stream wait on it right before the
+    tile kernel, so the noise generation overlaps the pyramid kernel.
+    Returns (loss, per-level argmin maps)."""
     target = _require_cuda_f32(images[0], "images[0]", (None, 3, None, None))
     b, _, h, w = target.shape
     source0 = _require_cuda_f32(images[1], "images[1]", (b, 3, h, w))
@@ -213,7 +219,7 @@ def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], dep
         motion1 = _require_cuda_f32(motions[1], "object_motion_maps[1]", (b, 3, h, w))
     state = PhotoState()
     loss = _PhotometricLoss.apply(depth, pose0, pose1, motion0, motion1, target, source0, source1, intrinsics,
-                                  noise, seed, num_levels, alpha, state)
+                                  noise, seed, num_levels, alpha, state, noise_event)
     return loss, state.argmin
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CDP_ABI_VERSION 3
+#define CDP_ABI_VERSION 4
 #define CDP_MAX_LEVELS 6           /* pyramid levels per call (reference uses 5) */
 #define CDP_MAX_BATCH_PER_LAUNCH 32 /* intrinsics travel in kernel-parameter (constant) space */
 
@@ -115,6 +115,10 @@ typedef struct cdp_photo_args {
    * misc/camera_model.py:36-41), so the per-sample CameraModel.from_tensor read-back
    * (misc/camera_model.py:27, one host synchronisation per sample) is not needed. */
   const float* intrinsics_dev;
+  /* Optional cudaEvent_t (as void*): if set, `stream` waits on it before the first kernel that
+   * reads the noise tensors.  Lets the caller produce the noise on another stream while the pyramid
+   * kernel runs (both are memory-bound and independent). */
+  void* noise_ready;
 } cdp_photo_args;
 
 size_t cdp_photo_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels,

@@ -421,6 +421,63 @@ def test_full_size_gradient_is_the_derivative_of_the_loss(cuda_device):
 
 
 @pytest.mark.gpu
+def test_side_stream_noise_equals_single_stream(cuda_device):
+    """ReconstructionLoss draws its torch.randn tie-break noise on an auxiliary stream and hands the
+    library an event to wait on (cdp_photo_args.noise_ready).  Same generator, same call order:
+    the result equals the plain single-stream evaluation with the same seed bit for bit, also
+    when the call is made from inside a user stream context and when it is captured into a graph."""
+    dev = cuda_device
+    tb = make_preset_batch("cityscapes", 2, seed=44).to(dev)
+    w, h, scales = tb.width, tb.height, 5
+    fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), scales, dev)
+    cams = tb.camera_models()
+    k_levels = fn._level_intrinsics(cams)
+
+    def reference(seed):
+        torch.manual_seed(seed)
+        noise = [torch.randn(2, 2, h >> s, w >> s, device=dev) for s in range(scales)]
+        depth = tb.depth.clone().requires_grad_(True)
+        loss, argmin = ops.photometric_loss(k_levels, tb.images, depth, tb.poses, noise, scales)
+        loss.backward()
+        return loss.detach(), depth.grad, argmin
+
+    def through_class(seed, stream=None):
+        torch.manual_seed(seed)
+        depth = tb.depth.clone().requires_grad_(True)
+        with torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext():
+            loss = fn(cams, tb.images, depth, tb.poses)
+            loss.backward()
+        torch.cuda.synchronize()
+        return loss.detach(), depth.grad, fn.last_argmin
+
+    import contextlib
+    want = reference(7)
+    for stream in (None, torch.cuda.Stream()):
+        torch.cuda.synchronize()
+        got = through_class(7, stream)
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        assert all(torch.equal(a, b) for a, b in zip(got[2], want[2]))
+    # captured: the forked noise stream joins before the tile kernel; replays draw fresh noise
+    static_depth = tb.depth.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fn(cams, tb.images, static_depth.detach().requires_grad_(True), tb.poses).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        d = static_depth.detach().requires_grad_(True)
+        out = fn(cams, tb.images, d, tb.poses)
+        (g,) = torch.autograd.grad(out, d)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert abs(float(out) - float(want[0])) <= 1e-5 * abs(float(want[0]))  # other noise draws, same loss to 1e-5
+    assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+
+@pytest.mark.gpu
 def test_cuda_graph_capture_and_replay(cuda_device):
     """The whole step (both losses, forward + backward, tie-break randn included) can be captured
     into a CUDA graph from the public classes and replayed on new data in place -- how bench.py
