@@ -114,14 +114,24 @@ def load() -> ctypes.CDLL:
         if _lib is not None:
             return _lib
         path = library_path()
-        if not os.path.exists(path):
+        if not os.environ.get("CODEPS_B200_LIB"):
+            # (re)build when the library is missing or older than its sources, so that a kernel fix
+            # that does not bump CDP_ABI_VERSION is never shadowed by a stale git-ignored .so
             from . import build
+            missing = not os.path.exists(path)
             try:
-                build.build_native()
+                if missing or build.is_stale():
+                    build.build_native()
             except Exception as exc:  # no nvcc, compile error ...
-                raise RuntimeError(
-                    f"codeps_b200: {path} is missing and could not be built ({exc}). The package "
-                    "has no CPU or PyTorch fallback; run `python -m codeps_b200.build`.") from exc
+                if missing:
+                    raise RuntimeError(
+                        f"codeps_b200: {path} is missing and could not be built ({exc}). The package "
+                        "has no CPU or PyTorch fallback; run `python -m codeps_b200.build`.") from exc
+                import warnings
+                warnings.warn(f"codeps_b200: {path} is older than its sources and could not be rebuilt ({exc}); "
+                              "loading the stale library")
+        elif not os.path.exists(path):
+            raise RuntimeError(f"codeps_b200: CODEPS_B200_LIB={path} does not exist")
         lib = ctypes.CDLL(path)
         for name, (restype, argtypes) in SIGNATURES.items():
             try:

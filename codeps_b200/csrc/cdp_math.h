@@ -28,15 +28,21 @@ CDP_HD float cdp_rcp(float x) {
   return 1.0f / x;
 #endif
 }
+#ifndef CDP_OPT_FAST_DIV
+#define CDP_OPT_FAST_DIV 1  // __fdividef (~2 ulp) in the SSIM ratio; 0 = IEEE division (A/B record: profiles/r02_parity.json)
+#endif
+#ifndef CDP_OPT_FAST_EXP
+#define CDP_OPT_FAST_EXP 1  // __expf in the smoothness edge weights; 0 = expf
+#endif
 CDP_HD float cdp_fdiv(float a, float b) {  // a / b to ~2 ulp
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && CDP_OPT_FAST_DIV
   return __fdividef(a, b);
 #else
   return a / b;
 #endif
 }
 CDP_HD float cdp_exp(float x) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && CDP_OPT_FAST_EXP
   return __expf(x);
 #else
   return expf(x);

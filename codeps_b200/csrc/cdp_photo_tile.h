@@ -49,6 +49,12 @@ struct CdpTileGeom {
   static constexpr int P_COEF = 9;
   static constexpr int NPLANES = G ? (CDP_OPT_PACKED_GATHER ? 19 : 18) : 15;
   static constexpr size_t SMEM_BYTES = (size_t)NPLANES * RN * sizeof(float) + ((RN + 15) & ~15);
+  // The B1/B2 strip walk always reads CDP_STRIP + 2 region rows, also for the last, partial strip:
+  // the rows past RH belong to the following plane (values discarded) and, for the last plane, to
+  // the winner-byte tail, which must therefore be large enough for any CDP_TILE_Y / CDP_STRIP.
+  static constexpr int OVER_ROWS = NSTRIP * CDP_STRIP + 2 > RH ? NSTRIP * CDP_STRIP + 2 - RH : 0;
+  static_assert((size_t)OVER_ROWS * RW * sizeof(float2) <= ((RN + 15) & ~15) + (size_t)(NPLANES - 15) * RN * sizeof(float),
+                "strip over-read leaves the shared-memory allocation: pick CDP_TILE_Y / CDP_STRIP so that it fits");
 };
 
 struct CdpTileCtx {

@@ -24,7 +24,11 @@ static inline void cdp_fill_pyr_params(const CdpPlan& plan, const cdp_photo_args
   }
   for (int s = 0; s < plan.L; ++s) { pp->Ws[s] = plan.Ws[s]; pp->Hs[s] = plan.Hs[s]; }
   pp->W = plan.W; pp->H = plan.H; pp->L = plan.L;
-  pp->fast1 = (plan.L > 1 && plan.W % 4 == 0 && plan.H % 2 == 0) ? 1 : 0;
+  // level 1 with two 16-byte loads per channel and output pair: needs every bound input 16-byte
+  // aligned (a contiguous fp32 view with an odd storage offset is not), else the table path runs
+  bool aligned = true;
+  for (int t = 0; t < pp->nt; ++t) aligned = aligned && (reinterpret_cast<uintptr_t>(pp->in[t]) & 15) == 0;
+  pp->fast1 = (plan.L > 1 && plan.W % 4 == 0 && plan.H % 2 == 0 && aligned) ? 1 : 0;
   int off = 0;
   pp->begin[0] = pp->begin[1] = 0;
   for (int s = 1; s < plan.L; ++s) {

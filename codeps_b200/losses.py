@@ -105,6 +105,8 @@ class ReconstructionLoss:
             self.scaled_height[i] = ref_img_height // 2**i
             self.image_warpers[i] = ImageWarper(self.scaled_width[i], self.scaled_height[i], device)
         self.last_argmin: List[Tensor] = []
+        self.keep_noise = False  # debugging / tests: keep the tie-break draws of the last call in last_noise
+        self.last_noise: Optional[List[Tensor]] = None
         self._k_cache = {}
 
     def _device_intrinsics(self, camera_models: List[CameraModel], device) -> Optional[Tensor]:
@@ -173,6 +175,7 @@ class ReconstructionLoss:
             for n in noise:
                 n.record_stream(current)
         self._calls += 1
+        self.last_noise = noise if self.keep_noise else None
         intrinsics = self._device_intrinsics(camera_models, depth_map.device)
         if intrinsics is None:
             intrinsics = self._level_intrinsics(camera_models)

@@ -426,7 +426,9 @@ class _WarpImage(torch.autograd.Function):
         src, depth, pose, motion = ctx.saved_tensors
         motion = motion if ctx.has_motion else None
         if ctx.mode != 0:
-            raise RuntimeError("ImageWarper: nearest-neighbour warping has no coordinate gradient")
+            # F.grid_sample(mode="nearest") has a zero coordinate gradient (ATen returns zeros)
+            return (None, torch.zeros_like(depth), torch.zeros_like(pose),
+                    torch.zeros_like(motion) if motion is not None else None, None, None)
         b, c, h, w = src.shape
         device = src.device
         lib = _lib_for(device)

@@ -77,7 +77,25 @@ def assert_argmin_matches(got, golden: Golden, level: int, what=""):
 # share is bounded.  The decisions themselves are tested separately (argmin bit-exact away from
 # ties).
 # ---------------------------------------------------------------------------------------------
-COORD_EPS = 2e-6  # relative to the image extent: a few fp32 ulps of the pixel coordinate
+COORD_EPS = 1e-6  # relative to the image extent (1e-3 px at 1024): ~10 fp32 ulps of the pixel coordinate
+
+
+# ---------------------------------------------------------------------------------------------
+# Parity records: every gradient comparison appends one JSON line (shape, excluded fraction,
+# 99.9 % quantile, worst element, the fp32 reference algorithm's own worst) to
+# gpurun_out/parity_records.jsonl; tools/collect_parity.py turns that into profiles/rNN_parity.json.
+# ---------------------------------------------------------------------------------------------
+def parity_record(entry: dict):
+    import json
+    root = os.environ.get("GRAFT_REPO_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out_dir = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        entry = dict(entry, build=os.environ.get("CDP_PARITY_TAG", "default"))
+        with open(os.path.join(out_dir, "parity_records.jsonl"), "a") as f:
+            f.write(json.dumps(entry) + "\n")
+    except OSError:
+        pass
 
 
 def _spread_to_full_res(masks, height, width, window):
@@ -158,19 +176,17 @@ def smooth_sign_shadow(disp, rel_eps=2e-6):
     return mask
 
 
-def assert_grad_close_masked(got, want, mask_out, what, rtol=GRAD_RTOL, max_masked_frac=0.25, ref32=None):
+def assert_grad_close_masked(got, want, mask_out, what, rtol=GRAD_RTOL, max_masked_frac=0.05, ref32=None,
+                             record=None):
     """Deviation from the fp64 result ``want``, normalised by max|want|, over the elements NOT in
     ``mask_out`` (discrete switches).
 
-    Without ``ref32``: every element within ``rtol``.
-
-    With ``ref32`` (the reference algorithm evaluated in fp32 on the same inputs): fp32 cannot
-    hold 1e-4 element-wise at BASELINE image sizes -- sample coordinates above 1000 px resolve
-    only ~1e-4 px, which moves warped values by ~5e-5 and, through SSIM variances E[x^2]-mu^2 of
-    order 1e-3, single gradient elements by ~1e-3 of max-abs; the fp32 reference deviates from
-    its own fp64 run by that much (5e-4 on dL/d depth, 8e-4 on dL/dT in the committed
-    fixtures).  So: 99.9 % of the elements within ``rtol``, and the worst element no worse than
-    ``rtol`` + 3x the fp32 reference's own worst deviation."""
+    Every kept element must be within ``rtol`` (north_star: 1e-4); at most ``max_masked_frac`` of
+    the elements may be excluded.  ``ref32`` (the reference algorithm evaluated in fp32 on the same
+    inputs) is only recorded next to the result: at BASELINE image sizes the fp32 reference itself
+    deviates from its fp64 run by 1e-3 .. 2e-2 of max-abs on single kept elements (sample coordinates
+    above 1000 px resolve only ~1e-4 px; SSIM variances E[x^2]-mu^2 of order 1e-3), the kernels'
+    displacement-form warp and centred statistics stay below 6e-5 (profiles/r02_parity.json)."""
     got = torch.as_tensor(got, dtype=torch.float64).cpu()
     want = torch.as_tensor(want, dtype=torch.float64).cpu()
     keep = ~mask_out.reshape(want.shape) if mask_out is not None else torch.ones_like(want, dtype=torch.bool)
@@ -180,21 +196,30 @@ def assert_grad_close_masked(got, want, mask_out, what, rtol=GRAD_RTOL, max_mask
     dev = ((got - want).abs() / scale)[keep]
     worst = float(dev.max())
     excluded = int((~keep).sum())
+    bulk = None
+    if dev.numel() >= 1000:
+        bulk = float(torch.quantile(dev[torch.randperm(dev.numel(), generator=torch.Generator().manual_seed(0))[:4_000_000]], 0.999))
+    ref_worst = None
+    if ref32 is not None:
+        ref_worst = float((((torch.as_tensor(ref32, dtype=torch.float64).cpu() - want).abs() / scale)[keep]).max())
+    if record is not None:
+        record.update(what=what, elements=int(want.numel()), excluded=excluded, excluded_frac=frac, q999=bulk,
+                      worst=worst, worst_unmasked=float(((got - want).abs() / scale).max()),
+                      fp32_reference_worst=ref_worst, rtol=rtol)
+        parity_record(record)
     if ref32 is None:
         assert worst <= rtol, (f"{what}: max-abs-normalised error {worst:.3e} > {rtol} "
                                f"({excluded} discontinuous elements excluded)")
         return excluded
-    ref_worst = float((((torch.as_tensor(ref32, dtype=torch.float64).cpu() - want).abs() / scale)[keep]).max())
-    if dev.numel() >= 1000:
-        bulk = float(torch.quantile(dev[torch.randperm(dev.numel())[:4_000_000]], 0.999))
+    if bulk is not None:
         assert bulk <= rtol, f"{what}: 99.9% quantile of the normalised error {bulk:.3e} > {rtol}"
-    assert worst <= rtol + 3 * ref_worst, (f"{what}: worst normalised error {worst:.3e} exceeds {rtol} + 3 x the fp32 "
-                                           f"reference's own worst deviation ({ref_worst:.3e})")
+    assert worst <= rtol, (f"{what}: worst normalised error {worst:.3e} > {rtol} over the {dev.numel()} elements away "
+                           f"from discrete switches (the fp32 reference's own worst: {ref_worst:.3e})")
     return excluded
 
 
 def check_photo_grads(out, inputs, num_scales, what, level_intrinsics=None, recon_weight=1.0,
-                      max_masked_frac=0.25, pose_rtol=GRAD_RTOL):
+                      max_masked_frac=0.05, pose_rtol=GRAD_RTOL):
     """Gradient parity of one photometric-loss result ``out`` (dict with argmin, grad_depth,
     grad_pose) against the oracle evaluated with the same min-reprojection selection, in fp64
     (truth) and fp32 (the reference's own rounding).  Returns a short report string."""
@@ -206,13 +231,22 @@ def check_photo_grads(out, inputs, num_scales, what, level_intrinsics=None, reco
     r64 = po.loss_and_grads(*args, dtype=torch.float64, **kw)
     r32 = po.loss_and_grads(*args, dtype=torch.float32, **kw)
     mask = unstable_depth_mask(r64, out["argmin"], h, w).unsqueeze(1)
+    shape = dict(case=what, batch=int(inputs["depth"].shape[0]), height=h, width=w, scales=num_scales)
     n = assert_grad_close_masked(out["grad_depth"], r64["grad_depth"], mask, f"{what} dL/d depth",
-                                 max_masked_frac=max_masked_frac, ref32=r32["grad_depth"])
+                                 max_masked_frac=max_masked_frac, ref32=r32["grad_depth"], record=dict(shape))
+    # dL/dT sums over all pixels, discrete-switch pixels included, so they cannot be masked out.  A
+    # pixel whose fp64 |warped - target| is below fp32 resolution (2e-7) has an undecidable
+    # sign() in its L1 term; flipping it moves dL/dT of its sample by about 2 / (H_s W_s) of its
+    # magnitude (one pixel's term of the sum, twice).  That share is added to the tolerance: it is
+    # ~1e-3 for one such pixel in a 64x32 image and < 2e-5 at BASELINE sizes.
+    risk = torch.zeros(inputs["depth"].shape[0], dtype=torch.float64)
+    for m in r64["l1_margin"]:
+        risk += (m < 2e-7).flatten(1).sum(1).double() / float(m.shape[-1] * m.shape[-2])
+    allowance = 2.0 * float(risk.max())
     for i in range(2):
-        # dL/dT sums over all pixels, discrete-switch pixels included: on images of a few thousand
-        # pixels a single undecidable sign(warped - target) moves it by ~1e-4 (pose_rtol)
         assert_grad_close_masked(out["grad_pose"][i], r64["grad_pose"][i], None, f"{what} dL/dT{i}",
-                                 ref32=r32["grad_pose"][i], rtol=pose_rtol)
+                                 ref32=r32["grad_pose"][i], rtol=pose_rtol + allowance,
+                                 record=dict(shape, sign_switch_allowance=allowance))
     raw = rel_err(out["grad_depth"], r64["grad_depth"])
     raw32 = rel_err(r32["grad_depth"], r64["grad_depth"])
     return (f"{what}: dL/d depth max-abs-normalised deviation from fp64 {raw:.2e} (fp32 reference algorithm: "

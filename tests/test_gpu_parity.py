@@ -13,7 +13,7 @@ import codeps_b200
 from codeps_b200 import ops
 from codeps_b200.synthetic import make_batch, make_preset_batch
 from helpers import (GOLDEN_CASES, Golden, assert_argmin_matches, assert_grad_close,
-                     assert_grad_close_masked, assert_loss_close, check_photo_grads, rel_err,
+                     assert_grad_close_masked, assert_loss_close, check_photo_grads, parity_record, rel_err,
                      smooth_sign_shadow, tie_shadow)
 from oracle import photo_oracle as po
 
@@ -55,7 +55,7 @@ def test_golden_fixture_parity(name, cuda_device):
     assert_grad_close(out["grad_disp"], g.z["ref64_grad_disp"], "dL/d disp")
     if flips == 0:  # same selection everywhere: compare with the reference's own gradients directly
         assert_grad_close_masked(out["grad_depth"], g.z["ref64_grad_depth"], None, "dL/d depth vs reference",
-                                 ref32=g.z["ref32_grad_depth"], rtol=2e-4)
+                                 ref32=g.z["ref32_grad_depth"], record=dict(case=f"{name} vs reference fixture"))
         assert_grad_close_masked(out["grad_pose"][0], g.z["ref64_grad_pose0"], None, "dL/dT0 vs reference",
                                  ref32=g.z["ref32_grad_pose0"])
         assert_grad_close_masked(out["grad_pose"][1], g.z["ref64_grad_pose1"], None, "dL/dT1 vs reference",
@@ -123,10 +123,13 @@ def test_object_motion_warp(cuda_device):
     assert_grad_close(m.grad, m_ref.grad, "dL/d motion")
 
 
-@pytest.mark.parametrize("preset,batch", [("cityscapes", 1), ("kitti360", 1), ("semkitti", 2)])
+@pytest.mark.parametrize("preset,batch", [("cityscapes", 1), ("kitti360", 1), ("semkitti", 2), ("kitti360_cfg", 1),
+                                          ("kitti360", 8), ("cityscapes", 8)])
 def test_full_size_against_oracle(preset, batch, cuda_device):
-    """BASELINE shapes (1024x512, 1408x376 with non-integer pyramid ratios, 1280x384) against the
-    CPU oracle in fp32 for values and fp64 for the argmin arbiter."""
+    """BASELINE shapes (1024x512, 1408x376 with non-integer pyramid ratios, 1280x384, the 1408x384
+    the adaptation config actually feeds) against the CPU oracle in fp32 for values and fp64 for
+    the argmin arbiter; batch 8 with the flipped principal point on every other sample (replay
+    samples, datasets/preprocessing.py:47-52)."""
     tb = make_preset_batch(preset, batch, seed=21, flip_every_other=(batch > 1))
     w, h, scales = tb.width, tb.height, 5
     noise = po.draw_noise(batch, w, h, scales, seed=4321)
@@ -140,8 +143,8 @@ def test_full_size_against_oracle(preset, batch, cuda_device):
     assert_loss_close(out["smooth"], ref["smooth"], "smooth")
     assert_grad_close_masked(out["grad_disp"], ref["grad_disp"], smooth_sign_shadow(tb.disp), "dL/d disp")
     inp["noise"] = noise
-    print(check_photo_grads(out, inp, scales, preset, level_intrinsics=list(k_levels), recon_weight=10.0,
-                            max_masked_frac=0.05))
+    print(check_photo_grads(out, inp, scales, f"{preset} b{batch}", level_intrinsics=list(k_levels), recon_weight=10.0,
+                            max_masked_frac=0.02))
     # argmin: bit-exact wherever the fp64 top-2 gap exceeds 1e-6, at full size too.  (The
     # reference algorithm evaluated in fp32 differs from its own fp64 run on 7-10 pixels per
     # 0.5 Mpx here, with gaps up to 1.1e-5, because fp32 sample coordinates above 1000 px resolve
@@ -160,6 +163,11 @@ def test_full_size_against_oracle(preset, batch, cuda_device):
     hist = torch.bincount(out["argmin"][0].flatten().long(), minlength=4)
     assert (hist > 0).all(), hist  # both reprojection and auto-mask winners present
     print(f"{preset}: near-tie argmin differences vs fp64 oracle: {flips}; level-0 histogram {hist.tolist()}")
+    parity_record(dict(case=f"{preset} b{batch}", what="loss / argmin", batch=batch, height=h, width=w, scales=scales,
+                       recon_rel_err=abs(float(out["recon"]) - float(ref["recon"])) / abs(float(ref["recon"])),
+                       smooth_rel_err=abs(float(out["smooth"]) - float(ref["smooth"])) / abs(float(ref["smooth"])),
+                       argmin_flips_vs_fp64=flips, argmin_flips_away_from_ties=0, tie_gap=TIE_GAP_FULL,
+                       argmin_histogram_level0=hist.tolist()))
 
 
 def test_seeded_torch_noise_matches_reference_stream(cuda_device):
@@ -245,7 +253,7 @@ def test_batch_chunking_over_32_samples(cuda_device):
     assert_loss_close(out["recon"], ref["recon"], "recon")
     assert_grad_close_masked(out["grad_disp"], ref["grad_disp"], smooth_sign_shadow(tb.disp), "dL/d disp")
     inp["noise"] = noise
-    print(check_photo_grads(out, inp, scales, "35 samples", max_masked_frac=0.5, pose_rtol=1e-3))
+    print(check_photo_grads(out, inp, scales, "35 samples", max_masked_frac=0.05))
 
 
 def test_fused_noise_mode_and_no_grad(cuda_device):
@@ -300,8 +308,7 @@ def test_tiny_and_ragged_sizes(w, h, scales, cuda_device):
         decided = (top2[:, 1] - top2[:, 0]) > 1e-6
         assert not ((out["argmin"][s] != ref["argmin"][s]) & decided).any()
     inp["noise"] = noise
-    print(check_photo_grads(out, inp, scales, f"{w}x{h}", level_intrinsics=list(k_levels), max_masked_frac=0.6,
-                            pose_rtol=1e-3))
+    print(check_photo_grads(out, inp, scales, f"{w}x{h}", level_intrinsics=list(k_levels), max_masked_frac=0.05))
     assert_grad_close_masked(out["grad_disp"], ref["grad_disp"], smooth_sign_shadow(tb.disp), "dL/d disp")
 
 
@@ -475,6 +482,32 @@ def test_side_stream_noise_equals_single_stream(cuda_device):
     torch.cuda.synchronize()
     assert abs(float(out) - float(want[0])) <= 1e-5 * abs(float(want[0]))  # other noise draws, same loss to 1e-5
     assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+    # the captured side-stream draws are the ones the captured tile kernel consumed: an eager
+    # evaluation fed with the replay's own noise tensors reproduces the replay bit for bit (a missing
+    # join or a reused noise buffer would show up as different tie-breaks), and successive
+    # replays draw different noise
+    fn.keep_noise = True
+    graph2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph2):
+        d2 = static_depth.detach().requires_grad_(True)
+        out2 = fn(cams, tb.images, d2, tb.poses)
+        (g2,) = torch.autograd.grad(out2, d2)
+    captured_noise, captured_argmin = fn.last_noise, fn.last_argmin
+    fn.keep_noise = False
+    draws = []
+    for _ in range(2):
+        graph2.replay()
+        torch.cuda.synchronize()
+        noise = [n.clone() for n in captured_noise]
+        draws.append(noise[0])
+        loss_r, grad_r, argmin_r = out2.clone(), g2.clone(), [a.clone() for a in captured_argmin]
+        depth = static_depth.detach().requires_grad_(True)
+        loss_e, argmin_e = ops.photometric_loss(k_levels, tb.images, depth, tb.poses, noise, scales)
+        loss_e.backward()
+        torch.cuda.synchronize()
+        assert torch.equal(loss_r, loss_e.detach()) and torch.equal(grad_r, depth.grad)
+        assert all(torch.equal(a, b) for a, b in zip(argmin_r, argmin_e))
+    assert not torch.equal(draws[0], draws[1]), "successive replays must draw fresh noise"
 
 
 @pytest.mark.gpu
@@ -550,7 +583,7 @@ def test_degenerate_and_general_poses(case, cuda_device):
         top2 = torch.sort(free["candidates"][s], dim=1).values[:, :2]
         decided = (top2[:, 1] - top2[:, 0]) > 1e-6
         assert not ((out["argmin"][s] != free["argmin"][s]) & decided).any(), f"level {s}"
-    print(check_photo_grads(out, inp, g.num_scales, case, max_masked_frac=0.5, pose_rtol=1e-3))
+    print(check_photo_grads(out, inp, g.num_scales, case, max_masked_frac=0.05))
     assert torch.isfinite(out["grad_depth"]).all() and all(torch.isfinite(p).all() for p in out["grad_pose"])
 
 
@@ -578,3 +611,106 @@ def test_batch_64_equals_mean_of_its_chunks(cuda_device):
         assert rel_err(out64["grad_depth"][sl] * 8, out8["grad_depth"]) < 1e-6
         assert rel_err(out64["grad_disp"][sl] * 8, out8["grad_disp"]) < 1e-5
         assert rel_err(out64["grad_pose"][0][sl] * 8, out8["grad_pose"][0]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_mixed_resolution_adaptation_batch(cuda_device):
+    """The loss combination of DepthAlgo.adaptation (algos/depth.py:507-568) over the drop-ins: the
+    source samples (2 @1024x512, cfg/adapt_cityscapes_kitti_360.yaml:17-24), the online target
+    sample (1 @1408x384) and the target replay samples (2 @1408x384, every other one with the
+    flipped principal point) go through two ReconstructionLoss objects of different resolution
+    (reconstruction_loss_adapt_source / reconstruction_loss), are combined as
+    sum_k n_k L_k / sum_k n_k and back-propagated ONCE; every key's gradients must equal the
+    oracle's for that key scaled by n_k / sum n."""
+    dev = cuda_device
+    scales = 5
+    keys = {"source": make_preset_batch("cityscapes", 2, seed=51),
+            "target": make_preset_batch("kitti360_cfg", 1, seed=52),
+            "target_replay": make_preset_batch("kitti360_cfg", 2, seed=53, flip_every_other=True)}
+    total = sum(tb.images[0].shape[0] for tb in keys.values())
+    fns = {"source": codeps_b200.ReconstructionLoss(1024, 512, codeps_b200.SSIMLoss(), scales, dev),
+           "target": codeps_b200.ReconstructionLoss(1408, 384, codeps_b200.SSIMLoss(), scales, dev)}
+    smooth_fn = codeps_b200.EdgeAwareSmoothnessLoss()
+    state, recon, smooth, num = {}, {}, {}, {}
+    for i, (key, tb) in enumerate(keys.items()):
+        fn = fns["source" if key == "source" else "target"]
+        n = tb.images[0].shape[0]
+        noise = po.draw_noise(n, tb.width, tb.height, scales, seed=60 + i)
+        depth = tb.depth.to(dev).requires_grad_(True)
+        disp = tb.disp.to(dev).requires_grad_(True)
+        poses = [p.to(dev).requires_grad_(True) for p in tb.poses]
+        images = tuple(im.to(dev) for im in tb.images)
+        k_levels = fn._level_intrinsics(tb.camera_models())
+        recon[key], argmin = ops.photometric_loss(k_levels, images, depth, poses, [x.to(dev) for x in noise], scales, 0.85)
+        smooth[key] = smooth_fn(images[0], disp)
+        num[key] = n
+        state[key] = dict(tb=tb, noise=noise, depth=depth, disp=disp, poses=poses, argmin=argmin, k_levels=k_levels)
+    # algos/depth.py:562-568
+    depth_recon = torch.stack([loss * num[k] for k, loss in recon.items()]).sum() / total
+    depth_smth = torch.stack([loss * num[k] for k, loss in smooth.items()]).sum() / total
+    (depth_recon + 0.001 * depth_smth).backward()
+    torch.cuda.synchronize()
+    want_recon, want_smth = 0.0, 0.0
+    for key, st in state.items():
+        tb = st["tb"]
+        share = num[key] / total
+        ref = po.loss_and_grads(tb.intrinsics.numpy(), tb.images, tb.depth, tb.disp, tb.poses, st["noise"], scales,
+                                dtype=torch.float64, level_intrinsics=list(st["k_levels"]))
+        want_recon += share * float(ref["recon"])
+        want_smth += share * float(ref["smooth"])
+        out = dict(argmin=[a.cpu() for a in st["argmin"]], grad_depth=st["depth"].grad.cpu(),
+                   grad_pose=[p.grad.cpu() for p in st["poses"]])
+        inp = dict(images=tb.images, depth=tb.depth, disp=tb.disp, poses=tb.poses, intrinsics=tb.intrinsics.numpy(),
+                   noise=st["noise"])
+        print(check_photo_grads(out, inp, scales, f"adapt_mix/{key}", level_intrinsics=list(st["k_levels"]),
+                                recon_weight=share, max_masked_frac=0.02))
+        assert_grad_close_masked(st["disp"].grad.cpu(), 0.001 * share * ref["grad_disp"], smooth_sign_shadow(tb.disp),
+                                 f"adapt_mix/{key} dL/d disp")
+    assert_loss_close(depth_recon.detach().cpu(), want_recon, "combined recon")
+    assert_loss_close(depth_smth.detach().cpu(), want_smth, "combined smooth")
+
+
+@pytest.mark.gpu
+def test_misaligned_views_take_the_table_path(cuda_device):
+    """Contiguous fp32 views whose storage offset is not a multiple of 4 floats (not 16-byte aligned)
+    must not reach the 16-byte-load pyramid path: same result as aligned copies, no fault."""
+    dev = cuda_device
+    tb = make_preset_batch("semkitti", 1, seed=3)
+    w, h, scales = tb.width, tb.height, 5
+    noise = [n.to(dev) for n in po.draw_noise(1, w, h, scales, seed=2)]
+    fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), scales, dev)
+    k_levels = fn._level_intrinsics(tb.camera_models())
+
+    def shifted(t):  # same values at a storage offset of one float
+        flat = torch.empty(t.numel() + 1, device=dev)
+        flat[1:].copy_(t.flatten())
+        view = flat[1:].view(t.shape)
+        assert view.is_contiguous() and view.data_ptr() % 16 != 0
+        return view
+
+    images = tuple(i.to(dev) for i in tb.images)
+    depth = tb.depth.to(dev)
+    poses = [p.to(dev) for p in tb.poses]
+    with torch.no_grad():
+        want, am_want = ops.photometric_loss(k_levels, images, depth, poses, noise, scales)
+        got, am_got = ops.photometric_loss(k_levels, tuple(shifted(i) for i in images), shifted(depth), poses, noise, scales)
+    torch.cuda.synchronize()
+    assert abs(float(got) - float(want)) <= 1e-6 * abs(float(want))
+    assert all((a != b).float().mean() < 1e-5 for a, b in zip(am_got, am_want))
+
+
+@pytest.mark.gpu
+def test_nearest_warp_has_zero_coordinate_gradient(cuda_device):
+    """F.grid_sample(mode='nearest') returns a zero grid gradient; a nearest-warped tensor that stays
+    connected to depth / pose must back-propagate zeros instead of raising."""
+    dev = cuda_device
+    g = Golden("city_near")
+    inp = g.inputs(dev)
+    cams = cams_from(inp["intrinsics"], g.width, g.height)
+    warper = codeps_b200.ImageWarper(g.width, g.height, dev)
+    depth = inp["depth"].clone().requires_grad_(True)
+    pose = inp["poses"][1].clone().requires_grad_(True)
+    out = warper(cams, inp["images"][2], depth, pose, interp_mode="nearest")
+    out.sum().backward()
+    assert depth.grad is not None and float(depth.grad.abs().max()) == 0.0
+    assert pose.grad is not None and float(pose.grad.abs().max()) == 0.0
