@@ -4,6 +4,7 @@
 // (shared-memory staging, block barriers, fixed-order block reductions) and the host-side entry
 // points (argument checks, launch planning, error reporting).  There is no CPU code path here:
 // every entry point enqueues CUDA kernels on the caller's stream or fails.
+#include <cuda.h>  // CUtensorMap, cuTensorMapEncodeTiled (types only: the entry point is fetched at run time)
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -180,14 +181,71 @@ __global__ void cdp_k_table_kernel(const __grid_constant__ CdpKTableParams p) {
   if (i < p.batch_count * p.L) cdp_k_table_entry(p, i / p.batch_count, i % p.batch_count);
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA staging of the tile kernel's boxes.  One descriptor per (level, tensor): rank 3
+// [planes = B*3 (or B), H_s, W_s], box = [3 (or 1), TBH, TBW] for target / depth and
+// [3, SBH, SBW] for the sources; out-of-image elements are zero-filled by the hardware.
+// ------------------------------------------------------------------------------------------
+struct CdpTmaMaps {
+  CUtensorMap m[CDP_MAX_LEVELS][4];  // target, depth, source0, source1
+};
+
+__device__ __forceinline__ uint32_t cdp_smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cdp_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cdp_smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async (TMA) proxy
+}
+__device__ __forceinline__ void cdp_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cdp_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cdp_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(cdp_smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cdp_tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(cdp_smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(cdp_smem_addr(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+
 template <bool G, bool M>
 __global__ void __launch_bounds__(CDP_PHOTO_THREADS, CDP_PHOTO_MIN_CTAS)
-cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p) {
-  extern __shared__ __align__(16) float sm[];
+cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant__ CdpTmaMaps tm) {
+  typedef CdpTileGeom<G> Geo;
+  extern __shared__ __align__(128) float sm[];
   const CdpTileCtx c = cdp_tile_ctx(p, blockIdx.x, blockIdx.y);
   float v[G ? 33 : 1];
 #pragma unroll
   for (int i = 0; i < (G ? 33 : 1); ++i) v[i] = 0.f;
+  if (p.lv[c.lvl].use_tma) {
+    // phase S by TMA: one thread arms the mbarrier with the byte count of the four boxes and
+    // issues them; every thread waits for the data to land
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + Geo::O_MBAR);
+    if (threadIdx.x == 0) cdp_mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      cdp_mbar_expect_tx(bar, Geo::TMA_BYTES);
+      const int ox = c.x0 - Geo::TXO, oy = c.y0 - Geo::TYO;  // (multiples of 4 in x: 16-byte aligned box starts)
+      cdp_tma_load_3d(sm + Geo::O_DEPTH, &tm.m[c.lvl][1], bar, ox, oy, c.b);
+      cdp_tma_load_3d(sm + Geo::O_SRC, &tm.m[c.lvl][2], bar, ox - Geo::SBM, oy - Geo::SBM, c.b * 3);
+      cdp_tma_load_3d(sm + Geo::O_SRC + Geo::SRC_STRIDE, &tm.m[c.lvl][3], bar, ox - Geo::SBM, oy - Geo::SBM, c.b * 3);
+      cdp_tma_load_3d(sm + Geo::O_TGT, &tm.m[c.lvl][0], bar, ox, oy, c.b * 3);
+    }
+    cdp_mbar_wait(bar, 0);
+  } else {
+    cdp_photo_stage<G>(p, c, threadIdx.x, blockDim.x, sm);
+    __syncthreads();
+  }
   cdp_photo_phase_a<G, M>(p, c, threadIdx.x, blockDim.x, sm);
   __syncthreads();
   cdp_photo_phase_b1<G>(p, c, threadIdx.x, blockDim.x, sm, v[0]);
@@ -392,6 +450,56 @@ extern "C" size_t cdp_photo_saved_bytes(int32_t batch, int32_t height, int32_t w
   return plan.saved_floats * sizeof(float);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup (no link against libcuda)
+typedef CUresult (*CdpEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CdpEncodeTiled cdp_encode_tiled_fn() {
+  static CdpEncodeTiled fn = []() -> CdpEncodeTiled {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<CdpEncodeTiled>(sym);
+  }();
+  return fn;
+}
+
+// fp32 tensor [planes][H][W] (contiguous) -> descriptor with a [box_p][box_h][box_w] box
+static bool cdp_encode_box(CUtensorMap* map, const float* base, int planes, int H, int W, int box_p, int box_h, int box_w) {
+  CdpEncodeTiled enc = cdp_encode_tiled_fn();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (W % 4) != 0) return false;  // pitch must be a multiple of 16 bytes
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_p};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Descriptors for every level whose four tensors qualify; the others keep use_tma = 0 and are
+// staged with plain loads.  CDP_PHOTO_TMA=0 in the environment disables TMA staging (A/B runs).
+static void cdp_make_tma_maps(const CdpPlan& plan, CdpPhotoParams* kp, CdpTmaMaps* tm) {
+  typedef CdpTileGeom<true> Geo;  // box sizes do not depend on the instantiation
+  static const bool enabled = []() { const char* e = getenv("CDP_PHOTO_TMA"); return !(e && e[0] == '0'); }();
+  memset(tm, 0, sizeof(*tm));
+  for (int s = 0; s < plan.L; ++s) {
+    CdpLevel& lv = kp->lv[s];
+    lv.use_tma = 0;
+    if (!enabled) continue;
+    const bool ok = cdp_encode_box(&tm->m[s][0], lv.tgt, plan.B * 3, lv.H, lv.W, 3, Geo::TBH, Geo::TBW) &&
+                    cdp_encode_box(&tm->m[s][1], lv.depth, plan.B, lv.H, lv.W, 1, Geo::TBH, Geo::TBW) &&
+                    cdp_encode_box(&tm->m[s][2], lv.src0, plan.B * 3, lv.H, lv.W, 3, Geo::SBH, Geo::SBW) &&
+                    cdp_encode_box(&tm->m[s][3], lv.src1, plan.B * 3, lv.H, lv.W, 3, Geo::SBH, Geo::SBW);
+    lv.use_tma = ok ? 1 : 0;
+  }
+}
+
 static int cdp_batch_chunks(int32_t batch) { return (batch + CDP_MAX_BATCH_PER_LAUNCH - 1) / CDP_MAX_BATCH_PER_LAUNCH; }
 
 extern "C" int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels) {
@@ -448,7 +556,7 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   const size_t smem = G ? CdpTileGeom<true>::SMEM_BYTES : CdpTileGeom<false>::SMEM_BYTES;
   static unsigned long long smem_done[4] = {0ull, 0ull, 0ull, 0ull};
   const bool M = plan.has_motion != 0;
-  typedef void (*PhotoKernel)(const CdpPhotoParams);
+  typedef void (*PhotoKernel)(const CdpPhotoParams, const CdpTmaMaps);
   static const PhotoKernel kernels[4] = {cdp_photo_kernel<false, false>, cdp_photo_kernel<false, true>,
                                          cdp_photo_kernel<true, false>, cdp_photo_kernel<true, true>};
   const int which = (G ? 2 : 0) + (M ? 1 : 0);
@@ -467,10 +575,12 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   {
     CdpPhotoParams kp;
     cdp_fill_photo_params(plan, a, 0, plan.B, &kp);
+    CdpTmaMaps tm;
+    cdp_make_tma_maps(plan, &kp, &tm);
     dim3 grid(plan.blocks_per_image, plan.B);
     {
       ProfScope prof_(CDP_KERNEL_PHOTO, stream);
-      photo_kernel<<<grid, CDP_PHOTO_THREADS, smem, stream>>>(kp);
+      photo_kernel<<<grid, CDP_PHOTO_THREADS, smem, stream>>>(kp, tm);
     }
     CDP_LAUNCH_CHECK("cdp_photo_kernel");
   }

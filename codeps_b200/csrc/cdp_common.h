@@ -96,6 +96,7 @@ struct CdpLevel {
   int32_t tiles_x, tiles_y;
   int32_t block_begin;  // first block index (within one image) belonging to this level
   float weight;         // 1 / (B * H * W * 2^s * num_levels)
+  int32_t use_tma;      // 1: the boxes of this level are staged by TMA (descriptors in CdpTmaMaps)
 };
 
 struct CdpPhotoParams {

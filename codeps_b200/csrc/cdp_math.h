@@ -125,23 +125,32 @@ struct CdpWarp {
   bool regular;        // depth clamp inactive and Q_w != 0
 };
 
+CDP_HD float cdp_fmaf(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return a * b + c;  // the emulator is built with -ffp-contract=off (as for cdp_fma2)
+#endif
+}
+
 CDP_HD void cdp_warp_point(float u, float v, float depth, const CdpCam& k, const CdpPose& T,
                            const float* motion3, CdpWarp& o) {
   o.rx = (u - k.cx) * k.ifx;
   o.ry = (v - k.cy) * k.ify;
   o.P[0] = depth * o.rx; o.P[1] = depth * o.ry; o.P[2] = depth;
-  float ax = T.d[0] * o.P[0] + T.d[1] * o.P[1] + T.d[2] * o.P[2] + T.d[3];
-  float ay = T.d[4] * o.P[0] + T.d[5] * o.P[1] + T.d[6] * o.P[2] + T.d[7];
-  float az = T.d[8] * o.P[0] + T.d[9] * o.P[1] + T.d[10] * o.P[2] + T.d[11];
+  // (explicit FMA order: the packed two-source version below evaluates the same expression tree)
+  float ax = cdp_fmaf(T.d[0], o.P[0], cdp_fmaf(T.d[1], o.P[1], cdp_fmaf(T.d[2], o.P[2], T.d[3])));
+  float ay = cdp_fmaf(T.d[4], o.P[0], cdp_fmaf(T.d[5], o.P[1], cdp_fmaf(T.d[6], o.P[2], T.d[7])));
+  float az = cdp_fmaf(T.d[8], o.P[0], cdp_fmaf(T.d[9], o.P[1], cdp_fmaf(T.d[10], o.P[2], T.d[11])));
   if (motion3) { ax += motion3[0]; ay += motion3[1]; az += motion3[2]; }
-  o.Q[3] = T.d[12] * o.P[0] + T.d[13] * o.P[1] + T.d[14] * o.P[2] + T.d[15];
+  o.Q[3] = cdp_fmaf(T.d[12], o.P[0], cdp_fmaf(T.d[13], o.P[1], cdp_fmaf(T.d[14], o.P[2], T.d[15])));
   o.Q[0] = o.P[0] + ax; o.Q[1] = o.P[1] + ay; o.Q[2] = o.P[2] + az;
   // E_z = Q_z / Q_w >= 1e-5 without dividing
   o.regular = o.Q[3] > 0.f ? (o.Q[2] >= CDP_Z_MIN * o.Q[3]) : (o.Q[3] < 0.f && o.Q[2] <= CDP_Z_MIN * o.Q[3]);
   if (o.regular) {
     o.iz = cdp_rcp(o.Q[2]);
-    o.dx = k.fx * (ax - o.rx * az) * o.iz;
-    o.dy = k.fy * (ay - o.ry * az) * o.iz;
+    o.dx = (k.fx * cdp_fmaf(-o.rx, az, ax)) * o.iz;
+    o.dy = (k.fy * cdp_fmaf(-o.ry, az, ay)) * o.iz;
     o.ix = u + o.dx;
     o.iy = v + o.dy;
   } else {  // literal reference formula: E = Q_xyz / Q_w, z = max(E_z, 1e-5)
@@ -153,6 +162,74 @@ CDP_HD void cdp_warp_point(float u, float v, float depth, const CdpCam& k, const
     o.dx = o.ix - u;
     o.dy = o.iy - v;
   }
+}
+
+// Both source frames at once, one per lane of packed fp32 (FFMA2 / FADD2 / FMUL2): sample
+// displacement and absolute sample position only (what the forward gather needs).  Lane results
+// are bit-identical to cdp_warp_point's regular branch; a lane whose depth clamp is active
+// (regular[k] false) must be redone with cdp_warp_point.
+struct CdpPose2 {
+  float2 d[16];  // lane x = source 0 (t-1), lane y = source 1 (t+1); T - diag(1,1,1,0) as in CdpPose
+};
+CDP_HD void cdp_pack_pose(const CdpPose& a, const CdpPose& b, CdpPose2& o) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { o.d[i].x = a.d[i]; o.d[i].y = b.d[i]; }
+}
+CDP_HD void cdp_unpack_pose(const CdpPose2& p, int k, CdpPose& o) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o.d[i] = k == 0 ? p.d[i].x : p.d[i].y;
+}
+struct CdpWarp2 {
+  float2 dx, dy, ix, iy;
+  bool regular[2];  // (only ever indexed with constants: stays in predicate registers)
+  // for the adjoint (regular lanes): viewing ray, back-projected point, transformed point, 1 / Q_z
+  float rx, ry, P[3];
+  float2 Qx, Qy, iz;
+};
+CDP_HD void cdp_warp_point2(float u, float v, float depth, const CdpCam& k, const CdpPose2& T,
+                            const float2* motion3, CdpWarp2& o) {
+  o.rx = (u - k.cx) * k.ifx; o.ry = (v - k.cy) * k.ify;
+  o.P[0] = depth * o.rx; o.P[1] = depth * o.ry; o.P[2] = depth;
+  const float2 Px = cdp_set2(o.P[0]), Py = cdp_set2(o.P[1]), Pz = cdp_set2(o.P[2]);
+  float2 ax = cdp_fma2(T.d[0], Px, cdp_fma2(T.d[1], Py, cdp_fma2(T.d[2], Pz, T.d[3])));
+  float2 ay = cdp_fma2(T.d[4], Px, cdp_fma2(T.d[5], Py, cdp_fma2(T.d[6], Pz, T.d[7])));
+  float2 az = cdp_fma2(T.d[8], Px, cdp_fma2(T.d[9], Py, cdp_fma2(T.d[10], Pz, T.d[11])));
+  if (motion3) { ax = cdp_add2(ax, motion3[0]); ay = cdp_add2(ay, motion3[1]); az = cdp_add2(az, motion3[2]); }
+  const float2 Qw = cdp_fma2(T.d[12], Px, cdp_fma2(T.d[13], Py, cdp_fma2(T.d[14], Pz, T.d[15])));
+  const float2 Qz = cdp_add2(Pz, az);
+  o.Qx = cdp_add2(Px, ax); o.Qy = cdp_add2(Py, ay);
+  o.regular[0] = Qw.x > 0.f ? (Qz.x >= CDP_Z_MIN * Qw.x) : (Qw.x < 0.f && Qz.x <= CDP_Z_MIN * Qw.x);
+  o.regular[1] = Qw.y > 0.f ? (Qz.y >= CDP_Z_MIN * Qw.y) : (Qw.y < 0.f && Qz.y <= CDP_Z_MIN * Qw.y);
+  // (an irregular lane gets iz = 0: its packed displacement and adjoint are exactly zero instead of
+  // inf / NaN, and the caller redoes that source with the literal formulas)
+  o.iz.x = o.regular[0] ? cdp_rcp(Qz.x) : 0.f; o.iz.y = o.regular[1] ? cdp_rcp(Qz.y) : 0.f;
+  o.dx = cdp_mul2(cdp_mul2(cdp_set2(k.fx), cdp_fma2(cdp_set2(-o.rx), az, ax)), o.iz);
+  o.dy = cdp_mul2(cdp_mul2(cdp_set2(k.fy), cdp_fma2(cdp_set2(-o.ry), az, ay)), o.iz);
+  o.ix = cdp_add2(cdp_set2(u), o.dx);
+  o.iy = cdp_add2(cdp_set2(v), o.dy);
+}
+
+// Adjoint of the regular branch for both sources at once (lanes): gu, gv = dL/d(ix, iy) with the
+// clip mask applied.  Adds to dT2[4 r + c] (rows 0..2; row 3 receives nothing when the depth
+// clamp is inactive, Q_w drops out) and returns dL/d depth summed over the two sources' lanes as
+// a pair (caller adds .x + .y); gQ[3] is handed back for dL/d motion.
+CDP_HD float2 cdp_warp_adjoint2(float2 gu, float2 gv, const CdpWarp2& w, const CdpCam& k, const CdpPose2& T,
+                                float2* dT2, float2* gQ) {
+  gQ[0] = cdp_mul2(cdp_mul2(gu, cdp_set2(k.fx)), w.iz);
+  gQ[1] = cdp_mul2(cdp_mul2(gv, cdp_set2(k.fy)), w.iz);
+  gQ[2] = cdp_mul2(cdp_fma2(gQ[0], w.Qx, cdp_mul2(gQ[1], w.Qy)), cdp_mul2(w.iz, cdp_set2(-1.0f)));
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    dT2[4 * r + 0] = cdp_fma2(gQ[r], cdp_set2(w.P[0]), dT2[4 * r + 0]);
+    dT2[4 * r + 1] = cdp_fma2(gQ[r], cdp_set2(w.P[1]), dT2[4 * r + 1]);
+    dT2[4 * r + 2] = cdp_fma2(gQ[r], cdp_set2(w.P[2]), dT2[4 * r + 2]);
+    dT2[4 * r + 3] = cdp_add2(dT2[4 * r + 3], gQ[r]);
+  }
+  // gP = T^T gQ with T = D + diag(1,1,1,0);  dP/d depth = (rx, ry, 1)
+  const float2 gPx = cdp_fma2(T.d[0], gQ[0], cdp_fma2(T.d[4], gQ[1], cdp_fma2(T.d[8], gQ[2], gQ[0])));
+  const float2 gPy = cdp_fma2(T.d[1], gQ[0], cdp_fma2(T.d[5], gQ[1], cdp_fma2(T.d[9], gQ[2], gQ[1])));
+  const float2 gPz = cdp_fma2(T.d[2], gQ[0], cdp_fma2(T.d[6], gQ[1], cdp_fma2(T.d[10], gQ[2], gQ[2])));
+  return cdp_fma2(gPx, cdp_set2(w.rx), cdp_fma2(gPy, cdp_set2(w.ry), gPz));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -200,6 +277,20 @@ CDP_HD void cdp_taps(int u, int v, const CdpWarp& w, int W, int H, CdpTaps& t) {
   cdp_tap_axis(u, w.dx, w.ix, W, x0, x1, t.wx0, t.wx1, t.mx);
   cdp_tap_axis(v, w.dy, w.iy, H, y0, y1, t.wy0, t.wy1, t.my);
   t.o00 = y0 * W + x0; t.o01 = y0 * W + x1; t.o10 = y1 * W + x0; t.o11 = y1 * W + x1;
+}
+
+// The same sampler with an always-full 2x2 footprint: lower tap index kept in [0, n-2], upper tap =
+// lower + 1, so that the four taps sit at base + {0, 1, stride, stride + 1} (one address and three
+// immediate offsets).  A coordinate clipped to the far border becomes (n-2, fraction 1), which is
+// the same value as (n-1, fraction 0).
+CDP_HD void cdp_tap_axis_full(int p, float d, float i, int n, int& i0, float& frac, float& m) {
+  const bool pos = i > 0.f, inside = pos && i < (float)(n - 1);  // NaN: both false -> border 0
+  const float fl = floorf(d);
+  int a = inside ? p + (int)fl : (pos ? n - 2 : 0);
+  a = a < 0 ? 0 : (a > n - 2 ? n - 2 : a);
+  i0 = a;
+  frac = inside ? d - fl : (pos ? 1.f : 0.f);
+  m = inside ? 1.f : 0.f;
 }
 
 CDP_HD float cdp_bilinear(const float* plane, const CdpTaps& t) {

@@ -2,15 +2,21 @@
 //
 // One CTA = one 32x32 tile of one pyramid level of one sample.  Phases (a block barrier between
 // consecutive ones):
-//   A   warp both source frames for every staged position (tile + halo, reflected at the image
-//       border), stage target / source / warped values in shared memory, centred on a tile
-//       constant; the two candidates of a pair are interleaved as float2.
+//   S   stage dense boxes in shared memory: target (tile + 2), depth (tile + 2) and both source
+//       frames (tile + 2 + a gather margin of 4).  On the GPU these are four TMA box loads
+//       (cp.async.bulk.tensor.3d, zero fill outside the image) issued by one thread and awaited on
+//       an mbarrier (cdp_api.cu); levels whose row pitch is not a multiple of 16 bytes -- and the
+//       CPU emulator -- fill the same boxes with cdp_photo_stage (plain loads).
+//   A   reflect the one-pixel ring outside the image inside shared memory (border tiles only);
+//       warp both source frames for every staged position with the two sources in the two lanes
+//       of packed fp32, bilinear taps served from the staged source boxes (global loads only for
+//       taps that leave the margin), warped values -> shared memory as (source 0, source 1) pairs.
 //   B1  min-reprojection: each thread owns a vertical strip of 5 pixels in one column and
 //       slides a 3-row window down it (separable 3x3 sums), all four candidates at once, the two
 //       candidates of a pair in the two lanes of packed fp32 (FFMA2).  -> candidate losses,
 //       tie-break noise, min / argmin, loss partial, argmin map, winner plane.
 //   B2  (with grad) same walk over the reprojection pair only, SSIM adjoint coefficients of the
-//       winner -> shared memory (the source planes are dead by then and are reused).
+//       winner -> shared memory (the source boxes are dead by then and are reused).
 //   C   (with grad) gather the adjoint over the reflected 3x3 neighbourhood, L1 term, chain
 //       through the bilinear sampler and the projection to depth and pose.
 // Reference: algos/depth.py:221-237, 272-325 (ReconstructionLoss), 128-155 (SSIMLoss);
@@ -19,42 +25,59 @@
 
 #include "cdp_math.h"
 
-#ifndef CDP_OPT_PACKED_GATHER
-#define CDP_OPT_PACKED_GATHER 0  // float2-packed coefficient gather in phase C: measured slower (spills), off
-#endif
 #ifndef CDP_OPT_DIRECT_DT
 #define CDP_OPT_DIRECT_DT 1  // phase C accumulates dL/dT without a per-pixel temporary
-#endif
-#ifndef CDP_OPT_PREFETCH_DEPTH
-#define CDP_OPT_PREFETCH_DEPTH 1  // phase A requests the next region pixel's depth one iteration ahead: -1 %
 #endif
 #ifndef CDP_STRIP
 #define CDP_STRIP 5  // pixels per thread strip in phases B1/B2
 #endif
+#ifndef CDP_SRC_MARGIN
+#define CDP_SRC_MARGIN 4  // gather margin of the staged source boxes (pixels beyond the target box)
+#endif
 
+// Shared-memory geometry.  All planes except the source boxes are TBW x TBH with origin
+// (x0 - TXO, y0 - TYO), whatever the halo the instantiation computes on, so that one set of TMA
+// descriptors serves both; "t-index" = ty * TBW + tx.  The source boxes are SBW x SBH with origin
+// (x0 - TXO - SBM, y0 - TYO - SBM); "s-index" = (ty + SBM) * SBW + tx + SBM.  A TMA box must start
+// at a multiple of 16 bytes in the innermost dimension (measured: an x coordinate that is not a
+// multiple of 4 floats faults with "illegal instruction", tools/experiments/tma_probe.cu), hence
+// TXO = 4 and SBM = 4 although the window sums only need two columns left of the tile.
 template <bool G>
 struct CdpTileGeom {
-  static constexpr int HALO = G ? 2 : 1;  // staged ring around the tile
+  static constexpr int HALO = G ? 2 : 1;  // ring around the tile on which warped values are needed
+  static constexpr int TXO = 4, TYO = 2;  // box position of the tile's first column / row
+  static constexpr int OFFX = TXO - HALO, OFFY = TYO - HALO;  // first box column / row of that region
   static constexpr int RW = CDP_TILE_X + 2 * HALO, RH = CDP_TILE_Y + 2 * HALO, RN = RW * RH;
   static constexpr int HB = HALO - 1;     // ring on which losses / argmin / coefficients are needed
   static constexpr int BW = CDP_TILE_X + 2 * HB, BH = CDP_TILE_Y + 2 * HB;
   static constexpr int NSTRIP = (BH + CDP_STRIP - 1) / CDP_STRIP;
   static constexpr int NITEMS = BW * NSTRIP;  // (column, strip) work items of phases B1/B2
-  // shared-memory planes of RN floats
-  static constexpr int P_TGT = 0;    // 3 planes: target, channel c
-  static constexpr int P_WARP = 3;   // 3 float2 planes (6 floats): warped (source 0, source 1), channel c
-  static constexpr int P_SRC = 9;    // 3 float2 planes: un-warped (source 0, source 1) = identity candidates
-  // with grad, after B1: adjoint coefficients of the winner as 5 float2 planes
-  // (A0,A1) (B0,B1) (C0,C1) (A2,B2) (C2,-)  [letter = coefficient, digit = channel]
-  static constexpr int P_COEF = 9;
-  static constexpr int NPLANES = G ? (CDP_OPT_PACKED_GATHER ? 19 : 18) : 15;
-  static constexpr size_t SMEM_BYTES = (size_t)NPLANES * RN * sizeof(float) + ((RN + 15) & ~15);
-  // The B1/B2 strip walk always reads CDP_STRIP + 2 region rows, also for the last, partial strip:
-  // the rows past RH belong to the following plane (values discarded) and, for the last plane, to
-  // the winner-byte tail, which must therefore be large enough for any CDP_TILE_Y / CDP_STRIP.
-  static constexpr int OVER_ROWS = NSTRIP * CDP_STRIP + 2 > RH ? NSTRIP * CDP_STRIP + 2 - RH : 0;
-  static_assert((size_t)OVER_ROWS * RW * sizeof(float2) <= ((RN + 15) & ~15) + (size_t)(NPLANES - 15) * RN * sizeof(float),
-                "strip over-read leaves the shared-memory allocation: pick CDP_TILE_Y / CDP_STRIP so that it fits");
+  static constexpr int TBW = CDP_TILE_X + 2 * TXO, TBH = CDP_TILE_Y + 2 * TYO, TBN = TBW * TBH;
+  static constexpr int SBM = CDP_SRC_MARGIN;
+  static constexpr int SBW = TBW + 2 * SBM, SBH = TBH + 2 * SBM, SBN = SBW * SBH;
+  static constexpr int align32(int n) { return (n + 31) & ~31; }  // TMA destinations: 128-byte aligned
+  // float offsets
+  static constexpr int O_TGT = 0;                                // [3][TBN] target
+  static constexpr int O_DEPTH = align32(O_TGT + 3 * TBN);       // [TBN]
+  static constexpr int O_WARP = align32(O_DEPTH + TBN);          // 3 float2 planes [TBN]: warped (source 0, source 1)
+  static constexpr int O_SRC = align32(O_WARP + 6 * TBN);        // 2 boxes [3][SBN], SRC_STRIDE apart
+  static constexpr int SRC_STRIDE = align32(3 * SBN);
+  // with grad, after B1: adjoint coefficients of the winner, 9 planes [TBN] (A, B, C per channel)
+  static constexpr int O_COEF = O_SRC;
+  static constexpr int SRC_FLOATS = (SRC_STRIDE + 3 * SBN > 9 * TBN) ? SRC_STRIDE + 3 * SBN : 9 * TBN;
+  static constexpr int O_K = align32(O_SRC + SRC_FLOATS);        // winner bytes [TBN]
+  static constexpr int O_MBAR = O_K + align32((TBN + 3) / 4);    // one 8-byte mbarrier
+  static constexpr size_t SMEM_BYTES = (size_t)(O_MBAR + 4) * sizeof(float);
+  static constexpr unsigned TMA_BYTES = (unsigned)((3 * TBN + TBN + 2 * 3 * SBN) * sizeof(float));
+  // The B1/B2 strip walk always reads CDP_STRIP + 2 rows, also for the last, partial strip: the
+  // rows past the box belong to the following plane (values discarded); in the source boxes they
+  // must stay inside the margin rows.
+  static constexpr int LAST_ROW = NSTRIP * CDP_STRIP + OFFY + 1;  // last box row a strip walk reads
+  static_assert(LAST_ROW + SBM <= SBH - 1, "strip over-read leaves the source box: pick CDP_TILE_Y / CDP_STRIP so that it fits");
+  static_assert((LAST_ROW + 1) * TBW <= 2 * TBN, "strip over-read leaves the shared-memory allocation");
+  static_assert(SBM % 4 == 0 && TXO % 4 == 0 && TBW % 4 == 0 && SBW % 4 == 0 && CDP_TILE_X % 4 == 0,
+                "TMA boxes must start and end at multiples of 16 bytes");
+  static_assert(TXO >= 2 && TYO >= 2, "the window sums of the gradient instantiation need two pixels around the tile");
 };
 
 struct CdpTileCtx {
@@ -95,99 +118,207 @@ CDP_HD void cdp_k_table_entry(const CdpKTableParams& p, int s, int b_local) {
   }
 }
 
-// Per-tile, per-channel constant subtracted from every staged image value (target value at the
-// tile centre).  SSIM variances / covariances, the L1 term and all value differences are
-// invariant to it; it only shrinks the magnitudes that get squared.
-CDP_HD void cdp_tile_centre(const CdpLevel& lv, const CdpTileCtx& c, float centre[3]) {
-  const int cx = c.x0 + CDP_TILE_X / 2 < lv.W ? c.x0 + CDP_TILE_X / 2 : lv.W - 1;
-  const int cy = c.y0 + CDP_TILE_Y / 2 < lv.H ? c.y0 + CDP_TILE_Y / 2 : lv.H - 1;
-  const size_t plane = (size_t)lv.W * lv.H;
+// Per-tile, per-channel constant (target value at the tile centre, read from the staged box) on
+// which the SSIM adjoint coefficients and the values they multiply are centred in phases B2 / C:
+// the three terms A + 2 x B + y C cancel almost completely, and the cancellation costs fewer
+// digits the smaller |x|, |y| are.
+template <bool G>
+CDP_HD void cdp_tile_centre(const CdpLevel& lv, const CdpTileCtx& c, const float* sm, float centre[3]) {
+  typedef CdpTileGeom<G> Geo;
+  const int cx = c.x0 + CDP_TILE_X / 2 < lv.W ? CDP_TILE_X / 2 : lv.W - 1 - c.x0;
+  const int cy = c.y0 + CDP_TILE_Y / 2 < lv.H ? CDP_TILE_Y / 2 : lv.H - 1 - c.y0;
+  const int ti = (cy + Geo::TYO) * Geo::TBW + cx + Geo::TXO;
 #pragma unroll
-  for (int ch = 0; ch < 3; ++ch) centre[ch] = CDP_LDG(lv.tgt + ((size_t)c.b * 3 + ch) * plane + cy * lv.W + cx);
+  for (int ch = 0; ch < 3; ++ch) centre[ch] = sm[Geo::O_TGT + ch * Geo::TBN + ti];
 }
 
 template <bool G>
-CDP_HD float2* cdp_pair_plane(float* sm, int first_plane, int ch) {
-  return reinterpret_cast<float2*>(sm + (size_t)(first_plane + 2 * ch) * CdpTileGeom<G>::RN);
+CDP_HD float2* cdp_warp_plane(float* sm, int ch) {
+  return reinterpret_cast<float2*>(sm + CdpTileGeom<G>::O_WARP + 2 * ch * CdpTileGeom<G>::TBN);
 }
 template <bool G>
-CDP_HD const float2* cdp_pair_plane(const float* sm, int first_plane, int ch) {
-  return reinterpret_cast<const float2*>(sm + (size_t)(first_plane + 2 * ch) * CdpTileGeom<G>::RN);
+CDP_HD const float2* cdp_warp_plane(const float* sm, int ch) {
+  return reinterpret_cast<const float2*>(sm + CdpTileGeom<G>::O_WARP + 2 * ch * CdpTileGeom<G>::TBN);
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase S without TMA: fill the boxes with plain loads, zeros outside the image (what the TMA
+// box loads do in hardware).
+// ------------------------------------------------------------------------------------------
+CDP_HD void cdp_stage_box(const float* g, size_t plane, int nplanes, float* dst, int bw, int bh, int ox, int oy,
+                          int W, int H, int tid, int nthreads) {
+  const int bn = bw * bh;
+#pragma unroll 1
+  for (int e = tid; e < nplanes * bn; e += nthreads) {
+    const int pl = e / bn, r = e - pl * bn;
+    const int ty = r / bw, tx = r - ty * bw;
+    const int x = ox + tx, y = oy + ty;
+    dst[e] = (x >= 0 && x < W && y >= 0 && y < H) ? CDP_LDG(g + pl * plane + (size_t)y * W + x) : 0.f;
+  }
+}
+
+template <bool G>
+CDP_HD void cdp_photo_stage(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm) {
+  typedef CdpTileGeom<G> Geo;
+  const CdpLevel& lv = p.lv[c.lvl];
+  const size_t plane = (size_t)lv.W * lv.H;
+  const int ox = c.x0 - Geo::TXO, oy = c.y0 - Geo::TYO;
+  cdp_stage_box(lv.tgt + (size_t)c.b * 3 * plane, plane, 3, sm + Geo::O_TGT, Geo::TBW, Geo::TBH, ox, oy, lv.W, lv.H,
+                tid, nthreads);
+  cdp_stage_box(lv.depth + (size_t)c.b * plane, plane, 1, sm + Geo::O_DEPTH, Geo::TBW, Geo::TBH, ox, oy, lv.W, lv.H,
+                tid, nthreads);
+  cdp_stage_box(lv.src0 + (size_t)c.b * 3 * plane, plane, 3, sm + Geo::O_SRC, Geo::SBW, Geo::SBH, ox - Geo::SBM,
+                oy - Geo::SBM, lv.W, lv.H, tid, nthreads);
+  cdp_stage_box(lv.src1 + (size_t)c.b * 3 * plane, plane, 3, sm + Geo::O_SRC + Geo::SRC_STRIDE, Geo::SBW, Geo::SBH,
+                ox - Geo::SBM, oy - Geo::SBM, lv.W, lv.H, tid, nthreads);
 }
 
 // ------------------------------------------------------------------------------------------
 // Phase A
 // ------------------------------------------------------------------------------------------
+// nn.ReflectionPad2d(1) of a staged box: the ring one pixel outside the image takes the value of
+// its mirror pixel (-1 <- 1, n <- n-2); sources are interior pixels, so no element is both read
+// and written.  bn = plane stride of the box stack.
+CDP_HD void cdp_reflect_ring(float* box, int nplanes, int bn, int bw, int bh, int ox, int oy, int W, int H, int tid,
+                             int nthreads) {
+#pragma unroll 1
+  for (int e = tid; e < 2 * bw; e += nthreads) {  // rows -1 and H (corners included)
+    const int far = e >= bw ? 1 : 0, tx = e - far * bw;
+    const int y = far ? H : -1, ty = y - oy, x = ox + tx;
+    if (ty < 0 || ty >= bh || x < -1 || x > W) continue;
+    const int s = (cdp_reflect(y, H) - oy) * bw + cdp_reflect(x, W) - ox;
+#pragma unroll 1
+    for (int pl = 0; pl < nplanes; ++pl) box[pl * bn + ty * bw + tx] = box[pl * bn + s];
+  }
+#pragma unroll 1
+  for (int e = tid; e < 2 * bh; e += nthreads) {  // columns -1 and W, image rows only
+    const int far = e >= bh ? 1 : 0, ty = e - far * bh;
+    const int x = far ? W : -1, tx = x - ox, y = oy + ty;
+    if (tx < 0 || tx >= bw || y < 0 || y > H - 1) continue;
+    const int s = ty * bw + cdp_reflect(x, W) - ox;
+#pragma unroll 1
+    for (int pl = 0; pl < nplanes; ++pl) box[pl * bn + ty * bw + tx] = box[pl * bn + s];
+  }
+}
+
+// One source's literal-formula warp (depth clamp active or Q_w <= 0) written into lane k of w.
+CDP_HD void cdp_warp_lane_literal(int k, float u, float v, float depth, const CdpCam& cam, const CdpPose2& T,
+                                  const float2* mo, CdpWarp2& w) {
+  CdpPose Tk;
+  cdp_unpack_pose(T, k, Tk);
+  float mk[3];
+  if (mo) { mk[0] = k ? mo[0].y : mo[0].x; mk[1] = k ? mo[1].y : mo[1].x; mk[2] = k ? mo[2].y : mo[2].x; }
+  CdpWarp ws;
+  cdp_warp_point(u, v, depth, cam, Tk, mo ? mk : nullptr, ws);
+  if (k == 0) { w.dx.x = ws.dx; w.dy.x = ws.dy; w.ix.x = ws.ix; w.iy.x = ws.iy; }
+  else { w.dx.y = ws.dx; w.dy.y = ws.dy; w.ix.y = ws.ix; w.iy.y = ws.iy; }
+}
+
+// bilinear blend of (source 0, source 1) tap pairs with per-lane fractions
+CDP_HD float2 cdp_lerp2(float2 nw, float2 ne, float2 sw, float2 se, float2 fx, float2 fy) {
+  const float2 neg1 = cdp_set2(-1.0f);
+  const float2 top = cdp_fma2(fx, cdp_fma2(nw, neg1, ne), nw);
+  const float2 bot = cdp_fma2(fx, cdp_fma2(sw, neg1, se), sw);
+  return cdp_fma2(fy, cdp_fma2(top, neg1, bot), top);
+}
+
 template <bool G, bool M>
 CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm) {
   typedef CdpTileGeom<G> Geo;
   const CdpLevel& lv = p.lv[c.lvl];
   const int W = lv.W, H = lv.H;
   const size_t plane = (size_t)W * H;
+  // 1. reflected ring of the target and source boxes (read by the window sums of B1 / B2)
+  const int ox = c.x0 - Geo::TXO, oy = c.y0 - Geo::TYO;  // image position of box element (0, 0)
+  if (c.x0 == 0 || c.y0 == 0 || ox + Geo::TBW > W || oy + Geo::TBH > H) {
+    cdp_reflect_ring(sm + Geo::O_TGT, 3, Geo::TBN, Geo::TBW, Geo::TBH, ox, oy, W, H, tid, nthreads);
+    cdp_reflect_ring(sm + Geo::O_SRC, 3, Geo::SBN, Geo::SBW, Geo::SBH, ox - Geo::SBM, oy - Geo::SBM, W, H, tid, nthreads);
+    cdp_reflect_ring(sm + Geo::O_SRC + Geo::SRC_STRIDE, 3, Geo::SBN, Geo::SBW, Geo::SBH, ox - Geo::SBM, oy - Geo::SBM,
+                     W, H, tid, nthreads);
+  }
+  // 2. warp + gather
   const CdpCam cam = cdp_tile_cam(p, c);
-  CdpPose T[2];
-  cdp_load_pose_aligned(p.pose0 + (size_t)c.b * 16, T[0]);  // cdp_photo_fwd requires 16-byte aligned poses
-  cdp_load_pose_aligned(p.pose1 + (size_t)c.b * 16, T[1]);
-  float centre[3];
-  cdp_tile_centre(lv, c, centre);
+  CdpPose2 T;
+  {
+    CdpPose t0, t1;
+    cdp_load_pose_aligned(p.pose0 + (size_t)c.b * 16, t0);  // cdp_photo_fwd requires 16-byte aligned poses
+    cdp_load_pose_aligned(p.pose1 + (size_t)c.b * 16, t1);
+    cdp_pack_pose(t0, t1, T);
+  }
   const float* src0 = lv.src0 + (size_t)c.b * 3 * plane;
   const float* src1 = lv.src1 + (size_t)c.b * 3 * plane;
-  const float* tgt = lv.tgt + (size_t)c.b * 3 * plane;
-#if CDP_OPT_PREFETCH_DEPTH
-  // the depth of the next region pixel is requested one iteration ahead: the loop body has two
-  // dependent global-memory round trips (depth -> sample position -> source taps) otherwise
-  float depth_next = 0.f;
-  {
-    const int ry = tid / Geo::RW, rx = tid - ry * Geo::RW;
-    const int px = c.x0 - Geo::HALO + rx, py = c.y0 - Geo::HALO + ry;
-    if (tid < Geo::RN && !(px < -1 || px > W || py < -1 || py > H))
-      depth_next = CDP_LDG(lv.depth + (size_t)c.b * plane + cdp_reflect(py, H) * W + cdp_reflect(px, W));
-  }
-#endif
+  const float* sdepth = sm + Geo::O_DEPTH;
+  const float* sbox0 = sm + Geo::O_SRC;
+  const float* sbox1 = sm + Geo::O_SRC + Geo::SRC_STRIDE;
+  const int box_x = ox - Geo::SBM, box_y = oy - Geo::SBM;  // image position of source box element (0, 0)
   for (int idx = tid; idx < Geo::RN; idx += nthreads) {
     const int ry = idx / Geo::RW, rx = idx - ry * Geo::RW;
-    const int px = c.x0 - Geo::HALO + rx, py = c.y0 - Geo::HALO + ry;
-#if CDP_OPT_PREFETCH_DEPTH
-    const float depth = depth_next;
-    {
-      const int nidx = idx + nthreads;
-      const int nry = nidx / Geo::RW, nrx = nidx - nry * Geo::RW;
-      const int npx = c.x0 - Geo::HALO + nrx, npy = c.y0 - Geo::HALO + nry;
-      if (nidx < Geo::RN && !(npx < -1 || npx > W || npy < -1 || npy > H))
-        depth_next = CDP_LDG(lv.depth + (size_t)c.b * plane + cdp_reflect(npy, H) * W + cdp_reflect(npx, W));
-    }
-#endif
+    const int tx = rx + Geo::OFFX, ty = ry + Geo::OFFY;
+    const int px = ox + tx, py = oy + ty;
     if (px < -1 || px > W || py < -1 || py > H) continue;  // never read
     const int u = cdp_reflect(px, W), v = cdp_reflect(py, H);
-    const int pix = v * W + u;
-#if !CDP_OPT_PREFETCH_DEPTH
-    const float depth = CDP_LDG(lv.depth + (size_t)c.b * plane + pix);
-#endif
-    float m0[3], m1[3];
+    const float depth = sdepth[(v - oy) * Geo::TBW + u - ox];
+    float2 mo[3];
     if (M) {  // object-motion maps (make_sflow): added to the transformed point
+      const int pix = v * W + u;
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        m0[ch] = CDP_LDG(lv.mot0 + ((size_t)c.b * 3 + ch) * plane + pix);
-        m1[ch] = CDP_LDG(lv.mot1 + ((size_t)c.b * 3 + ch) * plane + pix);
+        mo[ch].x = CDP_LDG(lv.mot0 + ((size_t)c.b * 3 + ch) * plane + pix);
+        mo[ch].y = CDP_LDG(lv.mot1 + ((size_t)c.b * 3 + ch) * plane + pix);
       }
     }
-    CdpWarp w0, w1;
-    cdp_warp_point((float)u, (float)v, depth, cam, T[0], M ? m0 : nullptr, w0);
-    cdp_warp_point((float)u, (float)v, depth, cam, T[1], M ? m1 : nullptr, w1);
-    CdpTaps t0, t1;
-    cdp_taps(u, v, w0, W, H, t0);
-    cdp_taps(u, v, w1, W, H, t1);
+    CdpWarp2 w;
+    cdp_warp_point2((float)u, (float)v, depth, cam, T, M ? mo : nullptr, w);
+    if (!(w.regular[0] && w.regular[1])) {  // depth clamp active or Q_w <= 0: literal formula, per source
+      if (!w.regular[0]) cdp_warp_lane_literal(0, (float)u, (float)v, depth, cam, T, M ? mo : nullptr, w);
+      if (!w.regular[1]) cdp_warp_lane_literal(1, (float)u, (float)v, depth, cam, T, M ? mo : nullptr, w);
+    }
+    int ax0, ay0, ax1, ay1;
+    float2 fx, fy;
+    float unused;
+    cdp_tap_axis_full(u, w.dx.x, w.ix.x, W, ax0, fx.x, unused);
+    cdp_tap_axis_full(v, w.dy.x, w.iy.x, H, ay0, fy.x, unused);
+    cdp_tap_axis_full(u, w.dx.y, w.ix.y, W, ax1, fx.y, unused);
+    cdp_tap_axis_full(v, w.dy.y, w.iy.y, H, ay1, fy.y, unused);
+    const int bx0 = ax0 - box_x, by0 = ay0 - box_y, bx1 = ax1 - box_x, by1 = ay1 - box_y;
+    const bool in0 = (unsigned)bx0 <= (unsigned)(Geo::SBW - 2) && (unsigned)by0 <= (unsigned)(Geo::SBH - 2);
+    const bool in1 = (unsigned)bx1 <= (unsigned)(Geo::SBW - 2) && (unsigned)by1 <= (unsigned)(Geo::SBH - 2);
+    const int ti = ty * Geo::TBW + tx;
+    if (in0 && in1) {
+      // both 2x2 footprints lie inside the staged source boxes: 24 shared-memory loads at
+      // immediate offsets from two addresses
+      const float* q0 = sbox0 + by0 * Geo::SBW + bx0;
+      const float* q1 = sbox1 + by1 * Geo::SBW + bx1;
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      const float cc = centre[ch];
-      sm[(Geo::P_TGT + ch) * Geo::RN + idx] = CDP_LDG(tgt + ch * plane + pix) - cc;
-      float2 s, wv;
-      s.x = CDP_LDG(src0 + ch * plane + pix) - cc;
-      s.y = CDP_LDG(src1 + ch * plane + pix) - cc;
-      wv.x = cdp_bilinear(src0 + ch * plane, t0) - cc;
-      wv.y = cdp_bilinear(src1 + ch * plane, t1) - cc;
-      cdp_pair_plane<G>(sm, Geo::P_SRC, ch)[idx] = s;
-      cdp_pair_plane<G>(sm, Geo::P_WARP, ch)[idx] = wv;
+      for (int ch = 0; ch < 3; ++ch) {
+        float2 nw, ne, sw, se;
+        nw.x = q0[ch * Geo::SBN]; ne.x = q0[ch * Geo::SBN + 1];
+        sw.x = q0[ch * Geo::SBN + Geo::SBW]; se.x = q0[ch * Geo::SBN + Geo::SBW + 1];
+        nw.y = q1[ch * Geo::SBN]; ne.y = q1[ch * Geo::SBN + 1];
+        sw.y = q1[ch * Geo::SBN + Geo::SBW]; se.y = q1[ch * Geo::SBN + Geo::SBW + 1];
+        cdp_warp_plane<G>(sm, ch)[ti] = cdp_lerp2(nw, ne, sw, se, fx, fy);
+      }
+    } else {
+      // a footprint leaves the gather margin: global loads for that source (rolled: cold path)
+#pragma unroll 1
+      for (int ch = 0; ch < 3; ++ch) {
+        float2 nw, ne, sw, se;
+        if (in0) {
+          const float* q = sbox0 + ch * Geo::SBN + by0 * Geo::SBW + bx0;
+          nw.x = q[0]; ne.x = q[1]; sw.x = q[Geo::SBW]; se.x = q[Geo::SBW + 1];
+        } else {
+          const float* g = src0 + ch * plane + (size_t)ay0 * W + ax0;
+          nw.x = CDP_LDG(g); ne.x = CDP_LDG(g + 1); sw.x = CDP_LDG(g + W); se.x = CDP_LDG(g + W + 1);
+        }
+        if (in1) {
+          const float* q = sbox1 + ch * Geo::SBN + by1 * Geo::SBW + bx1;
+          nw.y = q[0]; ne.y = q[1]; sw.y = q[Geo::SBW]; se.y = q[Geo::SBW + 1];
+        } else {
+          const float* g = src1 + ch * plane + (size_t)ay1 * W + ax1;
+          nw.y = CDP_LDG(g); ne.y = CDP_LDG(g + 1); sw.y = CDP_LDG(g + W); se.y = CDP_LDG(g + W + 1);
+        }
+        cdp_warp_plane<G>(sm, ch)[ti] = cdp_lerp2(nw, ne, sw, se, fx, fy);
+      }
     }
   }
 }
@@ -249,9 +380,7 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
   typedef CdpTileGeom<G> Geo;
   const CdpLevel& lv = p.lv[c.lvl];
   const int W = lv.W, H = lv.H;
-  uint8_t* kplane = reinterpret_cast<uint8_t*>(sm + (size_t)Geo::NPLANES * Geo::RN);
-  float centre[3];
-  cdp_tile_centre(lv, c, centre);
+  uint8_t* kplane = reinterpret_cast<uint8_t*>(sm + Geo::O_K);
   // (computed per thread on purpose: reading them from the parameter bank instead measured 1.7 % slower)
   const float a3 = p.alpha * (1.0f / 3.0f), b3 = (float)(1.0 - (double)p.alpha) * (1.0f / 3.0f);
   for (int item = tid; item < Geo::NITEMS; item += nthreads) {
@@ -259,8 +388,9 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
     const int by0 = strip * CDP_STRIP;
     const int qx = c.x0 - Geo::HB + bx;
     const int qy0 = c.y0 - Geo::HB + by0;
-    // region index of the window centre of output row 0 of this strip
-    const int r00 = (by0 + 1) * Geo::RW + bx + 1;
+    // t-index / s-index of the window centre of output row 0 of this strip
+    const int r00 = (by0 + 1 + Geo::OFFY) * Geo::TBW + bx + 1 + Geo::OFFX;
+    const int s00 = (by0 + 1 + Geo::OFFY + Geo::SBM) * Geo::SBW + bx + 1 + Geo::OFFX + Geo::SBM;
     float2 acc_id[CDP_STRIP], acc_pe[CDP_STRIP];
 #pragma unroll
     for (int o = 0; o < CDP_STRIP; ++o) { acc_id[o] = cdp_set2(0.f); acc_pe[o] = cdp_set2(0.f); }
@@ -278,19 +408,19 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
       }
     }
     const int qc = qy0 + CDP_STRIP / 2 < 0 ? 0 : (qy0 + CDP_STRIP / 2 > H - 1 ? H - 1 : qy0 + CDP_STRIP / 2);
-    const int cs_idx = (qc - c.y0 + Geo::HALO) * Geo::RW + bx + 1;
+    const int cs_idx = (qc - c.y0 + Geo::TYO) * Geo::TBW + bx + 1 + Geo::OFFX;
     if (col_ok && qy0 < H && qy0 + CDP_STRIP > 0) {
       // the channel loop stays rolled: unrolled, this phase alone is ~60 KB of SASS that every
       // warp streams through once per tile, and instruction fetch becomes the top stall reason
 #pragma unroll 1
       for (int ch = 0; ch < 3; ++ch) {
-        const float* ty = sm + (size_t)(Geo::P_TGT + ch) * Geo::RN;
-        const float2* ts = cdp_pair_plane<G>(sm, Geo::P_SRC, ch);
-        const float2* tw = cdp_pair_plane<G>(sm, Geo::P_WARP, ch);
-        // strip constant: target value at the strip's middle pixel (already tile-centred),
-        // clamped into the image so that it is always a staged value
+        const float* ty = sm + Geo::O_TGT + ch * Geo::TBN;
+        const float* ts0 = sm + Geo::O_SRC + ch * Geo::SBN;
+        const float* ts1 = ts0 + Geo::SRC_STRIDE;
+        const float2* tw = cdp_warp_plane<G>(sm, ch);
+        // strip constant: target value at the strip's middle pixel, clamped into the image so
+        // that it is always a staged value; every window value is centred on it
         const float cs = ty[cs_idx];
-        const float ct = cs + centre[ch];
         const float2 cs2 = cdp_set2(-cs);
         CdpRowTgt hy[3];
         CdpRowPair hs[3], hw[3];
@@ -298,13 +428,16 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
         float2 sc_prev = cdp_set2(0.f), wc_prev = cdp_set2(0.f);
 #pragma unroll
         for (int r = 0; r < CDP_STRIP + 2; ++r) {
-          const int row = r00 + (r - 1) * Geo::RW;  // window row r-1 relative to output row 0
+          const int row = r00 + (r - 1) * Geo::TBW;  // window row r-1 relative to output row 0
+          const int srow = s00 + (r - 1) * Geo::SBW;
           float y[3];
           float2 s[3], w[3];
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
             y[t] = ty[row + t - 1] - cs;
-            s[t] = cdp_add2(ts[row + t - 1], cs2);
+            float2 sv;
+            sv.x = ts0[srow + t - 1]; sv.y = ts1[srow + t - 1];
+            s[t] = cdp_add2(sv, cs2);
             w[t] = cdp_add2(tw[row + t - 1], cs2);
           }
           cdp_row_tgt(y, hy[r % 3]);
@@ -315,10 +448,10 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
             const float sy = hy[0].s + hy[1].s + hy[2].s, syy = hy[0].ss + hy[1].ss + hy[2].ss;
             const float2 l_id = cdp_ssim_pair_loss(cdp_add2(cdp_add2(hs[0].s, hs[1].s), hs[2].s),
                                                    cdp_add2(cdp_add2(hs[0].ss, hs[1].ss), hs[2].ss),
-                                                   cdp_add2(cdp_add2(hs[0].sy, hs[1].sy), hs[2].sy), sy, syy, ct);
+                                                   cdp_add2(cdp_add2(hs[0].sy, hs[1].sy), hs[2].sy), sy, syy, cs);
             const float2 l_pe = cdp_ssim_pair_loss(cdp_add2(cdp_add2(hw[0].s, hw[1].s), hw[2].s),
                                                    cdp_add2(cdp_add2(hw[0].ss, hw[1].ss), hw[2].ss),
-                                                   cdp_add2(cdp_add2(hw[0].sy, hw[1].sy), hw[2].sy), sy, syy, ct);
+                                                   cdp_add2(cdp_add2(hw[0].sy, hw[1].sy), hw[2].sy), sy, syy, cs);
             float2 d_id = cdp_add2(sc_prev, cdp_set2(-yc_prev)), d_pe = cdp_add2(wc_prev, cdp_set2(-yc_prev));
             d_id.x = fabsf(d_id.x); d_id.y = fabsf(d_id.y);
             d_pe.x = fabsf(d_pe.x); d_pe.y = fabsf(d_pe.y);
@@ -335,7 +468,7 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
       const int by = by0 + o;
       if (by >= Geo::BH) break;
       const int qy = qy0 + o;
-      const int ridx = r00 + o * Geo::RW;
+      const int ridx = r00 + o * Geo::TBW;
       if (!col_ok || qy < 0 || qy >= H) {
         if (G) kplane[ridx] = 255;
         continue;
@@ -365,36 +498,36 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
 CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm) {
   typedef CdpTileGeom<true> Geo;
   const CdpLevel& lv = p.lv[c.lvl];
-  const uint8_t* kplane = reinterpret_cast<const uint8_t*>(sm + (size_t)Geo::NPLANES * Geo::RN);
+  const uint8_t* kplane = reinterpret_cast<const uint8_t*>(sm + Geo::O_K);
   float centre[3];
-  cdp_tile_centre(lv, c, centre);
+  cdp_tile_centre<true>(lv, c, sm, centre);
   for (int item = tid; item < Geo::NITEMS; item += nthreads) {
     const int strip = item / Geo::BW, bx = item - strip * Geo::BW;
     const int by0 = strip * CDP_STRIP;
-    const int r00 = (by0 + 1) * Geo::RW + bx + 1;
+    const int r00 = (by0 + 1 + Geo::OFFY) * Geo::TBW + bx + 1 + Geo::OFFX;
     int kk[CDP_STRIP];
     bool any = false;
 #pragma unroll
     for (int o = 0; o < CDP_STRIP; ++o) {
-      kk[o] = (by0 + o < Geo::BH) ? kplane[r00 + o * Geo::RW] : 255;
+      kk[o] = (by0 + o < Geo::BH) ? kplane[r00 + o * Geo::TBW] : 255;
       any = any || kk[o] < 2;
     }
     if (!any) continue;  // every pixel of the strip is auto-masked or outside the image
     const int qy0 = c.y0 - Geo::HB + by0;
     const int qc = qy0 + CDP_STRIP / 2 < 0 ? 0 : (qy0 + CDP_STRIP / 2 > lv.H - 1 ? lv.H - 1 : qy0 + CDP_STRIP / 2);
-    const int cs_idx = (qc - c.y0 + Geo::HALO) * Geo::RW + bx + 1;
+    const int cs_idx = (qc - c.y0 + Geo::TYO) * Geo::TBW + bx + 1 + Geo::OFFX;
 #pragma unroll 1
     for (int ch = 0; ch < 3; ++ch) {
-      const float* ty = sm + (size_t)(Geo::P_TGT + ch) * Geo::RN;
-      const float2* tw = cdp_pair_plane<true>(sm, Geo::P_WARP, ch);
+      const float* ty = sm + Geo::O_TGT + ch * Geo::TBN;
+      const float2* tw = cdp_warp_plane<true>(sm, ch);
       const float cs = ty[cs_idx];
-      const float ct = cs + centre[ch];
+      const float csc = cs - centre[ch];  // strip constant in the tile-centred frame
       const float2 cs2 = cdp_set2(-cs);
       CdpRowTgt hy[3];
       CdpRowPair hw[3];
 #pragma unroll
       for (int r = 0; r < CDP_STRIP + 2; ++r) {
-        const int row = r00 + (r - 1) * Geo::RW;
+        const int row = r00 + (r - 1) * Geo::TBW;
         float y[3];
         float2 w[3];
 #pragma unroll
@@ -418,24 +551,14 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
             const float myc = (hy[0].s + hy[1].s + hy[2].s) * ninth;
             const float eyy = (hy[0].ss + hy[1].ss + hy[2].ss) * ninth;
             CdpSsimTerms t;
-            cdp_ssim_terms(mxc, myc, exx, eyy, exy, ct, t);
+            cdp_ssim_terms(mxc, myc, exx, eyy, exy, cs, t);
             float A, B, C;
-            // means in the tile-centred frame are mxc + cs, myc + cs
-            cdp_ssim_coeffs_abc(t, mxc + cs, myc + cs, A, B, C);
-            // packed layout: see CdpTileGeom::P_COEF
-#if CDP_OPT_PACKED_GATHER
-            float* cf = sm + (size_t)Geo::P_COEF * Geo::RN + 2 * (r00 + o * Geo::RW);
-            if (ch < 2) {
-              cf[0 * 2 * Geo::RN + ch] = A; cf[1 * 2 * Geo::RN + ch] = B; cf[2 * 2 * Geo::RN + ch] = C;
-            } else {
-              cf[3 * 2 * Geo::RN + 0] = A; cf[3 * 2 * Geo::RN + 1] = B; cf[4 * 2 * Geo::RN + 0] = C;
-            }
-#else
-            const int ridx = r00 + o * Geo::RW;
-            sm[(size_t)(Geo::P_COEF + ch * 3 + 0) * Geo::RN + ridx] = A;
-            sm[(size_t)(Geo::P_COEF + ch * 3 + 1) * Geo::RN + ridx] = B;
-            sm[(size_t)(Geo::P_COEF + ch * 3 + 2) * Geo::RN + ridx] = C;
-#endif
+            // means in the tile-centred frame are mxc + csc, myc + csc
+            cdp_ssim_coeffs_abc(t, mxc + csc, myc + csc, A, B, C);
+            const int ridx = r00 + o * Geo::TBW;
+            sm[Geo::O_COEF + (ch * 3 + 0) * Geo::TBN + ridx] = A;
+            sm[Geo::O_COEF + (ch * 3 + 1) * Geo::TBN + ridx] = B;
+            sm[Geo::O_COEF + (ch * 3 + 2) * Geo::TBN + ridx] = C;
           }
         }
       }
@@ -444,164 +567,197 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
 }
 
 // ------------------------------------------------------------------------------------------
-// Phase C (with grad)
+// Phase C (with grad): both sources in the two lanes of packed fp32.
 // ------------------------------------------------------------------------------------------
+// One source of one pixel through the literal (depth clamp active / Q_w <= 0) formulas: rare.
+// gw[ch] = dL/d warped value of this source; adds to lane k of dT2, returns dL/d depth.
+template <bool M>
+CDP_HD float cdp_phase_c_lane_literal(int k, const CdpPhotoParams& p, const CdpLevel& lv, const CdpTileCtx& c, int px,
+                                      int py, float depth, const CdpCam& cam, const float gw[3], float2* dT2) {
+  const int W = lv.W, H = lv.H;
+  const size_t plane = (size_t)W * H;
+  CdpPose T;
+  cdp_load_pose_aligned((k == 0 ? p.pose0 : p.pose1) + (size_t)c.b * 16, T);
+  const float* srck = (k == 0 ? lv.src0 : lv.src1) + (size_t)c.b * 3 * plane;
+  float mo[3], gmo[3];
+  if (M) {
+    const float* motk = k == 0 ? lv.mot0 : lv.mot1;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) mo[ch] = CDP_LDG(motk + ((size_t)c.b * 3 + ch) * plane + py * W + px);
+  }
+  CdpWarp w;
+  cdp_warp_point((float)px, (float)py, depth, cam, T, M ? mo : nullptr, w);
+  CdpTaps t;
+  cdp_taps(px, py, w, W, H, t);
+  float gix = 0.f, giy = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < 3; ++ch) {
+    float dix, diy;
+    cdp_bilinear_grad(srck + ch * plane, t, dix, diy);
+    gix += gw[ch] * dix;
+    giy += gw[ch] * diy;
+  }
+  float dTk[16], gd = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dTk[i] = 0.f;
+  cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dTk, M ? gmo : nullptr);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (k == 0) dT2[i].x += dTk[i]; else dT2[i].y += dTk[i];
+  }
+  if (M) {
+    float* dst = (k == 0 ? lv.gmot0 : lv.gmot1) + (size_t)c.b * 3 * plane + py * W + px;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) dst[ch * plane] = gmo[ch];
+  }
+  return gd;
+}
+
 template <bool M>
 CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads,
-                              const float* sm, float* dT /*[32]*/) {
+                              const float* sm, float* dT /*[32]: source-major 4x4 blocks*/) {
   typedef CdpTileGeom<true> Geo;
   const CdpLevel& lv = p.lv[c.lvl];
   const int W = lv.W, H = lv.H;
   const size_t plane = (size_t)W * H;
   const CdpCam cam = cdp_tile_cam(p, c);
-  const uint8_t* kplane = reinterpret_cast<const uint8_t*>(sm + (size_t)Geo::NPLANES * Geo::RN);
-  const float w_ssim = p.alpha / 27.0f;  // alpha * (1/3 channels) * (1/9 window)
-  const float w_l1 = (float)(1.0 - (double)p.alpha) * (1.0f / 3.0f);
+  CdpPose2 T;
+  {
+    CdpPose t0, t1;
+    cdp_load_pose_aligned(p.pose0 + (size_t)c.b * 16, t0);
+    cdp_load_pose_aligned(p.pose1 + (size_t)c.b * 16, t1);
+    cdp_pack_pose(t0, t1, T);
+  }
+  const uint8_t* kplane = reinterpret_cast<const uint8_t*>(sm + Geo::O_K);
+  float centre[3];
+  cdp_tile_centre<true>(lv, c, sm, centre);
+  const float w_ssim = p.alpha / 27.0f * lv.weight;  // alpha * (1/3 channels) * (1/9 window) * level weight
+  const float w_l1 = (float)(1.0 - (double)p.alpha) * (1.0f / 3.0f) * lv.weight;
+  const float* src0 = lv.src0 + (size_t)c.b * 3 * plane;
+  const float* src1 = lv.src1 + (size_t)c.b * 3 * plane;
+  float2 dT2[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dT2[i] = cdp_set2(0.f);
   for (int idx = tid; idx < CDP_TILE_X * CDP_TILE_Y; idx += nthreads) {
     const int ly = idx / CDP_TILE_X, lx = idx - ly * CDP_TILE_X;
     const int px = c.x0 + lx, py = c.y0 + ly;
     if (px >= W || py >= H) continue;
-    const int ridx = (ly + Geo::HALO) * Geo::RW + lx + Geo::HALO;
+    const int ridx = (ly + Geo::TYO) * Geo::TBW + lx + Geo::TXO;
     const int kown = kplane[ridx];
-    // winners and reflection multiplicities of the 3x3 neighbourhood
-    int kn[9];
-    float mn[9];
-    bool any0 = kown == 0, any1 = kown == 1;
+    // winners of the 3x3 neighbourhood as per-source weights (reflection multiplicity where the
+    // neighbour's window reaches this pixel and it picked that source, else 0)
+    float2 mk[9];
+    bool any = false;
     const bool interior = px >= 2 && px <= W - 3 && py >= 2 && py <= H - 3;
-    if (interior) {  // no reflection in reach: weights are 1
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        mn[j] = 1.f;
-        kn[j] = (int)kplane[ridx + (j / 3 - 1) * Geo::RW + (j % 3 - 1)];
-        any0 = any0 || kn[j] == 0;
-        any1 = any1 || kn[j] == 1;
-      }
-    } else {
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const float my = cdp_reflect_mult(py, dy, H);
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int j = (dy + 1) * 3 + dx + 1;
-          mn[j] = my * cdp_reflect_mult(px, dx, W);
-          kn[j] = mn[j] != 0.f ? (int)kplane[ridx + dy * Geo::RW + dx] : 255;
-          any0 = any0 || kn[j] == 0;
-          any1 = any1 || kn[j] == 1;
-        }
-      }
+    for (int j = 0; j < 9; ++j) {
+      const int dy = j / 3 - 1, dx = j % 3 - 1;
+      const float m = interior ? 1.f : cdp_reflect_mult(py, dy, H) * cdp_reflect_mult(px, dx, W);
+      const int kj = (int)kplane[ridx + dy * Geo::TBW + dx];  // (255 outside the image: matches neither)
+      mk[j].x = kj == 0 ? m : 0.f;
+      mk[j].y = kj == 1 ? m : 0.f;
+      any = any || (kj < 2 && m != 0.f);
     }
     float gd = 0.f;
-    if (M) {  // dL/d motion: zero unless the source contributes below
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        if (!any0) lv.gmot0[((size_t)c.b * 3 + ch) * plane + py * W + px] = 0.f;
-        if (!any1) lv.gmot1[((size_t)c.b * 3 + ch) * plane + py * W + px] = 0.f;
-      }
-    }
-    if (any0 || any1) {
-      const float depth = CDP_LDG(lv.depth + (size_t)c.b * plane + py * W + px);
-#pragma unroll 1
-      for (int k = 0; k < 2; ++k) {
-        if (!(k == 0 ? any0 : any1)) continue;
-#if CDP_OPT_PACKED_GATHER
-        // masked, reflection-weighted 3x3 sums of the packed coefficient planes
-        float2 acc[5];
-#pragma unroll
-        for (int f = 0; f < 5; ++f) acc[f] = cdp_set2(0.f);
-        const float2* cf = reinterpret_cast<const float2*>(sm + (size_t)Geo::P_COEF * Geo::RN);
-        if (interior) {
-#pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            if (kn[j] != k) continue;
-            const int n = ridx + (j / 3 - 1) * Geo::RW + (j % 3 - 1);
-#pragma unroll
-            for (int f = 0; f < 5; ++f) acc[f] = cdp_add2(acc[f], cf[(size_t)f * Geo::RN + n]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            if (kn[j] != k) continue;
-            const int n = ridx + (j / 3 - 1) * Geo::RW + (j % 3 - 1);
-            const float2 m2 = cdp_set2(mn[j]);
-#pragma unroll
-            for (int f = 0; f < 5; ++f) acc[f] = cdp_fma2(cf[(size_t)f * Geo::RN + n], m2, acc[f]);
-          }
-        }
-        const float sa[3] = {acc[0].x, acc[0].y, acc[3].x};
-        const float sb[3] = {acc[1].x, acc[1].y, acc[3].y};
-        const float sc[3] = {acc[2].x, acc[2].y, acc[4].x};
-#else
-        float sa[3] = {0.f, 0.f, 0.f}, sb[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-          if (kn[j] != k) continue;
-          const int n = ridx + (j / 3 - 1) * Geo::RW + (j % 3 - 1);
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            sa[ch] += mn[j] * sm[(size_t)(Geo::P_COEF + ch * 3 + 0) * Geo::RN + n];
-            sb[ch] += mn[j] * sm[(size_t)(Geo::P_COEF + ch * 3 + 1) * Geo::RN + n];
-            sc[ch] += mn[j] * sm[(size_t)(Geo::P_COEF + ch * 3 + 2) * Geo::RN + n];
-          }
-        }
-#endif
-        // (the source loop is rolled to keep the code small: no register arrays indexed by k)
-        CdpPose T;
-        cdp_load_pose_aligned((k == 0 ? p.pose0 : p.pose1) + (size_t)c.b * 16, T);
-        const float* srck = (k == 0 ? lv.src0 : lv.src1) + (size_t)c.b * 3 * plane;
-        float mo[3], gmo[3];
-        const float* motk = k == 0 ? lv.mot0 : lv.mot1;
-        if (M) {
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) mo[ch] = CDP_LDG(motk + ((size_t)c.b * 3 + ch) * plane + py * W + px);
-        }
-        CdpWarp w;
-        cdp_warp_point((float)px, (float)py, depth, cam, T, M ? mo : nullptr, w);
-        CdpTaps t;
-        cdp_taps(px, py, w, W, H, t);
-        float gix = 0.f, giy = 0.f;
+    if (!any) {  // every window that reaches this pixel is auto-masked: no gradient
+      if (M) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          const float2 xv = cdp_pair_plane<true>(sm, Geo::P_WARP, ch)[ridx];
-          const float x = k == 0 ? xv.x : xv.y;
-          const float y = sm[(size_t)(Geo::P_TGT + ch) * Geo::RN + ridx];
-          float gw = w_ssim * (sa[ch] + 2.f * x * sb[ch] + y * sc[ch]);
-          if (kown == k) gw += w_l1 * (x > y ? 1.f : (x < y ? -1.f : 0.f));
-          gw *= lv.weight;
-          float dix, diy;
-          cdp_bilinear_grad(srck + ch * plane, t, dix, diy);
-          gix += gw * dix;
-          giy += gw * diy;
+          lv.gmot0[((size_t)c.b * 3 + ch) * plane + py * W + px] = 0.f;
+          lv.gmot1[((size_t)c.b * 3 + ch) * plane + py * W + px] = 0.f;
         }
-#if CDP_OPT_DIRECT_DT
-        float* gmk = M ? gmo : nullptr;
-        if (k == 0) cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dT, gmk);
-        else cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dT + 16, gmk);
-        if (M) {
-          float* dst = (k == 0 ? lv.gmot0 : lv.gmot1) + (size_t)c.b * 3 * plane + py * W + px;
+      }
+      lv.gdepth[(size_t)c.b * plane + py * W + px] = 0.f;
+      continue;
+    }
+    const float depth = sm[Geo::O_DEPTH + ridx];
+    float2 mo[3];
+    if (M) {
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch) dst[ch * plane] = gmo[ch];
-        }
-#else
-        float dTk[16];
+      for (int ch = 0; ch < 3; ++ch) {
+        mo[ch].x = CDP_LDG(lv.mot0 + ((size_t)c.b * 3 + ch) * plane + py * W + px);
+        mo[ch].y = CDP_LDG(lv.mot1 + ((size_t)c.b * 3 + ch) * plane + py * W + px);
+      }
+    }
+    CdpWarp2 w;
+    cdp_warp_point2((float)px, (float)py, depth, cam, T, M ? mo : nullptr, w);
+    // bilinear taps of both sources, requested before the coefficient gather so that their
+    // latency (L2: the shared-memory carve-out leaves almost no L1) overlaps it
+    int ax0, ay0, ax1, ay1;
+    float2 fx, fy, mx, my;
+    cdp_tap_axis_full(px, w.dx.x, w.ix.x, W, ax0, fx.x, mx.x);
+    cdp_tap_axis_full(py, w.dy.x, w.iy.x, H, ay0, fy.x, my.x);
+    cdp_tap_axis_full(px, w.dx.y, w.ix.y, W, ax1, fx.y, mx.y);
+    cdp_tap_axis_full(py, w.dy.y, w.iy.y, H, ay1, fy.y, my.y);
+    const float* g0 = src0 + ay0 * W + ax0;
+    const float* g1 = src1 + ay1 * W + ax1;
+    float2 nw[3], ne[3], sw[3], se[3];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) dTk[i] = 0.f;
-        float* gmk = M ? gmo : nullptr;
-        cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dTk, gmk);
-        if (M) {
-          float* dst = (k == 0 ? lv.gmot0 : lv.gmot1) + (size_t)c.b * 3 * plane + py * W + px;
+    for (int ch = 0; ch < 3; ++ch) {
+      nw[ch].x = CDP_LDG(g0 + ch * plane); ne[ch].x = CDP_LDG(g0 + ch * plane + 1);
+      sw[ch].x = CDP_LDG(g0 + ch * plane + W); se[ch].x = CDP_LDG(g0 + ch * plane + W + 1);
+      nw[ch].y = CDP_LDG(g1 + ch * plane); ne[ch].y = CDP_LDG(g1 + ch * plane + 1);
+      sw[ch].y = CDP_LDG(g1 + ch * plane + W); se[ch].y = CDP_LDG(g1 + ch * plane + W + 1);
+    }
+    // masked, reflection-weighted 3x3 sums of the coefficient planes, both sources at once
+    float2 sa[3], sb[3], sc[3];
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch) dst[ch * plane] = gmo[ch];
-        }
-        if (k == 0) {
+    for (int ch = 0; ch < 3; ++ch) { sa[ch] = cdp_set2(0.f); sb[ch] = cdp_set2(0.f); sc[ch] = cdp_set2(0.f); }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dT[i] += dTk[i];
-        } else {
+    for (int j = 0; j < 9; ++j) {
+      const int n = ridx + (j / 3 - 1) * Geo::TBW + (j % 3 - 1);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dT[16 + i] += dTk[i];
-        }
-#endif
+      for (int ch = 0; ch < 3; ++ch) {
+        sa[ch] = cdp_fma2(mk[j], cdp_set2(sm[Geo::O_COEF + (ch * 3 + 0) * Geo::TBN + n]), sa[ch]);
+        sb[ch] = cdp_fma2(mk[j], cdp_set2(sm[Geo::O_COEF + (ch * 3 + 1) * Geo::TBN + n]), sb[ch]);
+        sc[ch] = cdp_fma2(mk[j], cdp_set2(sm[Geo::O_COEF + (ch * 3 + 2) * Geo::TBN + n]), sc[ch]);
+      }
+    }
+    // dL/d warped value per channel and source; chain through the sampler's coordinate derivative
+    float2 gw[3];
+    float2 gix = cdp_set2(0.f), giy = cdp_set2(0.f);
+    const float2 wy0 = cdp_fma2(fy, cdp_set2(-1.0f), cdp_set2(1.0f)), wx0 = cdp_fma2(fx, cdp_set2(-1.0f), cdp_set2(1.0f));
+    const float2 neg1 = cdp_set2(-1.0f);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float2 x = cdp_add2(cdp_warp_plane<true>(sm, ch)[ridx], cdp_set2(-centre[ch]));
+      const float y = sm[Geo::O_TGT + ch * Geo::TBN + ridx] - centre[ch];
+      float2 g = cdp_mul2(cdp_set2(w_ssim), cdp_fma2(cdp_mul2(x, cdp_set2(2.f)), sb[ch], cdp_fma2(cdp_set2(y), sc[ch], sa[ch])));
+      if (kown == 0) g.x += w_l1 * (x.x > y ? 1.f : (x.x < y ? -1.f : 0.f));
+      if (kown == 1) g.y += w_l1 * (x.y > y ? 1.f : (x.y < y ? -1.f : 0.f));
+      gw[ch] = g;
+      const float2 dix = cdp_fma2(cdp_fma2(nw[ch], neg1, ne[ch]), wy0, cdp_mul2(cdp_fma2(sw[ch], neg1, se[ch]), fy));
+      const float2 diy = cdp_fma2(cdp_fma2(nw[ch], neg1, sw[ch]), wx0, cdp_mul2(cdp_fma2(ne[ch], neg1, se[ch]), fx));
+      gix = cdp_fma2(g, dix, gix);
+      giy = cdp_fma2(g, diy, giy);
+    }
+    float2 gQ[3];
+    float2 gdep = cdp_warp_adjoint2(cdp_mul2(gix, mx), cdp_mul2(giy, my), w, cam, T, dT2, gQ);
+    if (!(w.regular[0] && w.regular[1])) {
+      // a lane with the depth clamp active contributed exactly zero above (iz = 0): redo that
+      // source with the literal formulas
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (w.regular[k]) continue;
+        float gwk[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) gwk[ch] = k == 0 ? gw[ch].x : gw[ch].y;
+        const float lit = cdp_phase_c_lane_literal<M>(k, p, lv, c, px, py, depth, cam, gwk, dT2);
+        if (k == 0) gdep.x = lit; else gdep.y = lit;
+      }
+    }
+    gd = gdep.x + gdep.y;
+    if (M) {
+      float* d0 = lv.gmot0 + (size_t)c.b * 3 * plane + py * W + px;
+      float* d1 = lv.gmot1 + (size_t)c.b * 3 * plane + py * W + px;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        if (w.regular[0]) d0[ch * plane] = gQ[ch].x;
+        if (w.regular[1]) d1[ch * plane] = gQ[ch].y;
       }
     }
     lv.gdepth[(size_t)c.b * plane + py * W + px] = gd;
   }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { dT[i] += dT2[i].x; dT[16 + i] += dT2[i].y; }
 }

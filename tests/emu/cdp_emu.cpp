@@ -40,6 +40,8 @@ static void emu_photo_block(const CdpPhotoParams& kp, int bx, int by) {
   std::vector<float> sm(Geo::SMEM_BYTES / sizeof(float) + 4, 0.f);
   const CdpTileCtx c = cdp_tile_ctx(kp, bx, by);
   std::vector<float> v((size_t)nt * 33, 0.f);
+  // phase S: the box fill the GPU does with TMA (zero fill outside the image), here with plain loads
+  for (int t = 0; t < nt; ++t) cdp_photo_stage<G>(kp, c, t, nt, sm.data());
   for (int t = 0; t < nt; ++t) cdp_photo_phase_a<G, M>(kp, c, t, nt, sm.data());
   for (int t = 0; t < nt; ++t) cdp_photo_phase_b1<G>(kp, c, t, nt, sm.data(), v[(size_t)t * 33]);
   if (G) {

@@ -154,9 +154,22 @@ def ssim_clamp_shadow(clamp_margin, height, width, eps=2e-5):
     return _spread_to_full_res([(m < eps).cpu() for m in clamp_margin], height, width, window=True)
 
 
+def near_tie_shadow(candidates, height, width, gap=TIE_GAP):
+    """[B,H,W] mask of the depth pixels inside the SSIM window of a level pixel whose two best
+    candidates are closer than ``gap`` in fp64: which of them wins is undecidable in fp32, and a
+    tile that recomputes such a pixel in its halo (with other centring constants, i.e. other
+    rounding) may pick the other one than the tile that owns it."""
+    masks = []
+    for c in candidates:
+        top2 = torch.sort(c, dim=1).values[:, :2]
+        masks.append(((top2[:, 1] - top2[:, 0]) < gap).cpu())
+    return _spread_to_full_res(masks, height, width, window=True)
+
+
 def unstable_depth_mask(ref, got_argmin, height, width):
     """Union of the masks above, from an fp64 oracle result ``ref`` (loss_and_grads)."""
-    return (tie_shadow(got_argmin, ref["argmin"], height, width) | tap_shadow(ref["grids"], height, width)
+    return (tie_shadow(got_argmin, ref["argmin"], height, width) | near_tie_shadow(ref["candidates"], height, width)
+            | tap_shadow(ref["grids"], height, width)
             | l1_sign_shadow(ref["l1_margin"], height, width)
             | ssim_clamp_shadow(ref["clamp_margin"], height, width))
 

@@ -211,3 +211,27 @@ def test_emulated_degenerate_and_general_poses(case):
         decided = (top2[:, 1] - top2[:, 0]) > 1e-6
         assert not ((out["argmin"][s] != free["argmin"][s]) & decided).any(), f"level {s}"
     print(check_photo_grads(out, inp, g.num_scales, case, max_masked_frac=0.05))
+
+
+def test_emulated_taps_outside_the_staged_source_box():
+    """Sample displacements of 7-11 px: the bilinear footprints leave the gather margin of the staged
+    source boxes (CDP_SRC_MARGIN = 4) and are served from global memory instead; same results."""
+    from codeps_b200 import synthetic
+    import codeps_b200
+    from helpers import check_photo_grads
+    w, h, scales = 96, 64, 2
+    tb = synthetic.make_batch(2, w, h, (0.9 * w, 0.95 * w, 0.5 * w, 0.5 * h), seed=17, shift_px=9, flip_every_other=True)
+    noise = po.draw_noise(2, w, h, scales, seed=5)
+    k = codeps_b200.ReconstructionLoss(w, h, None, scales, "cpu")._level_intrinsics(tb.camera_models())
+    out = emu.photo(k, tb.images, tb.depth, tb.poses, noise, scales)
+    ref = po.loss_and_grads(tb.intrinsics.numpy(), tb.images, tb.depth, tb.disp, tb.poses, noise, scales,
+                            dtype=torch.float64, level_intrinsics=list(k))
+    shift = (ref["grids"][0][0][..., 0].double() + 1) / 2 * (w - 1) - torch.arange(w, dtype=torch.float64)
+    assert float(shift.abs().max()) > 6.0, "the case must leave the margin"
+    assert_loss_close(out["recon"], ref["recon"], "recon")
+    for s in range(scales):
+        top2 = torch.sort(ref["candidates"][s], dim=1).values[:, :2]
+        decided = (top2[:, 1] - top2[:, 0]) > 1e-6
+        assert not ((out["argmin"][s] != ref["argmin"][s]) & decided).any()
+    inp = dict(intrinsics=tb.intrinsics.numpy(), images=tb.images, depth=tb.depth, disp=tb.disp, poses=tb.poses, noise=noise)
+    check_photo_grads(out, inp, scales, "taps outside the source box", level_intrinsics=list(k))
