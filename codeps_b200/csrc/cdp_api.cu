@@ -253,7 +253,26 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
     __syncthreads();
     cdp_photo_phase_b2(p, c, threadIdx.x, blockDim.x, sm);
     __syncthreads();
-    cdp_photo_phase_c<M>(p, c, threadIdx.x, blockDim.x, sm, &v[1]);
+    cdp_photo_phase_c1(p, c, threadIdx.x, blockDim.x, sm);
+    // phase S2: the coefficient planes are dead, the source boxes come back for the sampler adjoint.
+    // Generic-proxy writes (coefficients) are ordered before the async-proxy (TMA) writes to the
+    // same bytes by a proxy fence on every thread + the block barrier.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (p.lv[c.lvl].use_tma) {
+      uint64_t* bar = reinterpret_cast<uint64_t*>(sm + Geo::O_MBAR);
+      if (threadIdx.x == 0) {
+        const int ox = c.x0 - Geo::TXO - Geo::SBM, oy = c.y0 - Geo::TYO - Geo::SBM;
+        cdp_mbar_expect_tx(bar, (unsigned)(2 * 3 * Geo::SBN * sizeof(float)));
+        cdp_tma_load_3d(sm + Geo::O_SRC, &tm.m[c.lvl][2], bar, ox, oy, c.b * 3);
+        cdp_tma_load_3d(sm + Geo::O_SRC + Geo::SRC_STRIDE, &tm.m[c.lvl][3], bar, ox, oy, c.b * 3);
+      }
+      cdp_mbar_wait(bar, 1);  // second use of the barrier: phase parity 1
+    } else {
+      cdp_photo_restage_sources(p, c, threadIdx.x, blockDim.x, sm);
+      __syncthreads();
+    }
+    cdp_photo_phase_c2<M>(p, c, threadIdx.x, blockDim.x, sm, &v[1]);
   }
   v[0] *= p.lv[c.lvl].weight;
   __syncthreads();  // tile planes are dead: reuse shared memory for the reduction

@@ -17,8 +17,11 @@
 //       tie-break noise, min / argmin, loss partial, argmin map, winner plane.
 //   B2  (with grad) same walk over the reprojection pair only, SSIM adjoint coefficients of the
 //       winner -> shared memory (the source boxes are dead by then and are reused).
-//   C   (with grad) gather the adjoint over the reflected 3x3 neighbourhood, L1 term, chain
-//       through the bilinear sampler and the projection to depth and pose.
+//   C1  (with grad) gather the adjoint over the reflected 3x3 neighbourhood, add the L1 term:
+//       dL/d warped value per channel and source, stored over the pixel's own warped values.
+//   S2  the two source boxes are staged again (TMA) over the dead coefficient planes.
+//   C2  (with grad) chain through the bilinear sampler (taps from the boxes) and the projection to
+//       depth and pose, both sources in the two lanes of packed fp32.
 // Reference: algos/depth.py:221-237, 272-325 (ReconstructionLoss), 128-155 (SSIMLoss);
 // misc/image_warper.py:100-184.
 #pragma once
@@ -613,9 +616,70 @@ CDP_HD float cdp_phase_c_lane_literal(int k, const CdpPhotoParams& p, const CdpL
   return gd;
 }
 
+// Phase C1: per tile pixel, the masked, reflection-weighted 3x3 sums of the coefficient planes
+// for both sources and the resulting dL/d warped value per channel (level weight included); the
+// pair overwrites the pixel's own entry of the warped planes (only this thread reads it again).
+// A pixel that no window selecting a reprojection reaches gets exact zeros.
+CDP_HD void cdp_photo_phase_c1(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm) {
+  typedef CdpTileGeom<true> Geo;
+  const CdpLevel& lv = p.lv[c.lvl];
+  const int W = lv.W, H = lv.H;
+  const uint8_t* kplane = reinterpret_cast<const uint8_t*>(sm + Geo::O_K);
+  float centre[3];
+  cdp_tile_centre<true>(lv, c, sm, centre);
+  const float w_ssim = p.alpha / 27.0f * lv.weight;  // alpha * (1/3 channels) * (1/9 window) * level weight
+  const float w_l1 = (float)(1.0 - (double)p.alpha) * (1.0f / 3.0f) * lv.weight;
+  for (int idx = tid; idx < CDP_TILE_X * CDP_TILE_Y; idx += nthreads) {
+    const int ly = idx / CDP_TILE_X, lx = idx - ly * CDP_TILE_X;
+    const int px = c.x0 + lx, py = c.y0 + ly;
+    if (px >= W || py >= H) continue;
+    const int ridx = (ly + Geo::TYO) * Geo::TBW + lx + Geo::TXO;
+    const int kown = kplane[ridx];
+    const bool interior = px >= 2 && px <= W - 3 && py >= 2 && py <= H - 3;
+    float2 sa[3], sb[3], sc[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) { sa[ch] = cdp_set2(0.f); sb[ch] = cdp_set2(0.f); sc[ch] = cdp_set2(0.f); }
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int dy = j / 3 - 1, dx = j % 3 - 1;
+      const int n = ridx + dy * Geo::TBW + dx;
+      const int kj = (int)kplane[n];  // (255 outside the image: matches neither source)
+      if (kj >= 2) continue;
+      // weight of neighbour j's window on this pixel: reflection multiplicity, per source lane
+      const float m = interior ? 1.f : cdp_reflect_mult(py, dy, H) * cdp_reflect_mult(px, dx, W);
+      float2 mk;
+      mk.x = kj == 0 ? m : 0.f;
+      mk.y = kj == 1 ? m : 0.f;
+      any = true;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        sa[ch] = cdp_fma2(mk, cdp_set2(sm[Geo::O_COEF + (ch * 3 + 0) * Geo::TBN + n]), sa[ch]);
+        sb[ch] = cdp_fma2(mk, cdp_set2(sm[Geo::O_COEF + (ch * 3 + 1) * Geo::TBN + n]), sb[ch]);
+        sc[ch] = cdp_fma2(mk, cdp_set2(sm[Geo::O_COEF + (ch * 3 + 2) * Geo::TBN + n]), sc[ch]);
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float2 g = cdp_set2(0.f);
+      if (any) {
+        const float2 x = cdp_add2(cdp_warp_plane<true>(sm, ch)[ridx], cdp_set2(-centre[ch]));
+        const float y = sm[Geo::O_TGT + ch * Geo::TBN + ridx] - centre[ch];
+        g = cdp_mul2(cdp_set2(w_ssim), cdp_fma2(cdp_mul2(x, cdp_set2(2.f)), sb[ch], cdp_fma2(cdp_set2(y), sc[ch], sa[ch])));
+        if (kown == 0) g.x += w_l1 * (x.x > y ? 1.f : (x.x < y ? -1.f : 0.f));
+        if (kown == 1) g.y += w_l1 * (x.y > y ? 1.f : (x.y < y ? -1.f : 0.f));
+      }
+      cdp_warp_plane<true>(sm, ch)[ridx] = g;
+    }
+  }
+}
+
+// Phase C2 (the source boxes are staged again: the coefficient planes that overlaid them are dead):
+// chain dL/d warped through the bilinear sampler's coordinate derivative and the projection to
+// dL/d depth_s (written) and dL/dT (accumulated), both sources in the two lanes of packed fp32.
 template <bool M>
-CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads,
-                              const float* sm, float* dT /*[32]: source-major 4x4 blocks*/) {
+CDP_HD void cdp_photo_phase_c2(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads,
+                               const float* sm, float* dT /*[32]: source-major 4x4 blocks*/) {
   typedef CdpTileGeom<true> Geo;
   const CdpLevel& lv = p.lv[c.lvl];
   const int W = lv.W, H = lv.H;
@@ -628,13 +692,11 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
     cdp_load_pose_aligned(p.pose1 + (size_t)c.b * 16, t1);
     cdp_pack_pose(t0, t1, T);
   }
-  const uint8_t* kplane = reinterpret_cast<const uint8_t*>(sm + Geo::O_K);
-  float centre[3];
-  cdp_tile_centre<true>(lv, c, sm, centre);
-  const float w_ssim = p.alpha / 27.0f * lv.weight;  // alpha * (1/3 channels) * (1/9 window) * level weight
-  const float w_l1 = (float)(1.0 - (double)p.alpha) * (1.0f / 3.0f) * lv.weight;
   const float* src0 = lv.src0 + (size_t)c.b * 3 * plane;
   const float* src1 = lv.src1 + (size_t)c.b * 3 * plane;
+  const float* sbox0 = sm + Geo::O_SRC;
+  const float* sbox1 = sm + Geo::O_SRC + Geo::SRC_STRIDE;
+  const int box_x = c.x0 - Geo::TXO - Geo::SBM, box_y = c.y0 - Geo::TYO - Geo::SBM;
   float2 dT2[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) dT2[i] = cdp_set2(0.f);
@@ -643,23 +705,11 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
     const int px = c.x0 + lx, py = c.y0 + ly;
     if (px >= W || py >= H) continue;
     const int ridx = (ly + Geo::TYO) * Geo::TBW + lx + Geo::TXO;
-    const int kown = kplane[ridx];
-    // winners of the 3x3 neighbourhood as per-source weights (reflection multiplicity where the
-    // neighbour's window reaches this pixel and it picked that source, else 0)
-    float2 mk[9];
-    bool any = false;
-    const bool interior = px >= 2 && px <= W - 3 && py >= 2 && py <= H - 3;
+    float2 gw[3];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const int dy = j / 3 - 1, dx = j % 3 - 1;
-      const float m = interior ? 1.f : cdp_reflect_mult(py, dy, H) * cdp_reflect_mult(px, dx, W);
-      const int kj = (int)kplane[ridx + dy * Geo::TBW + dx];  // (255 outside the image: matches neither)
-      mk[j].x = kj == 0 ? m : 0.f;
-      mk[j].y = kj == 1 ? m : 0.f;
-      any = any || (kj < 2 && m != 0.f);
-    }
-    float gd = 0.f;
-    if (!any) {  // every window that reaches this pixel is auto-masked: no gradient
+    for (int ch = 0; ch < 3; ++ch) gw[ch] = cdp_warp_plane<true>(sm, ch)[ridx];
+    const bool any = gw[0].x != 0.f || gw[0].y != 0.f || gw[1].x != 0.f || gw[1].y != 0.f || gw[2].x != 0.f || gw[2].y != 0.f;
+    if (!any) {  // no gradient reaches this pixel (auto-masked neighbourhood)
       if (M) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
@@ -681,55 +731,57 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
     }
     CdpWarp2 w;
     cdp_warp_point2((float)px, (float)py, depth, cam, T, M ? mo : nullptr, w);
-    // bilinear taps of both sources, requested before the coefficient gather so that their
-    // latency (L2: the shared-memory carve-out leaves almost no L1) overlaps it
     int ax0, ay0, ax1, ay1;
     float2 fx, fy, mx, my;
     cdp_tap_axis_full(px, w.dx.x, w.ix.x, W, ax0, fx.x, mx.x);
     cdp_tap_axis_full(py, w.dy.x, w.iy.x, H, ay0, fy.x, my.x);
     cdp_tap_axis_full(px, w.dx.y, w.ix.y, W, ax1, fx.y, mx.y);
     cdp_tap_axis_full(py, w.dy.y, w.iy.y, H, ay1, fy.y, my.y);
-    const float* g0 = src0 + ay0 * W + ax0;
-    const float* g1 = src1 + ay1 * W + ax1;
-    float2 nw[3], ne[3], sw[3], se[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      nw[ch].x = CDP_LDG(g0 + ch * plane); ne[ch].x = CDP_LDG(g0 + ch * plane + 1);
-      sw[ch].x = CDP_LDG(g0 + ch * plane + W); se[ch].x = CDP_LDG(g0 + ch * plane + W + 1);
-      nw[ch].y = CDP_LDG(g1 + ch * plane); ne[ch].y = CDP_LDG(g1 + ch * plane + 1);
-      sw[ch].y = CDP_LDG(g1 + ch * plane + W); se[ch].y = CDP_LDG(g1 + ch * plane + W + 1);
-    }
-    // masked, reflection-weighted 3x3 sums of the coefficient planes, both sources at once
-    float2 sa[3], sb[3], sc[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) { sa[ch] = cdp_set2(0.f); sb[ch] = cdp_set2(0.f); sc[ch] = cdp_set2(0.f); }
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const int n = ridx + (j / 3 - 1) * Geo::TBW + (j % 3 - 1);
+    const int bx0 = ax0 - box_x, by0 = ay0 - box_y, bx1 = ax1 - box_x, by1 = ay1 - box_y;
+    const bool in0 = (unsigned)bx0 <= (unsigned)(Geo::SBW - 2) && (unsigned)by0 <= (unsigned)(Geo::SBH - 2);
+    const bool in1 = (unsigned)bx1 <= (unsigned)(Geo::SBW - 2) && (unsigned)by1 <= (unsigned)(Geo::SBH - 2);
+    float2 gix = cdp_set2(0.f), giy = cdp_set2(0.f);
+    const float2 neg1 = cdp_set2(-1.0f);
+    const float2 wy0 = cdp_fma2(fy, neg1, cdp_set2(1.0f)), wx0 = cdp_fma2(fx, neg1, cdp_set2(1.0f));
+    if (in0 && in1) {
+      const float* q0 = sbox0 + by0 * Geo::SBW + bx0;
+      const float* q1 = sbox1 + by1 * Geo::SBW + bx1;
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        sa[ch] = cdp_fma2(mk[j], cdp_set2(sm[Geo::O_COEF + (ch * 3 + 0) * Geo::TBN + n]), sa[ch]);
-        sb[ch] = cdp_fma2(mk[j], cdp_set2(sm[Geo::O_COEF + (ch * 3 + 1) * Geo::TBN + n]), sb[ch]);
-        sc[ch] = cdp_fma2(mk[j], cdp_set2(sm[Geo::O_COEF + (ch * 3 + 2) * Geo::TBN + n]), sc[ch]);
+        float2 nw, ne, sw, se;
+        nw.x = q0[ch * Geo::SBN]; ne.x = q0[ch * Geo::SBN + 1];
+        sw.x = q0[ch * Geo::SBN + Geo::SBW]; se.x = q0[ch * Geo::SBN + Geo::SBW + 1];
+        nw.y = q1[ch * Geo::SBN]; ne.y = q1[ch * Geo::SBN + 1];
+        sw.y = q1[ch * Geo::SBN + Geo::SBW]; se.y = q1[ch * Geo::SBN + Geo::SBW + 1];
+        const float2 dix = cdp_fma2(cdp_fma2(nw, neg1, ne), wy0, cdp_mul2(cdp_fma2(sw, neg1, se), fy));
+        const float2 diy = cdp_fma2(cdp_fma2(nw, neg1, sw), wx0, cdp_mul2(cdp_fma2(ne, neg1, se), fx));
+        gix = cdp_fma2(gw[ch], dix, gix);
+        giy = cdp_fma2(gw[ch], diy, giy);
       }
-    }
-    // dL/d warped value per channel and source; chain through the sampler's coordinate derivative
-    float2 gw[3];
-    float2 gix = cdp_set2(0.f), giy = cdp_set2(0.f);
-    const float2 wy0 = cdp_fma2(fy, cdp_set2(-1.0f), cdp_set2(1.0f)), wx0 = cdp_fma2(fx, cdp_set2(-1.0f), cdp_set2(1.0f));
-    const float2 neg1 = cdp_set2(-1.0f);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      const float2 x = cdp_add2(cdp_warp_plane<true>(sm, ch)[ridx], cdp_set2(-centre[ch]));
-      const float y = sm[Geo::O_TGT + ch * Geo::TBN + ridx] - centre[ch];
-      float2 g = cdp_mul2(cdp_set2(w_ssim), cdp_fma2(cdp_mul2(x, cdp_set2(2.f)), sb[ch], cdp_fma2(cdp_set2(y), sc[ch], sa[ch])));
-      if (kown == 0) g.x += w_l1 * (x.x > y ? 1.f : (x.x < y ? -1.f : 0.f));
-      if (kown == 1) g.y += w_l1 * (x.y > y ? 1.f : (x.y < y ? -1.f : 0.f));
-      gw[ch] = g;
-      const float2 dix = cdp_fma2(cdp_fma2(nw[ch], neg1, ne[ch]), wy0, cdp_mul2(cdp_fma2(sw[ch], neg1, se[ch]), fy));
-      const float2 diy = cdp_fma2(cdp_fma2(nw[ch], neg1, sw[ch]), wx0, cdp_mul2(cdp_fma2(ne[ch], neg1, se[ch]), fx));
-      gix = cdp_fma2(g, dix, gix);
-      giy = cdp_fma2(g, diy, giy);
+    } else {
+#pragma unroll 1
+      for (int ch = 0; ch < 3; ++ch) {
+        float2 nw, ne, sw, se;
+        if (in0) {
+          const float* q = sbox0 + ch * Geo::SBN + by0 * Geo::SBW + bx0;
+          nw.x = q[0]; ne.x = q[1]; sw.x = q[Geo::SBW]; se.x = q[Geo::SBW + 1];
+        } else {
+          const float* g = src0 + ch * plane + (size_t)ay0 * W + ax0;
+          nw.x = CDP_LDG(g); ne.x = CDP_LDG(g + 1); sw.x = CDP_LDG(g + W); se.x = CDP_LDG(g + W + 1);
+        }
+        if (in1) {
+          const float* q = sbox1 + ch * Geo::SBN + by1 * Geo::SBW + bx1;
+          nw.y = q[0]; ne.y = q[1]; sw.y = q[Geo::SBW]; se.y = q[Geo::SBW + 1];
+        } else {
+          const float* g = src1 + ch * plane + (size_t)ay1 * W + ax1;
+          nw.y = CDP_LDG(g); ne.y = CDP_LDG(g + 1); sw.y = CDP_LDG(g + W); se.y = CDP_LDG(g + W + 1);
+        }
+        const float2 dix = cdp_fma2(cdp_fma2(nw, neg1, ne), wy0, cdp_mul2(cdp_fma2(sw, neg1, se), fy));
+        const float2 diy = cdp_fma2(cdp_fma2(nw, neg1, sw), wx0, cdp_mul2(cdp_fma2(ne, neg1, se), fx));
+        const float2 g = ch == 0 ? gw[0] : (ch == 1 ? gw[1] : gw[2]);
+        gix = cdp_fma2(g, dix, gix);
+        giy = cdp_fma2(g, diy, giy);
+      }
     }
     float2 gQ[3];
     float2 gdep = cdp_warp_adjoint2(cdp_mul2(gix, mx), cdp_mul2(giy, my), w, cam, T, dT2, gQ);
@@ -746,7 +798,6 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
         if (k == 0) gdep.x = lit; else gdep.y = lit;
       }
     }
-    gd = gdep.x + gdep.y;
     if (M) {
       float* d0 = lv.gmot0 + (size_t)c.b * 3 * plane + py * W + px;
       float* d1 = lv.gmot1 + (size_t)c.b * 3 * plane + py * W + px;
@@ -756,8 +807,20 @@ CDP_HD void cdp_photo_phase_c(const CdpPhotoParams& p, const CdpTileCtx& c, int 
         if (w.regular[1]) d1[ch * plane] = gQ[ch].y;
       }
     }
-    lv.gdepth[(size_t)c.b * plane + py * W + px] = gd;
+    lv.gdepth[(size_t)c.b * plane + py * W + px] = gdep.x + gdep.y;
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) { dT[i] += dT2[i].x; dT[16 + i] += dT2[i].y; }
+}
+
+// Re-staging of the two source boxes for phase C2 without TMA (plain loads).
+CDP_HD void cdp_photo_restage_sources(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm) {
+  typedef CdpTileGeom<true> Geo;
+  const CdpLevel& lv = p.lv[c.lvl];
+  const size_t plane = (size_t)lv.W * lv.H;
+  const int ox = c.x0 - Geo::TXO - Geo::SBM, oy = c.y0 - Geo::TYO - Geo::SBM;
+  cdp_stage_box(lv.src0 + (size_t)c.b * 3 * plane, plane, 3, sm + Geo::O_SRC, Geo::SBW, Geo::SBH, ox, oy, lv.W, lv.H,
+                tid, nthreads);
+  cdp_stage_box(lv.src1 + (size_t)c.b * 3 * plane, plane, 3, sm + Geo::O_SRC + Geo::SRC_STRIDE, Geo::SBW, Geo::SBH, ox,
+                oy, lv.W, lv.H, tid, nthreads);
 }

@@ -46,7 +46,9 @@ static void emu_photo_block(const CdpPhotoParams& kp, int bx, int by) {
   for (int t = 0; t < nt; ++t) cdp_photo_phase_b1<G>(kp, c, t, nt, sm.data(), v[(size_t)t * 33]);
   if (G) {
     for (int t = 0; t < nt; ++t) cdp_photo_phase_b2(kp, c, t, nt, sm.data());
-    for (int t = 0; t < nt; ++t) cdp_photo_phase_c<M>(kp, c, t, nt, sm.data(), &v[(size_t)t * 33 + 1]);
+    for (int t = 0; t < nt; ++t) cdp_photo_phase_c1(kp, c, t, nt, sm.data());
+    for (int t = 0; t < nt; ++t) cdp_photo_restage_sources(kp, c, t, nt, sm.data());
+    for (int t = 0; t < nt; ++t) cdp_photo_phase_c2<M>(kp, c, t, nt, sm.data(), &v[(size_t)t * 33 + 1]);
   }
   float* rec = kp.partials + ((size_t)c.b * kp.blocks_per_image + bx) * CDP_PARTIAL_STRIDE;
   for (int j = 0; j < 33; ++j) {
