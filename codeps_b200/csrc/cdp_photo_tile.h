@@ -620,8 +620,18 @@ CDP_HD float cdp_phase_c_lane_literal(int k, const CdpPhotoParams& p, const CdpL
 // for both sources and the resulting dL/d warped value per channel (level weight included); the
 // pair overwrites the pixel's own entry of the warped planes (only this thread reads it again).
 // A pixel that no window selecting a reprojection reaches gets exact zeros.
+//
+// Each thread owns CDP_C1_ROWS vertically adjacent pixels of one column and walks down their
+// window rows: per row the horizontal 3-tap sums of all nine planes (neighbour's winner and the
+// horizontal reflection multiplicity folded into a per-source weight pair), kept in a ring of
+// three rows; an output is the vertically weighted sum of the ring.  ~2.5x fewer shared-memory
+// loads and FMAs than nine separate 3x3 gathers per pixel.
+#ifndef CDP_C1_ROWS
+#define CDP_C1_ROWS 4
+#endif
 CDP_HD void cdp_photo_phase_c1(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm) {
   typedef CdpTileGeom<true> Geo;
+  static_assert(CDP_TILE_Y % CDP_C1_ROWS == 0, "C1 strips must tile the rows");
   const CdpLevel& lv = p.lv[c.lvl];
   const int W = lv.W, H = lv.H;
   const uint8_t* kplane = reinterpret_cast<const uint8_t*>(sm + Geo::O_K);
@@ -629,47 +639,56 @@ CDP_HD void cdp_photo_phase_c1(const CdpPhotoParams& p, const CdpTileCtx& c, int
   cdp_tile_centre<true>(lv, c, sm, centre);
   const float w_ssim = p.alpha / 27.0f * lv.weight;  // alpha * (1/3 channels) * (1/9 window) * level weight
   const float w_l1 = (float)(1.0 - (double)p.alpha) * (1.0f / 3.0f) * lv.weight;
-  for (int idx = tid; idx < CDP_TILE_X * CDP_TILE_Y; idx += nthreads) {
-    const int ly = idx / CDP_TILE_X, lx = idx - ly * CDP_TILE_X;
-    const int px = c.x0 + lx, py = c.y0 + ly;
-    if (px >= W || py >= H) continue;
-    const int ridx = (ly + Geo::TYO) * Geo::TBW + lx + Geo::TXO;
-    const int kown = kplane[ridx];
-    const bool interior = px >= 2 && px <= W - 3 && py >= 2 && py <= H - 3;
-    float2 sa[3], sb[3], sc[3];
+  for (int item = tid; item < CDP_TILE_X * (CDP_TILE_Y / CDP_C1_ROWS); item += nthreads) {
+    const int strip = item / CDP_TILE_X, lx = item - strip * CDP_TILE_X;
+    const int ly0 = strip * CDP_C1_ROWS;
+    const int px = c.x0 + lx;
+    if (px >= W || c.y0 + ly0 >= H) continue;
+    // horizontal reflection multiplicities of the three window columns (0 outside the image)
+    float mxw[3];
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) { sa[ch] = cdp_set2(0.f); sb[ch] = cdp_set2(0.f); sc[ch] = cdp_set2(0.f); }
-    bool any = false;
+    for (int d = 0; d < 3; ++d) mxw[d] = cdp_reflect_mult(px, d - 1, W);
+    float2 h[3][9];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const int dy = j / 3 - 1, dx = j % 3 - 1;
-      const int n = ridx + dy * Geo::TBW + dx;
-      const int kj = (int)kplane[n];  // (255 outside the image: matches neither source)
-      if (kj >= 2) continue;
-      // weight of neighbour j's window on this pixel: reflection multiplicity, per source lane
-      const float m = interior ? 1.f : cdp_reflect_mult(py, dy, H) * cdp_reflect_mult(px, dx, W);
-      float2 mk;
-      mk.x = kj == 0 ? m : 0.f;
-      mk.y = kj == 1 ? m : 0.f;
-      any = true;
+    for (int r = 0; r < CDP_C1_ROWS + 2; ++r) {
+      const int ty = ly0 - 1 + r + Geo::TYO;  // box row of window row r
+      const int n0 = ty * Geo::TBW + lx + Geo::TXO;
+      float2 mk[3];
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        sa[ch] = cdp_fma2(mk, cdp_set2(sm[Geo::O_COEF + (ch * 3 + 0) * Geo::TBN + n]), sa[ch]);
-        sb[ch] = cdp_fma2(mk, cdp_set2(sm[Geo::O_COEF + (ch * 3 + 1) * Geo::TBN + n]), sb[ch]);
-        sc[ch] = cdp_fma2(mk, cdp_set2(sm[Geo::O_COEF + (ch * 3 + 2) * Geo::TBN + n]), sc[ch]);
+      for (int d = 0; d < 3; ++d) {
+        const int kj = (int)kplane[n0 + d - 1];  // (255 outside the image: matches neither source)
+        mk[d].x = kj == 0 ? mxw[d] : 0.f;
+        mk[d].y = kj == 1 ? mxw[d] : 0.f;
       }
-    }
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      float2 g = cdp_set2(0.f);
-      if (any) {
-        const float2 x = cdp_add2(cdp_warp_plane<true>(sm, ch)[ridx], cdp_set2(-centre[ch]));
-        const float y = sm[Geo::O_TGT + ch * Geo::TBN + ridx] - centre[ch];
-        g = cdp_mul2(cdp_set2(w_ssim), cdp_fma2(cdp_mul2(x, cdp_set2(2.f)), sb[ch], cdp_fma2(cdp_set2(y), sc[ch], sa[ch])));
-        if (kown == 0) g.x += w_l1 * (x.x > y ? 1.f : (x.x < y ? -1.f : 0.f));
-        if (kown == 1) g.y += w_l1 * (x.y > y ? 1.f : (x.y < y ? -1.f : 0.f));
+      for (int pl = 0; pl < 9; ++pl) {
+        const float* cf = sm + Geo::O_COEF + pl * Geo::TBN + n0;
+        h[r % 3][pl] = cdp_fma2(mk[2], cdp_set2(cf[1]), cdp_fma2(mk[1], cdp_set2(cf[0]), cdp_mul2(mk[0], cdp_set2(cf[-1]))));
       }
-      cdp_warp_plane<true>(sm, ch)[ridx] = g;
+      if (r >= 2) {
+        const int ly = ly0 + r - 2, py = c.y0 + ly;
+        if (py < H) {
+          const int ridx = (ly + Geo::TYO) * Geo::TBW + lx + Geo::TXO;
+          const int kown = kplane[ridx];
+          // vertical weights: rows (r-2, r-1, r) of the ring are window rows dy = -1, 0, +1
+          const float2 m0 = cdp_set2(cdp_reflect_mult(py, -1, H)), m2 = cdp_set2(cdp_reflect_mult(py, 1, H));
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            float2 sabc[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const int pl = ch * 3 + q;
+              sabc[q] = cdp_fma2(m2, h[r % 3][pl], cdp_fma2(m0, h[(r - 2) % 3][pl], h[(r - 1) % 3][pl]));
+            }
+            const float2 x = cdp_add2(cdp_warp_plane<true>(sm, ch)[ridx], cdp_set2(-centre[ch]));
+            const float y = sm[Geo::O_TGT + ch * Geo::TBN + ridx] - centre[ch];
+            float2 g = cdp_mul2(cdp_set2(w_ssim), cdp_fma2(cdp_mul2(x, cdp_set2(2.f)), sabc[1], cdp_fma2(cdp_set2(y), sabc[2], sabc[0])));
+            if (kown == 0) g.x += w_l1 * (x.x > y ? 1.f : (x.x < y ? -1.f : 0.f));
+            if (kown == 1) g.y += w_l1 * (x.y > y ? 1.f : (x.y < y ? -1.f : 0.f));
+            cdp_warp_plane<true>(sm, ch)[ridx] = g;
+          }
+        }
+      }
     }
   }
 }
