@@ -145,7 +145,9 @@ __device__ __forceinline__ void cdp_block_reduce_store(float (&v)[N], float* red
 // memory (value-major, conflict free), then each warp sums whole values: lane l adds the entries
 // of threads l, l+32, ... in order, a shuffle tree combines the lanes.  ~4x fewer instructions
 // than N shuffle trees per warp.  red: >= N * blockDim.x floats.  Fixed order, no atomics.
-template <int N>
+// SKIP_AT > 0: value i >= SKIP_AT is stored at out[i + SKIP_BY] (the caller left a gap of entries
+// it knows to be zero out of the reduction).
+template <int N, int SKIP_AT = 0, int SKIP_BY = 0>
 __device__ __forceinline__ void cdp_block_reduce_store_wide(const float (&v)[N], float* red, float* out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, nt = blockDim.x;
 #pragma unroll
@@ -156,7 +158,7 @@ __device__ __forceinline__ void cdp_block_reduce_store_wide(const float (&v)[N],
     for (int t = lane; t < nt; t += 32) acc += red[i * nt + t];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-    if (lane == 0) out[i] = acc;
+    if (lane == 0) out[(SKIP_AT > 0 && i >= SKIP_AT) ? i + SKIP_BY : i] = acc;
   }
 }
 
@@ -275,11 +277,27 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
     cdp_photo_phase_c2<M>(p, c, threadIdx.x, blockDim.x, sm, &v[1]);
   }
   v[0] *= p.lv[c.lvl].weight;
-  __syncthreads();  // tile planes are dead: reuse shared memory for the reduction
   float* rec = p.partials + ((size_t)c.b * p.blocks_per_image + blockIdx.x) * CDP_PARTIAL_STRIDE;
   if constexpr (G) {
-    cdp_block_reduce_store_wide(v, sm, rec);
+    // The last row of dL/dT only receives something from pixels whose depth clamp is active (Q_w
+    // drops out of the projection otherwise): when no thread of the block saw one, the block
+    // reduction covers the loss and rows 0..2 of the two matrices only (25 instead of 33 values).
+    bool row3 = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) row3 = row3 || v[13 + i] != 0.f || v[29 + i] != 0.f;
+    // (the barrier also retires the tile planes: shared memory is reused for the reduction)
+    if (__syncthreads_or(row3)) {
+      cdp_block_reduce_store_wide(v, sm, rec);
+    } else {
+      float r[25];
+      r[0] = v[0];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) { r[1 + i] = v[1 + i]; r[13 + i] = v[17 + i]; }
+      cdp_block_reduce_store_wide<25, 13, 4>(r, sm, rec);
+      if (threadIdx.x < 8) rec[13 + (threadIdx.x & 3) + (threadIdx.x >> 2) * 16] = 0.f;
+    }
   } else {
+    __syncthreads();  // tile planes are dead: reuse shared memory for the reduction
     cdp_block_reduce_store(v, sm, rec);
     if (threadIdx.x >= 1 && threadIdx.x < 33) rec[threadIdx.x] = 0.f;
   }

@@ -49,6 +49,22 @@ CDP_HD float cdp_exp(float x) {
 #endif
 }
 
+CDP_HD float cdp_fmaf(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return a * b + c;  // the emulator is built with -ffp-contract=off (as for cdp_fma2)
+#endif
+}
+
+CDP_HD float cdp_saturate(float x) {  // clamp to [0, 1]
+#if defined(__CUDA_ARCH__)
+  return __saturatef(x);
+#else
+  return fminf(fmaxf(x, 0.f), 1.f);
+#endif
+}
+
 // Packed fp32 pairs: on sm_100a these are single FADD2 / FMUL2 / FFMA2 instructions working on
 // an aligned register pair (two pixels' or two candidates' worth of math per issue slot).
 CDP_HD float2 cdp_set2(float v) { float2 r; r.x = v; r.y = v; return r; }
@@ -124,14 +140,6 @@ struct CdpWarp {
   float dx, dy;        // ix - u, iy - v at full relative precision (regular case)
   bool regular;        // depth clamp inactive and Q_w != 0
 };
-
-CDP_HD float cdp_fmaf(float a, float b, float c) {
-#if defined(__CUDA_ARCH__)
-  return __fmaf_rn(a, b, c);
-#else
-  return a * b + c;  // the emulator is built with -ffp-contract=off (as for cdp_fma2)
-#endif
-}
 
 CDP_HD void cdp_warp_point(float u, float v, float depth, const CdpCam& k, const CdpPose& T,
                            const float* motion3, CdpWarp& o) {

@@ -368,9 +368,9 @@ CDP_HD float2 cdp_ssim_pair_loss(float2 sx, float2 sxx, float2 sxy, float sy, fl
   float2 S;
   S.x = cdp_fdiv(num.x, den.x);
   S.y = cdp_fdiv(num.y, den.y);
-  float2 l = cdp_fma2(S, cdp_set2(-0.5f), cdp_set2(0.5f));
-  l.x = fminf(fmaxf(l.x, 0.f), 1.f);
-  l.y = fminf(fmaxf(l.y, 0.f), 1.f);
+  float2 l;  // clamp((1 - S) / 2, 0, 1): one saturating FMA per lane (NaN -> 0 like fmin(fmax(NaN, 0), 1))
+  l.x = cdp_saturate(cdp_fmaf(S.x, -0.5f, 0.5f));
+  l.y = cdp_saturate(cdp_fmaf(S.y, -0.5f, 0.5f));
   return l;
 }
 
