@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- photometric-loss fwd+bwd throughput of the CoDEPS hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of synthetic frame triplets: the
@@ -19,6 +19,9 @@ Output: ONE JSON line on rank 0 (see the keys at the bottom of main()).
             duration from CUDA events recorded around every launch in an eager pass of the same
             K steps; peak from MEASURED_PEAKS.json.
   cpu_baseline  the oracle port of the reference torch path timed on the host cores (rank 0, N=1).
+  extras    short runs of the other configurations BASELINE.json names (workloads below), the
+            reference algorithm in torch eager on cuda:0 (informational) and the full adaptation
+            step (bench_adapt.py); `--workload NAME` runs one of them as the main line instead.
 """
 from __future__ import annotations
 
@@ -36,12 +39,28 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+# name: groups of (preset, batch, flip every other cx, key), batch mode, description.
+#   "per_gpu": every rank processes `batch` triplets of every group (weak scaling);
+#   "global":  `batch` is the global batch, split contiguously over the ranks (strong scaling).
 WORKLOADS = {
-    # name: (preset, per-GPU batch, description)
-    "cityscapes_b8": ("cityscapes", 8, "Cityscapes-shaped 1024x512 triplets, batch 8 per GPU, 5 scales"),
-    "kitti360_b8": ("kitti360", 8, "KITTI-360-shaped 1408x376 triplets, batch 8 per GPU, per-sample intrinsics"),
-    "semkitti_b8": ("semkitti", 8, "SemKITTI-DVPS-shaped 1280x384 triplets, batch 8 per GPU"),
+    "cityscapes_b8": dict(groups=[("cityscapes", 8, False, "train")], mode="per_gpu",
+                          desc="Cityscapes-shaped 1024x512 triplets, batch 8 per GPU, 5 scales (BASELINE config 2)"),
+    "kitti360_b8": dict(groups=[("kitti360", 8, True, "train")], mode="per_gpu",
+                        desc="KITTI-360-shaped 1408x376 triplets, batch 8 per GPU, per-sample intrinsics"),
+    "semkitti_b8": dict(groups=[("semkitti", 8, True, "train")], mode="per_gpu",
+                        desc="SemKITTI-DVPS-shaped 1280x384 triplets, batch 8 per GPU"),
+    "kitti360_b16_mixed": dict(groups=[("kitti360", 16, True, "online+replay")], mode="global",
+                               desc="KITTI-360-shaped 1408x376 triplets, GLOBAL batch 16 (online + replay samples, every "
+                                    "other one with the flipped principal point) sharded over the GPUs (BASELINE config 3)"),
+    "semkitti_b64": dict(groups=[("semkitti", 64, True, "train")], mode="global",
+                         desc="SemKITTI-DVPS-shaped 1280x384 triplets, GLOBAL batch 64 sharded over the GPUs, loss only "
+                              "(BASELINE config 5)"),
+    "adapt_mix": dict(groups=[("cityscapes", 2, False, "source"), ("kitti360_cfg", 1, False, "target"),
+                              ("kitti360_cfg", 2, True, "target_replay")], mode="per_gpu",
+                      desc="online-adaptation batch per GPU: 2 source @1024x512 + 1 target + 2 target-replay @1408x384, "
+                           "losses combined as sum n_k L_k / sum n_k (algos/depth.py:562-568)"),
 }
+EXTRA_WORKLOADS = ("kitti360_b16_mixed", "semkitti_b64", "adapt_mix")
 RECON_WEIGHT, SMOOTH_WEIGHT = 10.0, 0.001  # cfg/train_cityscapes.yaml:40-41
 NUM_SCALES = 5
 INPUT_SETS = 3  # rotating input sets so that consecutive steps do not hit L2
@@ -53,7 +72,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cityscapes_b8")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + ["adapt_step"], default="cityscapes_b8")
     ap.add_argument("--noise", choices=("torch", "fused"), default="torch")
     ap.add_argument("--intrinsics", choices=("host", "device"), default="host",
                     help="host: CameraModel objects hold host values (kernel parameter space); device: lazy "
@@ -63,6 +82,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other configurations")
     return ap.parse_args()
 
 
@@ -70,8 +90,8 @@ def profiled_kernel(workload: str, kernel_substr: str):
     """Latest tracked ncu record (profiles/*_ncu.json, written by tools/ncu_to_profile.py) of a
     kernel for this workload: DRAM traffic per launch, issue-slot utilisation, L2 hit rate."""
     import glob
-    best = None
     import re
+    best = None
 
     def natural(path):  # r01_9_... before r01_11_...
         return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", os.path.basename(path))]
@@ -145,50 +165,113 @@ class ClockSampler:
                 "sm_max_mhz": self.max_mhz, "samples": len(self.samples), "reasons": sorted(self.reasons)}
 
 
+def local_groups(workload: str, rank: int, world: int):
+    """[(preset, local batch, flip, key, global offset)] of this rank for a workload."""
+    from codeps_b200.distributed import shard_bounds
+    spec = WORKLOADS[workload]
+    out = []
+    for preset, batch, flip, key in spec["groups"]:
+        if spec["mode"] == "global":
+            lo, hi = shard_bounds(batch, rank, world)
+            if hi > lo:
+                out.append((preset, hi - lo, flip, key, lo))
+        else:
+            out.append((preset, batch, flip, key, 0))
+    return out
+
+
+def global_triplets(workload: str, world: int) -> int:
+    spec = WORKLOADS[workload]
+    total = sum(g[1] for g in spec["groups"])
+    return total if spec["mode"] == "global" else total * world
+
+
+def make_group_batch(preset, batch, flip, seed, offset=0):
+    """`batch` triplets of a preset; with `flip`, samples with odd GLOBAL index get the mirrored
+    principal point (replay samples, datasets/preprocessing.py:47-52)."""
+    from codeps_b200 import synthetic
+    tb = synthetic.make_preset_batch(preset, batch, seed=seed)
+    if flip:
+        k = tb.intrinsics.clone()
+        odd = (torch.arange(batch) + offset) % 2 == 1
+        k[odd, 2] = tb.width - k[odd, 2] - 1
+        tb = synthetic.TripletBatch(tb.images, tb.disp, tb.depth, tb.poses, k, tb.width, tb.height)
+    return tb
+
+
 # ------------------------------------------------------------------------------------------
 # CPU reference arm / baseline: the oracle port of the reference torch path on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_reference_rate(preset: str, steps: int, warmup: int, budget_s: float = 25.0):
-    """fwd+bwd of the reference algorithm (oracle/photo_oracle.py, same ATen ops as the
-    reference) on ONE triplet of the workload per step, all host threads.  Returns
-    (triplets/s, cores, iterations, median seconds)."""
-    from codeps_b200 import synthetic
+def reference_step_fn(workload: str, device: str, rank: int = 0, world: int = 1, per_group_batch=None):
+    """step() -> (recon, smooth) running the oracle port (the reference's ATen op sequence) fwd+bwd
+    on this rank's batch of the workload on `device`; returns (step, triplets per step)."""
     from oracle import photo_oracle as po
+    groups = []
+    for preset, batch, flip, key, off in local_groups(workload, rank, world):
+        if per_group_batch is not None:
+            batch = min(batch, per_group_batch)
+        tb = make_group_batch(preset, batch, flip, seed=1000 * rank, offset=off)
+        noise = po.draw_noise(batch, tb.width, tb.height, NUM_SCALES, seed=1)
+        mv = lambda t: t.to(device)
+        groups.append(dict(n=batch, k=tb.intrinsics.numpy(), images=[mv(i) for i in tb.images], depth=mv(tb.depth),
+                           disp=mv(tb.disp), poses=[mv(p) for p in tb.poses], noise=[mv(n) for n in noise]))
+    total = sum(g["n"] for g in groups)
+
+    def step():
+        recon_sum, smooth_sum = 0.0, 0.0
+        for g in groups:
+            share = g["n"] / total  # sum n_k L_k / sum n_k
+            r = po.loss_and_grads(g["k"], g["images"], g["depth"], g["disp"], g["poses"], g["noise"], NUM_SCALES,
+                                  recon_weight=RECON_WEIGHT * share, smooth_weight=SMOOTH_WEIGHT * share)
+            recon_sum += share * float(r["recon"])
+            smooth_sum += share * float(r["smooth"])
+        return recon_sum, smooth_sum
+    return step, total
+
+
+def cpu_reference_rate(workload: str, steps: int, warmup: int, budget_s: float, per_group_batch=None):
+    """Times the reference algorithm (oracle port, same ATen ops as the reference) fwd+bwd on the host
+    cores, all threads, on this workload's per-GPU batch (or `per_group_batch` triplets of every
+    group for a bounded sample).  Returns (triplets/s, cores, iterations, median s, triplets/step)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    tb = synthetic.make_preset_batch(preset, 1, seed=1000)
-    noise = po.draw_noise(1, tb.width, tb.height, NUM_SCALES, seed=1)
+    step, total = reference_step_fn(workload, "cpu", per_group_batch=per_group_batch)
     times = []
     t_begin = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        po.loss_and_grads(tb.intrinsics.numpy(), tb.images, tb.depth, tb.disp, tb.poses, noise, NUM_SCALES,
-                          recon_weight=RECON_WEIGHT, smooth_weight=SMOOTH_WEIGHT)
+        step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
         if i >= warmup and time.perf_counter() - t_begin > budget_s:
             break
     med = statistics.median(times)
-    return 1.0 / med, cores, len(times), med
+    return total / med, cores, len(times), med, total
 
 
 def run_reference_arm(args):
+    """The reference's own implementation of the path on the box's host cores: same workload, same
+    per-GPU batch per step (same_config), bounded by a time budget."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from codeps_b200 import synthetic
-    preset, batch, desc = WORKLOADS[args.workload]
+    workload = args.workload if args.workload != "adapt_step" else "adapt_mix"
+    spec = WORKLOADS[workload]
+    preset = spec["groups"][0][0]
     w, h = synthetic.PRESETS[preset][0], synthetic.PRESETS[preset][1]
-    rate, cores, iters, med = cpu_reference_rate(preset, args.steps, max(args.warmup, 1), budget_s=120.0)
-    sample = f"1 of {batch} triplets of the batch per step ({iters} steps timed), oracle port of the reference torch-CPU path"
+    # per-GPU batch of the N=1 run of our arm (global workloads are sharded there, not here: one host)
+    rate, cores, iters, med, total = cpu_reference_rate(workload, args.steps, max(args.warmup, 1), budget_s=150.0)
+    sample = (f"the full per-GPU batch ({total} triplets) per step, {iters} steps timed within the time budget, "
+              f"oracle port of the reference torch-CPU path (oracle/photo_oracle.py), torch {torch.__version__}")
     line = {
         "impl": "reference", "metric": f"photometric-loss fwd+bwd frame-triplets/sec @{w}x{h}", "value": rate,
         "unit": "triplets/s", "n_gpus": args.gpus, "steps": iters, "warmup": max(args.warmup, 1),
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "per_gpu_batch": batch, "num_scales": NUM_SCALES,
-                   "device": "host CPU", "torch_threads": cores},
+        "config": {"workload": workload, "description": spec["desc"], "per_gpu_batch": total, "num_scales": NUM_SCALES,
+                   "device": "host CPU", "torch_threads": cores, "same_config": True},
         "cpu_baseline": {"value": rate, "unit": "triplets/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -199,6 +282,106 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+class LossWorkload:
+    """Device-resident inputs and loss objects of one workload on this rank."""
+
+    def __init__(self, name, rank, world, dev, noise="torch", intrinsics="host", input_sets=INPUT_SETS, pin=True):
+        import codeps_b200
+        from codeps_b200 import synthetic
+        self.name, self.dev = name, dev
+        self.groups = local_groups(name, rank, world)
+        self.triplets = sum(g[1] for g in self.groups)
+        self.input_sets = input_sets
+        self.host, self.devs, self.cams, self.fns = [], [], [], []
+        for gi, (preset, batch, flip, key, off) in enumerate(self.groups):
+            w, h = synthetic.PRESETS[preset][0], synthetic.PRESETS[preset][1]
+            hs = [make_group_batch(preset, batch, flip, seed=1000 * rank + 10 * gi + i, offset=off) for i in range(input_sets)]
+            if pin:
+                hs = [x.pin() for x in hs]
+            ds = [x.to(dev) for x in hs]
+            if intrinsics == "device":
+                cams = [[codeps_b200.CameraModel.from_tensor(w, h, k[i]) for i in range(batch)]
+                        for k in (x.intrinsics.to(dev) for x in hs)]
+            else:
+                cams = [x.camera_models() for x in hs]
+            self.host.append(hs)
+            self.devs.append(ds)
+            self.cams.append(cams)
+            self.fns.append(codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), NUM_SCALES, dev, noise=noise))
+        self.smooth_fn = codeps_b200.EdgeAwareSmoothnessLoss()
+        self.w_recon = torch.tensor(RECON_WEIGHT, device=dev)
+        self.w_smooth = torch.tensor(SMOOTH_WEIGHT, device=dev)
+        self.resident_bytes = sum(x.nbytes() for hs in self.host for x in hs)
+        self.h2d_bytes = sum(hs[0].nbytes() for hs in self.host)
+
+    def with_noise(self, noise):
+        """Shallow copy sharing the resident inputs, with loss objects in another noise mode."""
+        import copy
+        import codeps_b200
+        other = copy.copy(self)
+        other.fns = [codeps_b200.ReconstructionLoss(f.scaled_width[0], f.scaled_height[0], codeps_b200.SSIMLoss(),
+                                                    NUM_SCALES, self.dev, noise=noise) for f in self.fns]
+        return other
+
+    def step(self, i, side_stream=None):
+        """fwd + bwd on resident input set i; returns (recon, smooth, grads).  Several groups are
+        combined as DepthAlgo.adaptation does: sum n_k L_k / sum n_k (algos/depth.py:562-568)."""
+        i %= self.input_sets
+        leaves, recons, smooths = [], [], []
+        for gi, (preset, batch, flip, key, off) in enumerate(self.groups):
+            ds = self.devs[gi][i]
+            # fresh autograd leaves every step (views, no copies), created on the launching stream
+            depth, disp = ds.depth.detach().requires_grad_(True), ds.disp.detach().requires_grad_(True)
+            p0, p1 = ds.poses[0].detach().requires_grad_(True), ds.poses[1].detach().requires_grad_(True)
+            if side_stream is not None:
+                # the two losses are independent: the smoothness kernels run on a second stream and
+                # fill the SMs the tile kernel's last wave and the small reduction kernels leave idle
+                cur = torch.cuda.current_stream()
+                side_stream.wait_stream(cur)
+                with torch.cuda.stream(side_stream):
+                    smooth = self.smooth_fn(ds.images[0], disp)
+                recon = self.fns[gi](self.cams[gi][i], ds.images, depth, (p0, p1))
+                cur.wait_stream(side_stream)
+            else:
+                recon = self.fns[gi](self.cams[gi][i], ds.images, depth, (p0, p1))
+                smooth = self.smooth_fn(ds.images[0], disp)
+            leaves += [depth, disp, p0, p1]
+            recons.append(recon * (batch / self.triplets) if len(self.groups) > 1 else recon)
+            smooths.append(smooth * (batch / self.triplets) if len(self.groups) > 1 else smooth)
+        recon = torch.stack(recons).sum() if len(recons) > 1 else recons[0]
+        smooth = torch.stack(smooths).sum() if len(smooths) > 1 else smooths[0]
+        # the caller's  loss = 10*recon + 0.001*smooth; loss.backward()  (train_codeps.py:102-107)
+        grads = torch.autograd.grad([recon, smooth], leaves, grad_outputs=[self.w_recon, self.w_smooth])
+        return recon, smooth, grads
+
+
+def make_runner(step_fn, use_graph, input_sets):
+    """Warm up, optionally capture one CUDA graph per input set, return run(i)."""
+    for i in range(3):
+        step_fn(i % input_sets)
+    torch.cuda.synchronize()
+    if not use_graph:
+        return lambda i: step_fn(i % input_sets)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(input_sets):
+            step_fn(i)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graphs, outs = [], []
+    for i in range(input_sets):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs.append(step_fn(i))
+        graphs.append(g)
+
+    def run(i):
+        graphs[i % input_sets].replay()
+        return outs[i % input_sets]
+    return run
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -222,97 +405,20 @@ def main():
     n_gpus = world
     _native.load()
 
-    preset, batch, desc = WORKLOADS[args.workload]
-    w, h = synthetic.PRESETS[preset][0], synthetic.PRESETS[preset][1]
-    flip = preset != "cityscapes"
-
-    # ---- inputs: INPUT_SETS distinct batches per rank, pinned on the host and resident in HBM
-    host_sets = [synthetic.make_preset_batch(preset, batch, seed=1000 * rank + i, flip_every_other=flip).pin()
-                 for i in range(INPUT_SETS)]
-    dev_sets = [hs.to(dev) for hs in host_sets]
-    cams = [hs.camera_models() for hs in host_sets]
-    if args.intrinsics == "device":
-        k_dev = [hs.intrinsics.to(dev) for hs in host_sets]
-        cams = [[codeps_b200.CameraModel.from_tensor(w, h, k[i]) for i in range(batch)] for k in k_dev]
-    resident_bytes = sum(hs.nbytes() for hs in host_sets)
-
-    recon_fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), NUM_SCALES, dev, noise=args.noise)
-    smooth_fn = codeps_b200.EdgeAwareSmoothnessLoss()
-    w_recon = torch.tensor(RECON_WEIGHT, device=dev)
-    w_smooth = torch.tensor(SMOOTH_WEIGHT, device=dev)
-
-    side_stream = torch.cuda.Stream() if args.overlap_smooth else None
-
-    def make_step(loss_fn):
-        def step(i):
-            """fwd + bwd on resident input set i; returns (recon, smooth, grads)."""
-            ds = dev_sets[i]
-            # fresh autograd leaves every step (views, no copies), created on the launching stream
-            depth, disp = ds.depth.detach().requires_grad_(True), ds.disp.detach().requires_grad_(True)
-            p0, p1 = ds.poses[0].detach().requires_grad_(True), ds.poses[1].detach().requires_grad_(True)
-            if side_stream is not None:
-                # the two losses are independent: the smoothness kernels run on a second stream and
-                # fill the SMs the tile kernel's last wave and the small reduction kernels leave idle
-                cur = torch.cuda.current_stream()
-                side_stream.wait_stream(cur)
-                with torch.cuda.stream(side_stream):
-                    smooth = smooth_fn(ds.images[0], disp)
-                recon = loss_fn(cams[i], ds.images, depth, (p0, p1))
-                cur.wait_stream(side_stream)
-            else:
-                recon = loss_fn(cams[i], ds.images, depth, (p0, p1))
-                smooth = smooth_fn(ds.images[0], disp)
-            # the caller's  loss = 10*recon + 0.001*smooth; loss.backward()  (train_codeps.py:102-107)
-            grads = torch.autograd.grad([recon, smooth], [depth, disp, p0, p1], grad_outputs=[w_recon, w_smooth])
-            return recon, smooth, grads
-        return step
-
-    def make_runner(step_fn, use_graph):
-        """Warm up, optionally capture one CUDA graph per input set, return run(i)."""
-        for i in range(3):
-            step_fn(i % INPUT_SETS)
-        torch.cuda.synchronize()
-        if not use_graph:
-            return lambda i: step_fn(i % INPUT_SETS)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for i in range(INPUT_SETS):
-                step_fn(i)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graphs, outs = [], []
-        for i in range(INPUT_SETS):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                outs.append(step_fn(i))
-            graphs.append(g)
-
-        def run(i):
-            graphs[i % INPUT_SETS].replay()
-            return outs[i % INPUT_SETS]
-        return run
-
-    step = make_step(recon_fn)
-    use_graph = not args.no_graph
-    torch.manual_seed(1234 + rank)
-    for i in range(3):  # eager warm-up (sizes the allocator pools, sets kernel attributes)
-        out = step(i % INPUT_SETS)
-    torch.cuda.synchronize()
-    launches_before = ops.launch_count()
-    out = step(0)
-    launches_per_step = ops.launch_count() - launches_before
-    torch.cuda.synchronize()
-    run_step = make_runner(step, use_graph)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(run, steps, sampler=None):
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(run, steps, warmup):
         """W warm-up steps, then exactly `steps` steps between barriers; device ms, max over ranks."""
-        for i in range(max(args.warmup, 3)):
+        for i in range(max(warmup, 3)):
             run(i)
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -322,134 +428,135 @@ def main():
             last = run(i)
         ev1.record()
         barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        return max_over_ranks(ev0.elapsed_time(ev1)), last
+
+    if args.workload == "adapt_step":
+        import bench_adapt
+        line = bench_adapt.run(args, rank, world, dev, barrier, max_over_ranks)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), last
+            dist.destroy_process_group()
+        return
+
+    spec = WORKLOADS[args.workload]
+    use_graph = not args.no_graph
+    wl = LossWorkload(args.workload, rank, world, dev, noise=args.noise, intrinsics=args.intrinsics)
+    preset = spec["groups"][0][0]
+    w, h = synthetic.PRESETS[preset][0], synthetic.PRESETS[preset][1]
+    total_triplets = global_triplets(args.workload, world)
+    side_stream = torch.cuda.Stream() if args.overlap_smooth else None
+    step = lambda i: wl.step(i, side_stream)
+
+    torch.manual_seed(1234 + rank)
+    for i in range(3):  # eager warm-up (sizes the allocator pools, sets kernel attributes)
+        step(i)
+    torch.cuda.synchronize()
+    launches_before = ops.launch_count()
+    step(0)
+    launches_per_step = ops.launch_count() - launches_before
+    torch.cuda.synchronize()
+    run_step = make_runner(step, use_graph, wl.input_sets)
 
     # ---- timed region: device-resident inputs
     with ClockSampler(local_rank) as clocks:
-        elapsed_ms, last = timed(run_step, args.steps)
-    value = n_gpus * batch * args.steps / (elapsed_ms * 1e-3)
+        elapsed_ms, last = timed(run_step, args.steps, args.warmup)
+    value = total_triplets * args.steps / (elapsed_ms * 1e-3)
     recon_val, smooth_val = float(last[0].detach()), float(last[1].detach())
 
     # ---- eager pass with per-kernel CUDA events (same K steps) -> dominant-kernel duration
     _native.profile_enable(True)
     for i in range(args.steps):
-        step(i % INPUT_SETS)
+        step(i)
     torch.cuda.synchronize()
     prof = _native.profile_read()
     _native.profile_enable(False)
     kernel_ms = {k: (ms / n if n else None) for k, (ms, n) in prof.items()}
-    photo_ms = kernel_ms["photo"]
-    s0 = sum(ww * hh for ww, hh in synthetic.level_sizes(w, h, NUM_SCALES))
-    a_alg = synthetic.algorithmic_bytes(w, h, NUM_SCALES)
-    # fused tile kernel = the per-level forward (41 B/level-px) and backward (45 B/level-px) of
-    # SURVEY.md section 8d done in one pass
-    photo_alg_bytes = 86 * s0 * batch
+    photo_ms = kernel_ms["photo"]  # mean per launch (one launch per group and step)
     peak, peak_src = measured_peaks()
+    # fused tile kernel = the per-level forward (41 B/level-px) and backward (45 B/level-px) of
+    # SURVEY.md section 8d done in one pass; per launch = one group
+    alg_launch, a_alg_step = [], 0
+    for g_preset, g_batch, _, _, _ in wl.groups:
+        gw, gh = synthetic.PRESETS[g_preset][0], synthetic.PRESETS[g_preset][1]
+        alg_launch.append(86 * sum(ww * hh for ww, hh in synthetic.level_sizes(gw, gh, NUM_SCALES)) * g_batch)
+        a_alg_step += synthetic.algorithmic_bytes(gw, gh, NUM_SCALES) * g_batch
+    photo_alg_bytes = sum(alg_launch) / len(alg_launch)
     achieved = photo_alg_bytes / (photo_ms * 1e-3) / 1e9
-    step_kernel_ms = sum(v for v in kernel_ms.values() if v)
+    step_kernel_ms = sum(v for v in kernel_ms.values() if v) * len(wl.groups)
     prof_rec = profiled_kernel(args.workload, "cdp_photo_kernel<1") or profiled_kernel(args.workload, "cdp_photo_kernel")
+    local_rate = wl.triplets * args.steps / (elapsed_ms * 1e-3)
     roofline = {
         "bound": "hbm", "kernel": "cdp_photo_kernel<true,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": prof_rec["dram_bytes"] if prof_rec else None, "peak_source": peak_src,
         "ncu": ({k: prof_rec.get(k) for k in ("profile", "duration_us", "issue_slot_pct", "sm_pct_of_peak",
                                               "dram_pct_of_peak", "l2_hit_pct", "l1_hit_pct",
-                                              "achieved_occupancy_pct", "registers_per_thread")}
+                                              "achieved_occupancy_pct", "registers_per_thread", "warp_instructions")}
                 if prof_rec else None),
         "limiter": "fp32 issue slots, not HBM (DESIGN.md section 6): see ncu.issue_slot_pct vs ncu.dram_pct_of_peak",
         "algorithmic_bytes_per_launch": photo_alg_bytes, "kernel_ms": photo_ms,
-        "kernel_share_of_step": photo_ms / step_kernel_ms if step_kernel_ms else None,
+        "kernel_share_of_step": photo_ms * len(wl.groups) / step_kernel_ms if step_kernel_ms else None,
         "kernel_ms_all": kernel_ms,
-        "path_bytes_per_triplet": a_alg,
-        "path_frac": (value / n_gpus) * a_alg / 1e9 / peak,
+        "path_bytes_per_step_per_gpu": a_alg_step,
+        "path_frac": (a_alg_step / wl.triplets) * local_rate / 1e9 / peak,
     }
 
-    # ---- same steps with the kernel's counter-based tie-break noise instead of torch.randn per level
     extras = {}
-    if args.noise == "torch":
-        fused_fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), NUM_SCALES, dev, noise="fused")
-        fused_ms, _ = timed(make_runner(make_step(fused_fn), use_graph), args.steps)
-        extras["value_fused_noise"] = n_gpus * batch * args.steps / (fused_ms * 1e-3)
+    # ---- same steps with the kernel's counter-based tie-break noise instead of torch.randn per level
+    if args.noise == "torch" and not args.no_extras:
+        wl_fused = wl.with_noise("fused")  # same resident inputs
+        fused_ms, _ = timed(make_runner(lambda i: wl_fused.step(i), use_graph, wl.input_sets), args.steps, args.warmup)
+        extras["value_fused_noise"] = total_triplets * args.steps / (fused_ms * 1e-3)
         extras["note"] = ("value_fused_noise: same step with ReconstructionLoss(noise='fused') -- no torch.randn "
                           "launches / noise traffic; different random numbers than the reference's stream")
 
     # ---- end to end: host (pinned) inputs -> public classes -> loss read back on the host
     e2e = None
     if not args.no_e2e:
-        copy_stream = torch.cuda.Stream()
-        main_stream = torch.cuda.current_stream()
-        e2e_steps = max(10, min(args.steps, 40))
+        e2e = run_e2e(wl, args, dev, barrier, max_over_ranks, total_triplets, world)
 
-        def upload(i):
-            with torch.cuda.stream(copy_stream):
-                dsb = host_sets[i % INPUT_SETS].to(dev, non_blocking=True)
-                evt = torch.cuda.Event()
-                evt.record(copy_stream)
-            return dsb, evt
+    # ---- the other configurations BASELINE.json names, as short runs
+    if not args.no_extras and args.workload == "cityscapes_b8":
+        extras["workloads"] = {}
+        for name in EXTRA_WORKLOADS:
+            extras["workloads"][name] = run_extra_workload(name, rank, world, dev, timed, use_graph)
+        extras["torch_cuda_eager"] = run_torch_cuda_eager(args.workload, rank, world, dev, timed, value)
+        try:
+            import bench_adapt
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.warmup = 12, 3
+            extras["adapt_step"] = bench_adapt.run(sub, rank, world, dev, barrier, max_over_ranks, brief=True)
+        except Exception as exc:  # e.g. torchvision missing
+            extras["adapt_step"] = {"unavailable": repr(exc)}
 
-        loss_host = torch.zeros(2, pin_memory=True)
-
-        def e2e_step(i, staged):
-            dsb, evt = staged
-            nxt = upload(i + 1)  # overlap the next step's H2D with this step's kernels
-            main_stream.wait_event(evt)
-            depth = dsb.depth.requires_grad_(True)
-            disp = dsb.disp.requires_grad_(True)
-            p0, p1 = dsb.poses[0].requires_grad_(True), dsb.poses[1].requires_grad_(True)
-            recon = recon_fn(cams[i % INPUT_SETS], dsb.images, depth, (p0, p1))
-            smooth = smooth_fn(dsb.images[0], disp)
-            loss = RECON_WEIGHT * recon + SMOOTH_WEIGHT * smooth
-            loss.backward()
-            loss_host.copy_(torch.stack((recon.detach(), smooth.detach())), non_blocking=True)
-            for tns in list(dsb.images) + [dsb.depth, dsb.disp] + list(dsb.poses):
-                tns.record_stream(main_stream)
-            return nxt
-
-        staged = upload(0)
-        for i in range(3):
-            staged = e2e_step(i, staged)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(e2e_steps):
-            staged = e2e_step(i, staged)
-        e1.record()
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-        e2e = {"value": n_gpus * batch * e2e_steps / (e2e_ms * 1e-3), "unit": "triplets/s",
-               "h2d_bytes_per_step": host_sets[0].nbytes(), "d2h_bytes_per_step": 8, "steps": e2e_steps,
-               "ms_per_step": e2e_ms / e2e_steps, "loss_readback": [float(x) for x in loss_host]}
-
-    # ---- CPU baseline (rank 0, N = 1 only)
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu_baseline = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        rate, cores, iters, med = cpu_reference_rate(preset, steps=12, warmup=1, budget_s=20.0)
+        rate, cores, iters, med, total = cpu_reference_rate(args.workload, steps=12, warmup=1, budget_s=20.0,
+                                                            per_group_batch=2)
         cpu_baseline = {"value": rate, "unit": "triplets/s", "cores": cores, "kind": "port",
-                        "sample": f"1 triplet of the workload per iteration (B=1, {w}x{h}), {iters} iterations, "
-                                  f"median {med * 1e3:.0f} ms, torch {torch.__version__} CPU"}
+                        "sample": f"{total} triplet(s) of the workload per iteration, {iters} iterations, "
+                                  f"median {med * 1e3:.0f} ms, torch {torch.__version__} CPU; the --impl reference arm "
+                                  f"times the full per-GPU batch"}
 
     # scalar statistics only (one coalesced all-reduce of 3 doubles); the data path has no collective
     from codeps_b200.distributed import reduce_loss_dict
     stats = reduce_loss_dict({"recon": torch.tensor(recon_val, device=dev, dtype=torch.float64),
-                              "smooth": torch.tensor(smooth_val, device=dev, dtype=torch.float64)}, batch)
+                              "smooth": torch.tensor(smooth_val, device=dev, dtype=torch.float64)}, max(wl.triplets, 1))
     checksum = [float(stats["recon"]), float(stats["smooth"])]
 
     if rank == 0:
         line = {
             "metric": f"photometric-loss fwd+bwd frame-triplets/sec @{w}x{h}",
             "value": value, "unit": "triplets/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if spec["mode"] == "global" else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "per_gpu_batch": batch,
-                       "global_batch": batch * n_gpus, "num_scales": NUM_SCALES, "noise": args.noise, "intrinsics": args.intrinsics, "overlap_smooth": bool(args.overlap_smooth),
+            "config": {"workload": args.workload, "description": spec["desc"], "per_gpu_batch": wl.triplets,
+                       "global_batch": total_triplets, "num_scales": NUM_SCALES, "noise": args.noise,
+                       "intrinsics": args.intrinsics, "overlap_smooth": bool(args.overlap_smooth),
                        "timed_with": "cuda_graph_replay" if use_graph else "eager_launches",
-                       "l2": f"{INPUT_SETS} rotating input sets, {resident_bytes / 1e6:.0f} MB resident > 126 MB L2",
+                       "l2": f"{wl.input_sets} rotating input sets, {wl.resident_bytes / 1e6:.0f} MB resident > 126 MB L2",
                        "loss_weights": [RECON_WEIGHT, SMOOTH_WEIGHT]},
             "clocks": clocks.summary(),
             "e2e": e2e,
@@ -463,6 +570,123 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_e2e(wl, args, dev, barrier, max_over_ranks, total_triplets, world):
+    """Host (pinned) inputs -> public classes -> loss read back on the host, every step; the next
+    step's upload runs on a copy stream while this step's kernels run."""
+    copy_stream = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
+    e2e_steps = max(10, min(args.steps, 40))
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            batches = [hs[i % wl.input_sets].to(dev, non_blocking=True) for hs in wl.host]
+            evt = torch.cuda.Event()
+            evt.record(copy_stream)
+        return batches, evt
+
+    loss_host = torch.zeros(2, pin_memory=True)
+
+    def e2e_step(i, staged):
+        batches, evt = staged
+        nxt = upload(i + 1)  # overlap the next step's H2D with this step's kernels
+        main_stream.wait_event(evt)
+        recon_t, smooth_t = 0.0, 0.0
+        for gi, dsb in enumerate(batches):
+            share = wl.groups[gi][1] / wl.triplets
+            depth = dsb.depth.requires_grad_(True)
+            disp = dsb.disp.requires_grad_(True)
+            p0, p1 = dsb.poses[0].requires_grad_(True), dsb.poses[1].requires_grad_(True)
+            recon = wl.fns[gi](wl.cams[gi][i % wl.input_sets], dsb.images, depth, (p0, p1))
+            smooth = wl.smooth_fn(dsb.images[0], disp)
+            recon_t = recon_t + share * recon
+            smooth_t = smooth_t + share * smooth
+        (RECON_WEIGHT * recon_t + SMOOTH_WEIGHT * smooth_t).backward()
+        loss_host.copy_(torch.stack((recon_t.detach(), smooth_t.detach())), non_blocking=True)
+        for dsb in batches:
+            for tns in list(dsb.images) + [dsb.depth, dsb.disp] + list(dsb.poses):
+                tns.record_stream(main_stream)
+        return nxt
+
+    # pinned H2D copy rate of this rank alone and of all ranks at once (the ceiling of the e2e number)
+    probe = wl.host[0][0]
+    copy_ms = []
+    for concurrent in (False, True):
+        if concurrent:
+            barrier()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            probe.to(dev, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        copy_ms.append(c0.elapsed_time(c1) / 5)
+        if not concurrent and world > 1:
+            barrier()
+    h2d_alone = probe.nbytes() / (copy_ms[0] * 1e-3) / 1e9
+    h2d_concurrent = probe.nbytes() / (max_over_ranks(copy_ms[1]) * 1e-3) / 1e9
+
+    staged = upload(0)
+    for i in range(3):
+        staged = e2e_step(i, staged)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        staged = e2e_step(i, staged)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    n_global = total_triplets
+    return {"value": n_global * e2e_steps / (e2e_ms * 1e-3), "unit": "triplets/s",
+            "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 8, "steps": e2e_steps,
+            "ms_per_step": e2e_ms / e2e_steps, "loss_readback": [float(x) for x in loss_host],
+            "h2d_gbs_per_rank_alone": h2d_alone, "h2d_gbs_per_rank_all_ranks_copying": h2d_concurrent,
+            "h2d_gbs_aggregate_all_ranks_copying": h2d_concurrent * world,
+            "h2d_gbs_per_rank_in_step": wl.h2d_bytes / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+            "copy_bound_ms_per_step": wl.h2d_bytes / (h2d_concurrent * 1e9) * 1e3}
+
+
+def run_extra_workload(name, rank, world, dev, timed, use_graph, steps=30):
+    """Short device-resident run of another configuration; ranks whose shard is empty idle."""
+    from codeps_b200 import _native
+    spec = WORKLOADS[name]
+    sets = 2 if name == "semkitti_b64" else INPUT_SETS
+    wl = LossWorkload(name, rank, world, dev, input_sets=sets, pin=False)
+    total = global_triplets(name, world)
+    if wl.triplets == 0:
+        run = lambda i: None
+    else:
+        run = make_runner(lambda i: wl.step(i), use_graph, wl.input_sets)
+    ms, _ = timed(run, steps, 3)
+    out = {"value": total * steps / (ms * 1e-3), "unit": "triplets/s", "ms_per_step": ms / steps, "steps": steps,
+           "global_batch": total, "per_gpu_batch_rank0": wl.triplets,
+           "scaling": "strong" if spec["mode"] == "global" else "weak", "description": spec["desc"]}
+    if wl.triplets:
+        _native.profile_enable(True)
+        for i in range(5):
+            wl.step(i)
+        torch.cuda.synchronize()
+        prof = _native.profile_read()
+        _native.profile_enable(False)
+        out["photo_kernel_ms_per_launch"] = prof["photo"][0] / max(prof["photo"][1], 1)
+    del wl
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_torch_cuda_eager(workload, rank, world, dev, timed, our_value, steps=5):
+    """The reference algorithm (oracle port = the reference's ATen op sequence) in torch eager on the
+    GPU, same per-GPU batch: what the unmodified CoDEPS loss costs on a B200 (informational)."""
+    step, total = reference_step_fn(workload, str(dev), rank, world)
+    ms, _ = timed(lambda i: step(), steps, 3)
+    rate = total * world * steps / (ms * 1e-3)
+    return {"value": rate, "unit": "triplets/s", "ms_per_step": ms / steps, "steps": steps, "per_gpu_batch": total,
+            "speedup_of_codeps_b200": our_value / rate,
+            "what": "oracle/photo_oracle.py (same ATen ops as algos/depth.py + misc/image_warper.py) fwd+bwd, torch "
+                    "eager on cuda, fp32, including its host-side launch overhead"}
 
 
 if __name__ == "__main__":
