@@ -578,35 +578,45 @@ def run_e2e(wl, args, dev, barrier, max_over_ranks, total_triplets, world):
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
     e2e_steps = max(10, min(args.steps, 40))
+    # two device staging sets per group (ping-pong), allocated once: the upload of step i+1 overwrites
+    # the buffers step i-1 computed on, after that step's kernels have finished (event)
+    slots = [[hs[0].to(dev) for hs in wl.host] for _ in range(2)]
+    free_evt = [None, None]
 
     def upload(i):
+        slot = i % 2
         with torch.cuda.stream(copy_stream):
-            batches = [hs[i % wl.input_sets].to(dev, non_blocking=True) for hs in wl.host]
+            if free_evt[slot] is not None:
+                copy_stream.wait_event(free_evt[slot])
+            for gi, hs in enumerate(wl.host):
+                src, dst = hs[i % wl.input_sets], slots[slot][gi]
+                for a, b in zip(list(dst.images) + [dst.disp, dst.depth] + list(dst.poses),
+                                list(src.images) + [src.disp, src.depth] + list(src.poses)):
+                    a.copy_(b, non_blocking=True)
             evt = torch.cuda.Event()
             evt.record(copy_stream)
-        return batches, evt
+        return slot, evt
 
     loss_host = torch.zeros(2, pin_memory=True)
 
     def e2e_step(i, staged):
-        batches, evt = staged
+        slot, evt = staged
         nxt = upload(i + 1)  # overlap the next step's H2D with this step's kernels
         main_stream.wait_event(evt)
         recon_t, smooth_t = 0.0, 0.0
-        for gi, dsb in enumerate(batches):
+        for gi, dsb in enumerate(slots[slot]):
             share = wl.groups[gi][1] / wl.triplets
-            depth = dsb.depth.requires_grad_(True)
-            disp = dsb.disp.requires_grad_(True)
-            p0, p1 = dsb.poses[0].requires_grad_(True), dsb.poses[1].requires_grad_(True)
+            depth = dsb.depth.detach().requires_grad_(True)
+            disp = dsb.disp.detach().requires_grad_(True)
+            p0, p1 = dsb.poses[0].detach().requires_grad_(True), dsb.poses[1].detach().requires_grad_(True)
             recon = wl.fns[gi](wl.cams[gi][i % wl.input_sets], dsb.images, depth, (p0, p1))
             smooth = wl.smooth_fn(dsb.images[0], disp)
             recon_t = recon_t + share * recon
             smooth_t = smooth_t + share * smooth
         (RECON_WEIGHT * recon_t + SMOOTH_WEIGHT * smooth_t).backward()
         loss_host.copy_(torch.stack((recon_t.detach(), smooth_t.detach())), non_blocking=True)
-        for dsb in batches:
-            for tns in list(dsb.images) + [dsb.depth, dsb.disp] + list(dsb.poses):
-                tns.record_stream(main_stream)
+        free_evt[slot] = torch.cuda.Event()
+        free_evt[slot].record(main_stream)
         return nxt
 
     # pinned H2D copy rate of this rank alone and of all ranks at once (the ceiling of the e2e number)
@@ -619,7 +629,9 @@ def run_e2e(wl, args, dev, barrier, max_over_ranks, total_triplets, world):
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         for _ in range(5):
-            probe.to(dev, non_blocking=True)
+            for a, b in zip(list(slots[0][0].images) + [slots[0][0].disp, slots[0][0].depth],
+                            list(probe.images) + [probe.disp, probe.depth]):
+                a.copy_(b, non_blocking=True)
         c1.record()
         torch.cuda.synchronize()
         copy_ms.append(c0.elapsed_time(c1) / 5)

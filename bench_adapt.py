@@ -39,6 +39,7 @@ class Encoder(nn.Module):
         net = getattr(torchvision.models, f"resnet{layers}")(weights=None)
         if in_channels != 3:
             net.conv1 = nn.Conv2d(in_channels, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        net.fc = nn.Identity()  # only the feature pyramid is used (no parameters without a gradient under DDP)
         self.net = net
         self.num_ch_enc = [64, 64, 128, 256, 512] if layers <= 34 else [64, 256, 512, 1024, 2048]
 
@@ -119,7 +120,8 @@ def run(args, rank, world, dev, barrier, max_over_ranks, brief: bool = False):
         prm.requires_grad_(False)
     model = Trainable().to(dev)
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index])
+        # the module runs once per group before the single backward: no in-place buffer broadcast between them
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=False)
     optim = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
 
     data, fns = {}, {}
