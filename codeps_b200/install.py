@@ -17,6 +17,7 @@ from .camera import CameraModel
 from .losses import (EdgeAwareSmoothnessLoss, FlowSmoothnessLoss, FlowSparsityLoss, ReconstructionLoss,
                      SSIMLoss)
 from .evaluator import DepthEvaluator
+from .heads import disp_to_depth, transformation_from_parameters
 from .mixup import warp_c2c
 from .warper import CoordinateWarper, ImageWarper
 
@@ -41,7 +42,13 @@ _PATCHES = {
     "eval": {"DepthEvaluator": DepthEvaluator},
 }
 # static methods rebound on a class: (module, class) -> {name: function}
-_METHOD_PATCHES = {("datasets.mixup", "Mixup"): {"warp_c2c": warp_c2c}}
+_METHOD_PATCHES = {
+    ("datasets.mixup", "Mixup"): {"warp_c2c": warp_c2c},
+    # the two conversions between the network heads and the loss (models/pose_head.py:56-77,
+    # models/depth_head.py:49-54): one kernel forward / backward each instead of ~40 element kernels
+    ("models.pose_head", "PoseHead"): {"transformation_from_parameters": transformation_from_parameters},
+    ("models.depth_head", "DepthHead"): {"disp_to_depth": disp_to_depth},
+}
 _originals = {}
 
 
