@@ -138,11 +138,10 @@ def run(args, rank, world, dev, barrier, max_over_ranks, brief: bool = False):
         if mode == "none":  # nets only: something that depends on every output
             return disp.mean() + (aa0.sum() + t0.sum() + aa1.sum() + t1.sum()), disp.mean()
         if mode == "ours":
-            depth = codeps_b200.disp_to_depth(disp)
-            poses = (codeps_b200.transformation_from_parameters(aa0, t0, invert=True),
-                     codeps_b200.transformation_from_parameters(aa1, t1, invert=False))
+            # fused entry: disparity and 6-DoF parameters go into the op (no conversion kernels)
             cams = [codeps_b200.CameraModel.from_tensor(tb.width, tb.height, d["k_dev"][i]) for i in range(d["n"])]
-            return fns[key](cams, tb.images, depth, poses), smooth_fn(tb.images[0], disp)
+            recon, _depth, _poses = fns[key].forward_from_heads(cams, tb.images, disp, ((aa0, t0), (aa1, t1)))
+            return recon, smooth_fn(tb.images[0], disp)
         depth = po.disp_to_depth(disp)
         poses = (po.transformation_from_parameters(aa0, t0, True), po.transformation_from_parameters(aa1, t1, False))
         recon = po.reconstruction_loss(d["k_np"], tb.images, depth, poses, d["noise"], NUM_SCALES)

@@ -13,9 +13,17 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_size_t, c_uint8, c_uin
 MAX_LEVELS = 6
 MAX_BATCH_PER_LAUNCH = 32
 MAX_FLOW_MAPS = 4    # CDP_MAX_FLOW_MAPS
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _fp = POINTER(c_float)
+
+
+class PhotoHeads(ctypes.Structure):
+    """struct cdp_photo_heads"""
+    _fields_ = [
+        ("disp", c_void_p), ("min_depth", c_float), ("max_depth", c_float),
+        ("axisangle", c_void_p * 2), ("translation", c_void_p * 2), ("invert", c_int32 * 2),
+    ]
 
 
 class PhotoArgs(ctypes.Structure):
@@ -36,6 +44,7 @@ class PhotoArgs(ctypes.Structure):
         ("motion0", c_void_p), ("motion1", c_void_p),
         ("intrinsics_dev", c_void_p),
         ("noise_ready", c_void_p),
+        ("heads", POINTER(PhotoHeads)),
     ]
 
 
@@ -53,6 +62,9 @@ SIGNATURES = {
     "cdp_photo_fwd": (c_int32, [POINTER(PhotoArgs), c_void_p]),
     "cdp_photo_bwd": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "cdp_photo_bwd_heads": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_void_p,
+                                      POINTER(PhotoHeads), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int32, c_void_p, c_void_p, c_void_p]),
     "cdp_photo_fwd_launches": (c_int32, [c_int32, c_int32]),
     "cdp_photo_bwd_launches": (c_int32, [c_int32, c_int32, c_int32]),
     "cdp_smooth_saved_bytes": (c_size_t, [c_int32] * 3),
@@ -172,5 +184,5 @@ def profile_read() -> dict:
     return out
 
 
-__all__ = ["PhotoArgs", "SIGNATURES", "load", "check", "library_path", "NativeError",
+__all__ = ["PhotoArgs", "PhotoHeads", "SIGNATURES", "load", "check", "library_path", "NativeError",
            "MAX_LEVELS", "MAX_BATCH_PER_LAUNCH", "MAX_FLOW_MAPS", "c_uint8"]

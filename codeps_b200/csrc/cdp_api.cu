@@ -175,6 +175,8 @@ __global__ void __launch_bounds__(256, CDP_PYR_MIN_BLOCKS) cdp_pyramid_fwd_kerne
   if (blockIdx.x == 0 && blockIdx.y == 0)
     for (int i = threadIdx.x; i < kt.batch_count * kt.L; i += blockDim.x)
       cdp_k_table_entry(kt, i / kt.batch_count, i % kt.batch_count);
+  if (p.pose_out[0] && blockIdx.x == 0 && blockIdx.y == 0)  // fused heads: 6-DoF parameters -> 4x4 matrices
+    for (int j = threadIdx.x; j < 2 * p.B; j += blockDim.x) cdp_pyr_pose_item(p, j);
   cdp_pyramid_fwd_item(p, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
@@ -318,6 +320,16 @@ __device__ __forceinline__ double cdp_warp_butterfly(double v) {  // same order 
   return v;
 }
 
+// first block of the depth-gradient launch: dL/dT = grad_loss * unit gradient, or (fused heads) its
+// chain to the 6-DoF parameters
+__device__ __forceinline__ void cdp_pose_grad_block(const CdpDepthGradParams& p) {
+  if (p.axisangle[0]) {
+    for (int j = threadIdx.x; j < 2 * p.B; j += blockDim.x) cdp_pose_grad_heads(p, j);
+  } else {
+    for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
+  }
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_constant__ CdpDepthGradParams p) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;  // one row per blockIdx.y: no index division
@@ -326,7 +338,7 @@ __global__ void __launch_bounds__(256) cdp_depth_grad_kernel(const __grid_consta
     else cdp_depth_grad_px(p, blockIdx.z, blockIdx.y, x);
   }
   if (p.scale_pose && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
-    for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
+    cdp_pose_grad_block(p);
 }
 
 template <bool ALL_EXACT>
@@ -334,7 +346,7 @@ __global__ void __launch_bounds__(256) cdp_depth_grad_quad_kernel(const __grid_c
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (x < p.W) cdp_depth_grad_quad<ALL_EXACT>(p, blockIdx.z, blockIdx.y, x);
   if (p.scale_pose && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
-    for (int i = threadIdx.x; i < 2 * p.B * 16; i += blockDim.x) cdp_pose_grad_scale(p, i);
+    cdp_pose_grad_block(p);
 }
 
 __global__ void __launch_bounds__(CDP_SMOOTH_THREADS) cdp_smooth_main_kernel(const CdpSmoothParams p) {
@@ -546,6 +558,11 @@ extern "C" int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels) {
 }
 extern "C" int cdp_photo_bwd_launches(int32_t, int32_t, int32_t with_motion) { return with_motion ? 3 : 1; }
 
+// (defined with the stand-alone head conversions further down)
+__global__ void cdp_pose_fwd_kernel(const float* aa, const float* tr, int B, int invert, float* M);
+__global__ void __launch_bounds__(256) cdp_disp_to_depth_fwd_kernel(const float* disp, size_t n, float lo, float span, float* depth);
+static int cdp_elementwise_grid(size_t n);
+
 extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   CDP_REQUIRE(a != nullptr, "args is null");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -574,6 +591,31 @@ extern "C" int cdp_photo_fwd(const cdp_photo_args* a, cdp_stream_t stream_) {
   bool any_noise = false, all_noise = true;
   for (int s = 0; s < plan.L; ++s) { any_noise |= a->noise[s] != nullptr; all_noise &= a->noise[s] != nullptr; }
   CDP_REQUIRE(!any_noise || all_noise, "noise must be given for every level or for none");
+
+  // fused heads: disparity -> depth and 6-DoF -> matrices ride along with the pyramid launch; where
+  // that launch cannot do it (no pyramid, or no level-1 fast path) they are separate small kernels
+  const cdp_photo_heads* hd = a->heads;
+  if (hd) {
+    CDP_REQUIRE((hd->axisangle[0] != nullptr) == (hd->axisangle[1] != nullptr) &&
+                (hd->axisangle[0] != nullptr) == (hd->translation[0] != nullptr) &&
+                (hd->axisangle[1] != nullptr) == (hd->translation[1] != nullptr),
+                "heads: axis-angle and translation must be given for both sources or for none");
+    CDP_REQUIRE(!hd->disp || (hd->min_depth > 0.f && hd->max_depth > hd->min_depth), "heads: need 0 < min_depth < max_depth");
+    CdpPyrParams probe;
+    if (plan.L > 1) cdp_fill_pyr_params(plan, a, &probe);
+    if (hd->disp && (plan.L == 1 || !probe.depth_out)) {
+      const size_t count = (size_t)plan.B * plan.H * plan.W;
+      const float lo = 1.0f / hd->max_depth, span = 1.0f / hd->min_depth - lo;
+      cdp_disp_to_depth_fwd_kernel<<<cdp_elementwise_grid(count), 256, 0, stream>>>(hd->disp, count, lo, span, const_cast<float*>(a->depth));
+      CDP_LAUNCH_CHECK("cdp_disp_to_depth_fwd_kernel");
+    }
+    if (hd->axisangle[0] && plan.L == 1) {
+      for (int k = 0; k < 2; ++k)
+        cdp_pose_fwd_kernel<<<(plan.B + 127) / 128, 128, 0, stream>>>(hd->axisangle[k], hd->translation[k], plan.B, hd->invert[k],
+                                                                  const_cast<float*>(k == 0 ? a->pose0 : a->pose1));
+      CDP_LAUNCH_CHECK("cdp_pose_fwd_kernel");
+    }
+  }
 
   // the per-level intrinsics table rides along with the pyramid launch when there is one and the
   // whole batch fits its parameter block; otherwise cdp_k_table_kernel writes it (step 2)
@@ -662,6 +704,43 @@ extern "C" int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32
     cdp_launch_depth_grad(p, stream);
   }
   CDP_LAUNCH_CHECK("cdp_depth_grad_kernel");
+  if (with_motion) {
+    float* outs[2] = {grad_motion0, grad_motion1};
+    for (int k = 0; k < 2; ++k) {
+      CdpDepthGradParams pm;
+      cdp_fill_motion_grad_params(plan, saved_, resize_tables, grad_loss, k, outs[k], &pm);
+      ProfScope prof_(CDP_KERNEL_DEPTH_GRAD, stream);
+      cdp_launch_depth_grad(pm, stream);
+      CDP_LAUNCH_CHECK("cdp_depth_grad_kernel (motion)");
+    }
+  }
+  return CDP_OK;
+}
+
+extern "C" int cdp_photo_bwd_heads(int32_t batch, int32_t height, int32_t width, int32_t num_levels, const void* saved_,
+                                   size_t saved_bytes, const void* resize_tables, const float* grad_loss,
+                                   const cdp_photo_heads* heads, const float* depth, float* grad_disp,
+                                   float* grad_axisangle0, float* grad_translation0, float* grad_axisangle1,
+                                   float* grad_translation1, int32_t with_motion, float* grad_motion0,
+                                   float* grad_motion1, cdp_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CdpPlan plan;
+  CDP_REQUIRE(cdp_make_plan(batch, height, width, num_levels, &plan, with_motion != 0), "invalid shape");
+  CDP_REQUIRE(heads && heads->disp && heads->axisangle[0] && heads->axisangle[1] && heads->translation[0] && heads->translation[1],
+              "cdp_photo_bwd_heads needs the disparity and both sources' 6-DoF parameters");
+  CDP_REQUIRE(!with_motion || (grad_motion0 && grad_motion1), "with_motion needs grad_motion0 and grad_motion1");
+  CDP_REQUIRE(saved_ && grad_loss && depth && grad_disp && grad_axisangle0 && grad_translation0 && grad_axisangle1 &&
+              grad_translation1, "null pointer");
+  CDP_REQUIRE(plan.L == 1 || resize_tables != nullptr, "resize_tables is null");
+  if (saved_bytes < plan.saved_floats * sizeof(float)) return cdp_fail(CDP_ERR_WORKSPACE, "saved too small");
+  CdpDepthGradParams p;
+  cdp_fill_depth_grad_params(plan, saved_, resize_tables, grad_loss, grad_disp, nullptr, nullptr, &p);
+  cdp_depth_grad_params_heads(heads, depth, grad_axisangle0, grad_translation0, grad_axisangle1, grad_translation1, &p);
+  {
+    ProfScope prof_(CDP_KERNEL_DEPTH_GRAD, stream);
+    cdp_launch_depth_grad(p, stream);
+  }
+  CDP_LAUNCH_CHECK("cdp_depth_grad_kernel (heads)");
   if (with_motion) {
     float* outs[2] = {grad_motion0, grad_motion1};
     for (int k = 0; k < 2; ++k) {

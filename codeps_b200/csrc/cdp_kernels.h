@@ -23,7 +23,21 @@ struct CdpPyrParams {
   int32_t begin[CDP_MAX_LEVELS + 1];   // prefix offsets of level work items within one image
   int32_t W, H, L;
   int32_t fast1;  // level 1 is an exact 2x2 mean (W % 4 == 0, H even): one item = two outputs
+  // fused heads (cdp_photo_heads): in[3] is the DISPARITY; depth = 1 / (min_disp + span * disp) is
+  // what gets resized, and the level-1 items also write the full-resolution depth map (depth_out)
+  float* depth_out;  // null: in[3] is a depth map
+  float min_disp, disp_span;
+  // poses from the 6-DoF parameters, written by the first block (null: pose matrices are inputs)
+  const float* axisangle[2];
+  const float* translation[2];
+  float* pose_out[2];
+  int32_t invert[2];
+  int32_t B;
 };
+
+CDP_HD float cdp_disp_to_depth(float disp, float min_disp, float span) { return 1.0f / (min_disp + span * disp); }
+CDP_HD float cdp_disp_to_depth_grad(float g_depth, float depth, float span) { return -g_depth * span * depth * depth; }
+
 
 CDP_HD void cdp_pyramid_fwd_item(const CdpPyrParams& p, int b, int item) {
   if (item >= p.begin[p.L]) return;
@@ -45,8 +59,16 @@ CDP_HD void cdp_pyramid_fwd_item(const CdpPyrParams& p, int b, int item) {
       const int ch = t == 3 ? 1 : 3;
       for (int c = 0; c < ch; ++c) {
         const float* src = p.in[t] + ((size_t)b * ch + c) * in_plane;
-        const float4 a = CDP_LDG(reinterpret_cast<const float4*>(src + o0));
-        const float4 d = CDP_LDG(reinterpret_cast<const float4*>(src + o1));
+        float4 a = CDP_LDG(reinterpret_cast<const float4*>(src + o0));
+        float4 d = CDP_LDG(reinterpret_cast<const float4*>(src + o1));
+        if (t == 3 && p.depth_out) {  // disparity in, depth out (full resolution) and resized
+          a.x = cdp_disp_to_depth(a.x, p.min_disp, p.disp_span); a.y = cdp_disp_to_depth(a.y, p.min_disp, p.disp_span);
+          a.z = cdp_disp_to_depth(a.z, p.min_disp, p.disp_span); a.w = cdp_disp_to_depth(a.w, p.min_disp, p.disp_span);
+          d.x = cdp_disp_to_depth(d.x, p.min_disp, p.disp_span); d.y = cdp_disp_to_depth(d.y, p.min_disp, p.disp_span);
+          d.z = cdp_disp_to_depth(d.z, p.min_disp, p.disp_span); d.w = cdp_disp_to_depth(d.w, p.min_disp, p.disp_span);
+          *reinterpret_cast<float4*>(p.depth_out + (size_t)b * in_plane + o0) = a;
+          *reinterpret_cast<float4*>(p.depth_out + (size_t)b * in_plane + o1) = d;
+        }
         float2 r;
         r.x = (a.x * 0.5f + a.y * 0.5f) * 0.5f + (d.x * 0.5f + d.y * 0.5f) * 0.5f;
         r.y = (a.z * 0.5f + a.w * 0.5f) * 0.5f + (d.z * 0.5f + d.w * 0.5f) * 0.5f;
@@ -66,8 +88,13 @@ CDP_HD void cdp_pyramid_fwd_item(const CdpPyrParams& p, int b, int item) {
     const int ch = t == 3 ? 1 : 3;
     for (int c = 0; c < ch; ++c) {
       const float* src = p.in[t] + ((size_t)b * ch + c) * in_plane;
-      const float top = CDP_LDG(src + o00) * tx.w0 + CDP_LDG(src + o01) * tx.w1;
-      const float bot = CDP_LDG(src + o10) * tx.w0 + CDP_LDG(src + o11) * tx.w1;
+      float v00 = CDP_LDG(src + o00), v01 = CDP_LDG(src + o01), v10 = CDP_LDG(src + o10), v11 = CDP_LDG(src + o11);
+      if (t == 3 && p.depth_out) {  // the taps are disparities: resize the depth they stand for
+        v00 = cdp_disp_to_depth(v00, p.min_disp, p.disp_span); v01 = cdp_disp_to_depth(v01, p.min_disp, p.disp_span);
+        v10 = cdp_disp_to_depth(v10, p.min_disp, p.disp_span); v11 = cdp_disp_to_depth(v11, p.min_disp, p.disp_span);
+      }
+      const float top = v00 * tx.w0 + v01 * tx.w1;
+      const float bot = v10 * tx.w0 + v11 * tx.w1;
       p.out[t][s][((size_t)b * ch + c) * out_plane + local] = top * ty.w0 + bot * ty.w1;
     }
   }
@@ -148,6 +175,15 @@ struct CdpDepthGradParams {
   float* grad_pose[2];     // [B,16]
   int32_t B, H, W, L;
   int32_t scale_pose;      // also write grad_pose = grad_loss * pose_unit (first launch only)
+  // fused heads: grad_depth receives dL/d DISPARITY = -span * depth^2 * dL/d depth, and the first
+  // block chains the scaled dL/dT through transformation_from_parameters instead of storing it
+  const float* depth_vals; // [B,1,H,W] or null
+  float disp_span;
+  const float* axisangle[2];   // [B,3] or null
+  const float* translation[2];
+  int32_t invert[2];
+  float* grad_axisangle[2];    // [B,3]
+  float* grad_translation[2];
 };
 
 // references of input index i into level s along one axis: transpose of the bilinear resize taps
@@ -199,7 +235,9 @@ CDP_HD void cdp_depth_grad_px(const CdpDepthGradParams& p, int b, int y, int x) 
     if (s >= p.L) break;
     acc += cdp_depth_grad_level(p, b, y, x, s);
   }
-  p.grad_depth[(size_t)b * W * p.H + pix] = CDP_LDG(p.grad_loss) * acc;
+  float g = CDP_LDG(p.grad_loss) * acc;
+  if (p.depth_vals) g = cdp_disp_to_depth_grad(g, CDP_LDG(p.depth_vals + (size_t)b * W * p.H + pix), p.disp_span);
+  p.grad_depth[(size_t)b * W * p.H + pix] = g;
 }
 
 // Same for pyramids whose every level is an exact power-of-two reduction on both axes (the common
@@ -217,7 +255,9 @@ CDP_HD void cdp_depth_grad_px_exact(const CdpDepthGradParams& p, int b, int y, i
     const bool hx = (unsigned)((x & (r - 1)) - (half - 1)) < 2u;
     if (hy && hx) acc += 0.25f * CDP_LDG(p.gdepth[s] + (size_t)b * p.Ws[s] * p.Hs[s] + (y >> s) * p.Ws[s] + (x >> s));
   }
-  p.grad_depth[(size_t)b * W * p.H + pix] = CDP_LDG(p.grad_loss) * acc;
+  float g = CDP_LDG(p.grad_loss) * acc;
+  if (p.depth_vals) g = cdp_disp_to_depth_grad(g, CDP_LDG(p.depth_vals + (size_t)b * W * p.H + pix), p.disp_span);
+  p.grad_depth[(size_t)b * W * p.H + pix] = g;
 }
 
 // Four consecutive pixels x..x+3 (x % 4 == 0) of row y in one thread, for W % 4 == 0 and 16-byte
@@ -261,6 +301,11 @@ CDP_HD void cdp_depth_grad_quad(const CdpDepthGradParams& p, int b, int y, int x
   }
   const float go = CDP_LDG(p.grad_loss);
   a.x *= go; a.y *= go; a.z *= go; a.w *= go;
+  if (p.depth_vals) {
+    const float4 dv = CDP_LDG(reinterpret_cast<const float4*>(p.depth_vals + o0));
+    a.x = cdp_disp_to_depth_grad(a.x, dv.x, p.disp_span); a.y = cdp_disp_to_depth_grad(a.y, dv.y, p.disp_span);
+    a.z = cdp_disp_to_depth_grad(a.z, dv.z, p.disp_span); a.w = cdp_disp_to_depth_grad(a.w, dv.w, p.disp_span);
+  }
   *reinterpret_cast<float4*>(p.grad_depth + o0) = a;
 }
 
@@ -268,6 +313,7 @@ CDP_HD void cdp_depth_grad_quad(const CdpDepthGradParams& p, int b, int y, int x
 CDP_HD bool cdp_depth_grad_quad_ok(const CdpDepthGradParams& p) {
   if ((p.W & 3) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p.gdepth[0]) & 15) != 0 || (reinterpret_cast<uintptr_t>(p.grad_depth) & 15) != 0) return false;
+  if (p.depth_vals && (reinterpret_cast<uintptr_t>(p.depth_vals) & 15) != 0) return false;
   if (p.L > 1 && p.exact_x[1] && p.exact_y[1] && (reinterpret_cast<uintptr_t>(p.gdepth[1]) & 7) != 0) return false;
   return true;
 }
@@ -819,9 +865,6 @@ CDP_HD void cdp_pose_bwd_sample(const float* gM, const float* axisangle, const f
   for (int i = 0; i < 3; ++i) { g_axisangle[i] = gv[i]; g_translation[i] = gt[i]; }
 }
 
-CDP_HD float cdp_disp_to_depth(float disp, float min_disp, float span) { return 1.0f / (min_disp + span * disp); }
-CDP_HD float cdp_disp_to_depth_grad(float g_depth, float depth, float span) { return -g_depth * span * depth * depth; }
-
 // ==========================================================================================
 // 8. Object-motion regularisers (FlowSmoothnessLoss / FlowSparsityLoss): see cdp_flow.h
 // ==========================================================================================
@@ -836,3 +879,23 @@ CDP_HD float cdp_disp_to_depth_grad(float g_depth, float depth, float span) { re
 // 10. Depth metrics (DepthEvaluator.compute_depth_metrics): see cdp_metrics.h
 // ==========================================================================================
 #include "cdp_metrics.h"
+
+// ==========================================================================================
+// 11. Fused heads (cdp_photo_heads): pose matrices in the pyramid launch, the chain back to the
+//     6-DoF parameters in the depth-gradient launch.
+// ==========================================================================================
+// item j in [0, 2*B): source k = j / B, sample b = j % B
+CDP_HD void cdp_pyr_pose_item(const CdpPyrParams& p, int j) {
+  const int k = j / p.B, b = j - k * p.B;
+  cdp_pose_fwd_sample(p.axisangle[k] + 3 * b, p.translation[k] + 3 * b, p.invert[k], p.pose_out[k] + 16 * b);
+}
+
+CDP_HD void cdp_pose_grad_heads(const CdpDepthGradParams& p, int j) {
+  const int k = j / p.B, b = j - k * p.B;
+  float gM[16];
+  const float go = CDP_LDG(p.grad_loss);
+  for (int i = 0; i < 16; ++i) gM[i] = go * p.pose_unit[((size_t)k * p.B + b) * 16 + i];
+  cdp_pose_bwd_sample(gM, p.axisangle[k] + 3 * b, p.translation[k] + 3 * b, p.invert[k], p.grad_axisangle[k] + 3 * b,
+                      p.grad_translation[k] + 3 * b);
+}
+

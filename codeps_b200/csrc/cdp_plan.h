@@ -28,7 +28,26 @@ static inline void cdp_fill_pyr_params(const CdpPlan& plan, const cdp_photo_args
   // aligned (a contiguous fp32 view with an odd storage offset is not), else the table path runs
   bool aligned = true;
   for (int t = 0; t < pp->nt; ++t) aligned = aligned && (reinterpret_cast<uintptr_t>(pp->in[t]) & 15) == 0;
+  if (a->heads && a->heads->disp) aligned = aligned && (reinterpret_cast<uintptr_t>(a->heads->disp) & 15) == 0;
   pp->fast1 = (plan.L > 1 && plan.W % 4 == 0 && plan.H % 2 == 0 && aligned) ? 1 : 0;
+  // fused heads: the pyramid launch converts the disparity (needs the level-1 fast path, whose
+  // items cover every full-resolution pixel exactly once) and builds the pose matrices
+  pp->B = plan.B;
+  if (a->heads) {
+    const cdp_photo_heads* hd = a->heads;
+    if (hd->disp && pp->fast1) {
+      pp->in[3] = hd->disp;
+      pp->depth_out = const_cast<float*>(a->depth);
+      pp->min_disp = 1.0f / hd->max_depth;
+      pp->disp_span = 1.0f / hd->min_depth - 1.0f / hd->max_depth;
+    }
+    if (hd->axisangle[0]) {
+      for (int k = 0; k < 2; ++k) {
+        pp->axisangle[k] = hd->axisangle[k]; pp->translation[k] = hd->translation[k]; pp->invert[k] = hd->invert[k];
+      }
+      pp->pose_out[0] = const_cast<float*>(a->pose0); pp->pose_out[1] = const_cast<float*>(a->pose1);
+    }
+  }
   int off = 0;
   pp->begin[0] = pp->begin[1] = 0;
   for (int s = 1; s < plan.L; ++s) {
@@ -118,6 +137,19 @@ static inline void cdp_fill_depth_grad_params(const CdpPlan& plan, const void* s
   p->grad_pose[0] = grad_pose0; p->grad_pose[1] = grad_pose1;
   p->B = plan.B; p->H = plan.H; p->W = plan.W; p->L = plan.L;
   p->scale_pose = 1;
+}
+
+// fused heads: dL/d disp instead of dL/d depth, dL/d (axis-angle, translation) instead of dL/dT
+static inline void cdp_depth_grad_params_heads(const cdp_photo_heads* hd, const float* depth, float* grad_axisangle0,
+                                               float* grad_translation0, float* grad_axisangle1,
+                                               float* grad_translation1, CdpDepthGradParams* p) {
+  p->depth_vals = depth;
+  p->disp_span = 1.0f / hd->min_depth - 1.0f / hd->max_depth;
+  for (int k = 0; k < 2; ++k) {
+    p->axisangle[k] = hd->axisangle[k]; p->translation[k] = hd->translation[k]; p->invert[k] = hd->invert[k];
+  }
+  p->grad_axisangle[0] = grad_axisangle0; p->grad_translation[0] = grad_translation0;
+  p->grad_axisangle[1] = grad_axisangle1; p->grad_translation[1] = grad_translation1;
 }
 
 // dL/d motion_k [B,3,H,W]: the same adjoint over 3B planes of the per-level motion gradients

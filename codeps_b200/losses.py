@@ -151,6 +151,35 @@ class ReconstructionLoss:
         if semantic_mask is not None:
             raise NotImplementedError("the semantic_mask branch (depth.py:284-292) is not taken by any "
                                       "caller in the reference and is not implemented")
+        noise, noise_event, intrinsics = self._prepare(camera_models, images, depth_map)
+        loss, self.last_argmin = ops.photometric_loss(
+            intrinsics, images, depth_map, poses, noise, self.num_scales,
+            self.alpha, seed=self.seed + self._calls, motions=object_motion_maps, noise_event=noise_event)
+        return loss
+
+    def forward_from_heads(self, camera_models: List[CameraModel], images: Tuple[Tensor, Tensor, Tensor],
+                           disparity_map: Tensor, pose_parameters: Tuple[Tuple[Tensor, Tensor], Tuple[Tensor, Tensor]],
+                           object_motion_maps: Optional[Tuple[Tensor, Tensor]] = None,
+                           min_depth: float = 0.1, max_depth: float = 100.0):
+        """Additive entry point: the loss on what the heads emit.
+
+        ``disparity_map`` is the depth head's sigmoid output (``DepthHead.disp_to_depth``,
+        /root/reference/models/depth_head.py:49-54, runs inside the op) and ``pose_parameters`` the
+        pose head's ((axisangle, translation) for t -> t-1, (axisangle, translation) for t -> t+1)
+        (``PoseHead.transformation_from_parameters``, /root/reference/models/pose_head.py:56-77,
+        runs inside the op; the first pair is inverted as at /root/reference/algos/depth.py:404-407).
+        Returns ``(loss, depth_map, (T0, T1))``; gradients go to the disparity and the 6-DoF
+        parameters directly, no conversion kernels or autograd nodes of their own in the step."""
+        assert len(camera_models) == images[0].shape[0], "Batch size of camera model does not match"
+        noise, noise_event, intrinsics = self._prepare(camera_models, images, disparity_map)
+        loss, self.last_argmin, depth, transformations = ops.photometric_loss_from_heads(
+            intrinsics, images, disparity_map, pose_parameters, noise, self.num_scales, self.alpha,
+            seed=self.seed + self._calls, min_depth=min_depth, max_depth=max_depth, motions=object_motion_maps,
+            noise_event=noise_event)
+        return loss, depth, transformations
+
+    def _prepare(self, camera_models, images, depth_map):
+        """Shape check, tie-break noise (drawn on a side stream) and intrinsics for one call."""
         h, w = images[0].shape[2], images[0].shape[3]
         if (w, h) != (self.scaled_width[0], self.scaled_height[0]):
             raise ValueError(f"images are {w}x{h} but this loss was built for "
@@ -159,7 +188,7 @@ class ReconstructionLoss:
         noise, noise_event = None, None
         if self.noise == "torch" and not depth_map.is_cuda:
             noise = [torch.randn((b, 2, self.scaled_height[s], self.scaled_width[s]), device=depth_map.device)
-                     for s in range(self.num_scales)]  # rejected below with the "CUDA only" error
+                     for s in range(self.num_scales)]  # rejected by the op with the "CUDA only" error
         elif self.noise == "torch":
             # drawn on a side stream so that the five randn kernels overlap the pyramid kernel (both
             # are independent and memory-bound); same generator, same call order, same values
@@ -179,10 +208,7 @@ class ReconstructionLoss:
         intrinsics = self._device_intrinsics(camera_models, depth_map.device)
         if intrinsics is None:
             intrinsics = self._level_intrinsics(camera_models)
-        loss, self.last_argmin = ops.photometric_loss(
-            intrinsics, images, depth_map, poses, noise, self.num_scales,
-            self.alpha, seed=self.seed + self._calls, motions=object_motion_maps, noise_event=noise_event)
-        return loss
+        return noise, noise_event, intrinsics
 
     _side_streams = {}
 

@@ -165,6 +165,154 @@ class _PhotometricLoss(torch.autograd.Function):
         return (grad_depth, grad_pose0, grad_pose1, gm0, gm1) + (None,) * 10
 
 
+class _PhotometricLossHeads(torch.autograd.Function):
+    """cdp_photo_fwd with cdp_photo_args.heads / cdp_photo_bwd_heads: the op takes the sigmoid
+    disparity and the 6-DoF pose parameters and returns gradients with respect to them; the depth
+    map and the two pose matrices come back as (non-differentiable) outputs."""
+
+    @staticmethod
+    def forward(ctx, disp, aa0, tr0, aa1, tr1, motion0, motion1, target, source0, source1, intrinsics, noise, seed,
+                num_levels, alpha, min_depth, max_depth, state, noise_event=None):
+        b, _, h, w = target.shape
+        device = target.device
+        lib = _lib_for(device)
+        need_grad = any(ctx.needs_input_grad[:7])
+        has_motion = motion0 is not None
+        tables = resize_tables(h, w, num_levels, device)
+        scratch = _bytes(lib.cdp_photo_scratch_bytes(b, h, w, num_levels, int(has_motion)), device)
+        saved = _bytes(lib.cdp_photo_saved_bytes(b, h, w, num_levels, int(has_motion)), device) if need_grad else None
+        loss = torch.empty(1, dtype=torch.float32, device=device)
+        depth = torch.empty(b, 1, h, w, dtype=torch.float32, device=device)
+        pose0 = torch.empty(b, 4, 4, dtype=torch.float32, device=device)
+        pose1 = torch.empty(b, 4, 4, dtype=torch.float32, device=device)
+        argmin = [torch.empty(b, h >> s, w >> s, dtype=torch.uint8, device=device) for s in range(num_levels)]
+        hd = _native.PhotoHeads()
+        hd.disp, hd.min_depth, hd.max_depth = disp.data_ptr(), float(min_depth), float(max_depth)
+        hd.axisangle[0], hd.axisangle[1] = aa0.data_ptr(), aa1.data_ptr()
+        hd.translation[0], hd.translation[1] = tr0.data_ptr(), tr1.data_ptr()
+        hd.invert[0], hd.invert[1] = 1, 0  # t -> t-1 is predicted in temporal order and inverted (algos/depth.py:404-407)
+        a = PhotoArgs()
+        a.batch, a.height, a.width, a.num_levels = b, h, w, num_levels
+        a.alpha, a.with_grad = float(alpha), int(need_grad)
+        if isinstance(intrinsics, torch.Tensor):
+            a.intrinsics_dev = intrinsics.data_ptr()
+        else:
+            a.intrinsics_host = intrinsics.ctypes.data
+        a.target, a.source0, a.source1 = target.data_ptr(), source0.data_ptr(), source1.data_ptr()
+        a.depth, a.pose0, a.pose1 = depth.data_ptr(), pose0.data_ptr(), pose1.data_ptr()
+        for s in range(num_levels):
+            a.noise[s] = noise[s].data_ptr() if noise is not None else None
+            a.argmin[s] = argmin[s].data_ptr()
+        a.noise_seed = int(seed)
+        if noise_event is not None:
+            a.noise_ready = noise_event.cuda_event
+        a.resize_tables = tables.data_ptr()
+        a.loss = loss.data_ptr()
+        a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
+        if need_grad:
+            a.saved, a.saved_bytes = saved.data_ptr(), saved.numel()
+        if has_motion:
+            a.motion0, a.motion1 = motion0.data_ptr(), motion1.data_ptr()
+        a.heads = ctypes.pointer(hd)
+        with torch.cuda.device(device):
+            check(lib.cdp_photo_fwd(ctypes.byref(a), _stream(device)), "cdp_photo_fwd")
+        _LAUNCHES["count"] += lib.cdp_photo_fwd_launches(b, num_levels)
+        state.argmin = argmin
+        ctx.shape = (b, h, w, num_levels)
+        ctx.saved_buf = saved
+        ctx.tables = tables
+        ctx.has_motion = has_motion
+        ctx.depth_range = (float(min_depth), float(max_depth))
+        ctx.save_for_backward(disp, aa0, tr0, aa1, tr1, depth)
+        ctx.mark_non_differentiable(depth, pose0, pose1)
+        return loss[0], depth, pose0, pose1
+
+    @staticmethod
+    def backward(ctx, grad_loss, _gd, _gp0, _gp1):
+        b, h, w, num_levels = ctx.shape
+        saved = ctx.saved_buf
+        if saved is None:
+            raise RuntimeError("photometric loss: backward called but no input required grad")
+        disp, aa0, tr0, aa1, tr1, depth = ctx.saved_tensors
+        device = saved.device
+        lib = _lib_for(device)
+        go = _require_cuda_f32(grad_loss.reshape(1), "grad_loss")
+        grad_disp = torch.empty_like(disp)
+        ga0, gt0, ga1, gt1 = (torch.empty_like(t) for t in (aa0, tr0, aa1, tr1))
+        gm0 = gm1 = None
+        if ctx.has_motion:
+            gm0 = torch.empty(b, 3, h, w, dtype=torch.float32, device=device)
+            gm1 = torch.empty(b, 3, h, w, dtype=torch.float32, device=device)
+        hd = _native.PhotoHeads()
+        hd.disp, hd.min_depth, hd.max_depth = disp.data_ptr(), ctx.depth_range[0], ctx.depth_range[1]
+        hd.axisangle[0], hd.axisangle[1] = aa0.data_ptr(), aa1.data_ptr()
+        hd.translation[0], hd.translation[1] = tr0.data_ptr(), tr1.data_ptr()
+        hd.invert[0], hd.invert[1] = 1, 0
+        with torch.cuda.device(device):
+            check(lib.cdp_photo_bwd_heads(b, h, w, num_levels, _ptr(saved), saved.numel(), _ptr(ctx.tables), _ptr(go),
+                                          ctypes.byref(hd), _ptr(depth), _ptr(grad_disp), _ptr(ga0), _ptr(gt0), _ptr(ga1),
+                                          _ptr(gt1), int(ctx.has_motion), _ptr(gm0), _ptr(gm1), _stream(device)),
+                  "cdp_photo_bwd_heads")
+        _LAUNCHES["count"] += lib.cdp_photo_bwd_launches(b, num_levels, int(ctx.has_motion))
+        return (grad_disp, ga0, gt0, ga1, gt1, gm0, gm1) + (None,) * 12
+
+
+def photometric_loss_from_heads(intrinsics, images: Sequence[torch.Tensor], disp: torch.Tensor,
+                                pose_params: Sequence[Tuple[torch.Tensor, torch.Tensor]],
+                                noise: Optional[Sequence[torch.Tensor]], num_levels: int, alpha: float = 0.85,
+                                seed: int = 0, min_depth: float = 0.1, max_depth: float = 100.0,
+                                motions: Optional[Sequence[torch.Tensor]] = None,
+                                noise_event: Optional[torch.cuda.Event] = None):
+    """The same loss taking what the network heads emit: ``disp`` [B,1,H,W] (sigmoid disparity,
+    models/depth_head.py:49-54) and ``pose_params`` = ((axis-angle, translation) for t -> t-1,
+    (axis-angle, translation) for t -> t+1), each [B,3] or [B,1,3] (models/pose_head.py:47-77;
+    the first pair is inverted like ``pose_head(feats, invert_pose=True)``, algos/depth.py:404-407).
+    Gradients flow to ``disp`` and the four parameter tensors directly; the conversions run inside
+    the pyramid / depth-gradient launches instead of as kernels (and autograd nodes) of their own.
+    Returns (loss, per-level argmin maps, depth [B,1,H,W], (T0, T1) [B,4,4])."""
+    target = _require_cuda_f32(images[0], "images[0]", (None, 3, None, None))
+    b, _, h, w = target.shape
+    source0 = _require_cuda_f32(images[1], "images[1]", (b, 3, h, w))
+    source1 = _require_cuda_f32(images[2], "images[2]", (b, 3, h, w))
+    disp = _require_cuda_f32(disp, "disparity_map", (b, 1, h, w))
+    if len(pose_params) != 2 or any(len(pp) != 2 for pp in pose_params):
+        raise ValueError("pose_params must be ((axisangle, translation), (axisangle, translation))")
+    flat = []
+    for k, (aa, tr) in enumerate(pose_params):
+        for name, t in (("axisangle", aa), ("translation", tr)):
+            if not (isinstance(t, torch.Tensor) and t.shape[0] == b and t.shape[-1] == 3 and t.numel() == 3 * b):
+                raise ValueError(f"pose_params[{k}] {name} must be [B,3] or [B,1,3], got {tuple(t.shape)}")
+            flat.append(_require_cuda_f32(t.reshape(b, 3), f"pose_params[{k}] {name}"))
+    for name, t in [("images[1]", source0), ("images[2]", source1), ("disparity_map", disp)] + [("pose_params", t) for t in flat]:
+        if t.device != target.device:
+            raise RuntimeError(f"{name} is on {t.device}, images[0] on {target.device}")
+    if not (min_depth > 0 and max_depth > min_depth):
+        raise ValueError("need 0 < min_depth < max_depth")
+    if isinstance(intrinsics, torch.Tensor):
+        intrinsics = _require_cuda_f32(intrinsics.detach(), "intrinsics", (b, 4))
+    else:
+        intrinsics = np.ascontiguousarray(intrinsics, dtype=np.float32)
+        if intrinsics.shape != (num_levels, b, 4):
+            raise ValueError(f"intrinsics has shape {intrinsics.shape}, expected {(num_levels, b, 4)}")
+    if not 1 <= num_levels <= _native.MAX_LEVELS:
+        raise ValueError(f"num_levels must be in [1, {_native.MAX_LEVELS}], got {num_levels}")
+    if noise is not None:
+        if len(noise) != num_levels:
+            raise ValueError(f"noise has {len(noise)} levels, expected {num_levels}")
+        noise = [_require_cuda_f32(n, f"noise[{s}]", (b, 2, h >> s, w >> s)) for s, n in enumerate(noise)]
+    motion0 = motion1 = None
+    if motions is not None:
+        if len(motions) != 2:
+            raise ValueError("object_motion_maps must hold one map per source frame")
+        motion0 = _require_cuda_f32(motions[0], "object_motion_maps[0]", (b, 3, h, w))
+        motion1 = _require_cuda_f32(motions[1], "object_motion_maps[1]", (b, 3, h, w))
+    state = PhotoState()
+    loss, depth, pose0, pose1 = _PhotometricLossHeads.apply(disp, flat[0], flat[1], flat[2], flat[3], motion0, motion1,
+                                                            target, source0, source1, intrinsics, noise, seed, num_levels,
+                                                            alpha, min_depth, max_depth, state, noise_event)
+    return loss, state.argmin, depth, (pose0, pose1)
+
+
 def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], depth: torch.Tensor,
                      poses: Sequence[torch.Tensor], noise: Optional[Sequence[torch.Tensor]],
                      num_levels: int, alpha: float = 0.85, seed: int = 0,

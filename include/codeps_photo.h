@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CDP_ABI_VERSION 4
+#define CDP_ABI_VERSION 5
 #define CDP_MAX_LEVELS 6           /* pyramid levels per call (reference uses 5) */
 #define CDP_MAX_BATCH_PER_LAUNCH 32 /* intrinsics travel in kernel-parameter (constant) space */
 
@@ -78,6 +78,20 @@ int cdp_resize_tables_build(int32_t height, int32_t width, int32_t num_levels, v
  * (algos/depth.py:128-155) and _compute_loss (algos/depth.py:221-237): multi-scale
  * min-reprojection with identity auto-mask.
  * ------------------------------------------------------------------------------------------- */
+/* Fused network-head conversions: the op takes what the heads emit --
+ * the sigmoid disparity (DepthHead.disp_to_depth, models/depth_head.py:49-54) and per source frame
+ * the 6-DoF pose parameters (PoseHead.transformation_from_parameters, models/pose_head.py:56-137,
+ * invert = 1 for the t -> t-1 pose) -- and returns gradients with respect to them.  The depth map
+ * and the two 4x4 matrices are still produced (DepthAlgo returns them): in this mode
+ * cdp_photo_args.depth / pose0 / pose1 are caller-owned OUTPUT buffers the library fills. */
+typedef struct cdp_photo_heads {
+  const float* disp;           /* [B,1,H,W] in (0,1) */
+  float min_depth, max_depth;  /* reference defaults 0.1, 100 */
+  const float* axisangle[2];   /* [B,3] per source frame */
+  const float* translation[2]; /* [B,3] per source frame */
+  int32_t invert[2];
+} cdp_photo_heads;
+
 typedef struct cdp_photo_args {
   int32_t batch, height, width; /* full resolution */
   int32_t num_levels;           /* level s has size (height >> s, width >> s) */
@@ -119,6 +133,8 @@ typedef struct cdp_photo_args {
    * reads the noise tensors.  Lets the caller produce the noise on another stream while the pyramid
    * kernel runs (both are memory-bound and independent). */
   void* noise_ready;
+  /* Optional: fused head conversions (see cdp_photo_heads); depth / pose0 / pose1 are then outputs. */
+  const cdp_photo_heads* heads;
 } cdp_photo_args;
 
 size_t cdp_photo_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels,
@@ -133,6 +149,16 @@ int cdp_photo_bwd(int32_t batch, int32_t height, int32_t width, int32_t num_leve
                   const void* saved, size_t saved_bytes, const void* resize_tables,
                   const float* grad_loss, float* grad_depth, float* grad_pose0, float* grad_pose1,
                   int32_t with_motion, float* grad_motion0, float* grad_motion1, cdp_stream_t stream);
+/* Backward of a forward call made with cdp_photo_args.heads: `depth` is the map that call wrote.
+ * Writes dL/d disp [B,1,H,W] and dL/d axis-angle / dL/d translation [B,3] per source frame (the
+ * chain through disp_to_depth and transformation_from_parameters is applied inside the same
+ * kernel that assembles dL/d depth and scales dL/dT). */
+int cdp_photo_bwd_heads(int32_t batch, int32_t height, int32_t width, int32_t num_levels,
+                        const void* saved, size_t saved_bytes, const void* resize_tables,
+                        const float* grad_loss, const cdp_photo_heads* heads, const float* depth,
+                        float* grad_disp, float* grad_axisangle0, float* grad_translation0,
+                        float* grad_axisangle1, float* grad_translation1,
+                        int32_t with_motion, float* grad_motion0, float* grad_motion1, cdp_stream_t stream);
 /* Number of kernels one cdp_photo_fwd / cdp_photo_bwd call launches (for launch accounting). */
 int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels);
 int cdp_photo_bwd_launches(int32_t batch, int32_t num_levels, int32_t with_motion);

@@ -61,9 +61,27 @@ static void emu_photo_block(const CdpPhotoParams& kp, int bx, int by) {
 EMU_API int emu_photo_fwd(const cdp_photo_args* a) {
   CdpPlan plan;
   if (!cdp_make_plan(a->batch, a->height, a->width, a->num_levels, &plan, a->motion0 != nullptr)) return CDP_ERR_INVALID;
+  // fused heads: the same fallbacks as cdp_photo_fwd where the pyramid launch cannot do the conversion
+  if (a->heads) {
+    const cdp_photo_heads* hd = a->heads;
+    CdpPyrParams probe;
+    if (plan.L > 1) cdp_fill_pyr_params(plan, a, &probe);
+    if (hd->disp && (plan.L == 1 || !probe.depth_out)) {
+      const float lo = 1.0f / hd->max_depth, span = 1.0f / hd->min_depth - lo;
+      float* out = const_cast<float*>(a->depth);
+      for (size_t i = 0; i < (size_t)plan.B * plan.H * plan.W; ++i) out[i] = cdp_disp_to_depth(hd->disp[i], lo, span);
+    }
+    if (hd->axisangle[0] && plan.L == 1)
+      for (int k = 0; k < 2; ++k)
+        for (int b = 0; b < plan.B; ++b)
+          cdp_pose_fwd_sample(hd->axisangle[k] + 3 * b, hd->translation[k] + 3 * b, hd->invert[k],
+                              const_cast<float*>(k == 0 ? a->pose0 : a->pose1) + 16 * b);
+  }
   if (plan.L > 1) {
     CdpPyrParams pp;
     cdp_fill_pyr_params(plan, a, &pp);
+    if (pp.pose_out[0])
+      for (int j = 0; j < 2 * pp.B; ++j) cdp_pyr_pose_item(pp, j);
     for (int b = 0; b < plan.B; ++b)
       for (int i = 0; i < pp.begin[plan.L]; ++i) cdp_pyramid_fwd_item(pp, b, i);
   }
@@ -117,6 +135,20 @@ EMU_API int emu_photo_bwd(int32_t b, int32_t h, int32_t w, int32_t l, const void
         for (int pix = 0; pix < h * w; ++pix) cdp_depth_grad_pixel(pm, i, pix);
     }
   }
+  return CDP_OK;
+}
+
+EMU_API int emu_photo_bwd_heads(int32_t b, int32_t h, int32_t w, int32_t l, const void* saved, const void* tables,
+                                const float* grad_loss, const cdp_photo_heads* heads, const float* depth, float* grad_disp,
+                                float* ga0, float* gt0, float* ga1, float* gt1) {
+  CdpPlan plan;
+  if (!cdp_make_plan(b, h, w, l, &plan, false)) return CDP_ERR_INVALID;
+  CdpDepthGradParams p;
+  cdp_fill_depth_grad_params(plan, saved, tables, grad_loss, grad_disp, nullptr, nullptr, &p);
+  cdp_depth_grad_params_heads(heads, depth, ga0, gt0, ga1, gt1, &p);
+  for (int i = 0; i < plan.B; ++i)
+    for (int pix = 0; pix < h * w; ++pix) cdp_depth_grad_pixel(p, i, pix);
+  for (int j = 0; j < 2 * plan.B; ++j) cdp_pose_grad_heads(p, j);
   return CDP_OK;
 }
 

@@ -118,6 +118,53 @@ def photo(level_intrinsics, images, depth, poses, noise, num_scales, alpha=0.85,
     return out
 
 
+def photo_from_heads(level_intrinsics, images, disp, pose_params, noise, num_scales, alpha=0.85, grad_loss=1.0,
+                     min_depth=0.1, max_depth=100.0):
+    """emu_photo_fwd with cdp_photo_args.heads + emu_photo_bwd_heads.  pose_params: ((aa0, t0), (aa1, t1)),
+    each [B,3]; the first pair is inverted."""
+    from codeps_b200._native import PhotoHeads
+    lib = load()
+    b, _, h, w = disp.shape
+    tgt, s0, s1 = (_f32(i) for i in images)
+    disp = _f32(disp)
+    flat = [_f32(t.reshape(b, 3)) for pair in pose_params for t in pair]
+    k = np.ascontiguousarray(level_intrinsics, dtype=np.float32)
+    tables = resize_tables(h, w, num_scales)
+    scratch = torch.zeros(lib.emu_photo_scratch_bytes(b, h, w, num_scales, 0), dtype=torch.uint8)
+    saved = torch.zeros(lib.emu_photo_saved_bytes(b, h, w, num_scales, 0), dtype=torch.uint8)
+    loss = torch.zeros(1)
+    depth = torch.zeros(b, 1, h, w)
+    p0, p1 = torch.zeros(b, 4, 4), torch.zeros(b, 4, 4)
+    argmin = [torch.full((b, h >> s, w >> s), 77, dtype=torch.uint8) for s in range(num_scales)]
+    noise = [_f32(n) for n in noise]
+    hd = PhotoHeads()
+    hd.disp, hd.min_depth, hd.max_depth = disp.data_ptr(), min_depth, max_depth
+    hd.axisangle[0], hd.translation[0], hd.axisangle[1], hd.translation[1] = (t.data_ptr() for t in flat)
+    hd.invert[0], hd.invert[1] = 1, 0
+    a = PhotoArgs()
+    a.batch, a.height, a.width, a.num_levels = b, h, w, num_scales
+    a.alpha, a.with_grad = alpha, 1
+    a.intrinsics_host = k.ctypes.data
+    a.target, a.source0, a.source1, a.depth = tgt.data_ptr(), s0.data_ptr(), s1.data_ptr(), depth.data_ptr()
+    a.pose0, a.pose1 = p0.data_ptr(), p1.data_ptr()
+    for s in range(num_scales):
+        a.noise[s] = noise[s].data_ptr()
+        a.argmin[s] = argmin[s].data_ptr()
+    a.resize_tables = tables.data_ptr()
+    a.loss = loss.data_ptr()
+    a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
+    a.saved, a.saved_bytes = saved.data_ptr(), saved.numel()
+    a.heads = ctypes.pointer(hd)
+    assert lib.emu_photo_fwd(ctypes.byref(a)) == 0
+    go = torch.tensor([grad_loss], dtype=torch.float32)
+    gdisp = torch.zeros_like(disp)
+    grads = [torch.zeros(b, 3) for _ in range(4)]
+    assert lib.emu_photo_bwd_heads(c_int32(b), c_int32(h), c_int32(w), c_int32(num_scales), _p(saved), _p(tables), _p(go),
+                                   ctypes.byref(hd), _p(depth), _p(gdisp), *(_p(g) for g in grads)) == 0
+    return {"recon": loss[0].clone(), "argmin": argmin, "depth": depth, "poses": [p0, p1], "grad_disp": gdisp,
+            "grad_pose_params": grads}
+
+
 def smooth(image, disp, with_grad=True, grad_loss=1.0):
     lib = load()
     b, _, h, w = disp.shape

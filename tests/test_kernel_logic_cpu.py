@@ -235,3 +235,43 @@ def test_emulated_taps_outside_the_staged_source_box():
         assert not ((out["argmin"][s] != ref["argmin"][s]) & decided).any()
     inp = dict(intrinsics=tb.intrinsics.numpy(), images=tb.images, depth=tb.depth, disp=tb.disp, poses=tb.poses, noise=noise)
     check_photo_grads(out, inp, scales, "taps outside the source box", level_intrinsics=list(k))
+
+
+@pytest.mark.parametrize("w,h,scales", [(64, 48, 3), (50, 34, 2), (40, 32, 1)])
+def test_emulated_fused_heads_equal_the_separate_conversions(w, h, scales):
+    """cdp_photo_args.heads: disparity and 6-DoF parameters in, gradients with
+    respect to them out.  Must equal the composition disp_to_depth / transformation_from_parameters
+    -> loss -> their backward: bit for bit where the pyramid launch does the conversion
+    (W % 4 == 0, even H, >= 2 levels), and through the fallback kernels otherwise."""
+    from codeps_b200 import synthetic
+    import codeps_b200
+    gen = torch.Generator().manual_seed(4)
+    tb = synthetic.make_batch(2, w, h, (0.9 * w, 0.95 * w, 0.5 * w, 0.5 * h), seed=12, shift_px=1)
+    noise = po.draw_noise(2, w, h, scales, seed=3)
+    k = codeps_b200.ReconstructionLoss(w, h, None, scales, "cpu")._level_intrinsics(tb.camera_models())
+    aa = [1e-2 * torch.randn(2, 3, generator=gen) for _ in range(2)]
+    tr = [torch.tensor([[-1.0 / (0.9 * w), 0.0, 0.0]]).repeat(2, 1) + 1e-3 * torch.randn(2, 3, generator=gen) for _ in range(2)]
+    fused = emu.photo_from_heads(k, tb.images, tb.disp, ((aa[0], tr[0]), (aa[1], tr[1])), noise, scales, grad_loss=2.5)
+    # the same through the stand-alone conversions
+    lo, span = 1.0 / 100.0, 1.0 / 0.1 - 1.0 / 100.0
+    depth = (1.0 / (np.float32(lo) + np.float32(span) * tb.disp)).float()
+    poses = [emu.pose(aa[0], tr[0], True), emu.pose(aa[1], tr[1], False)]
+    for got, want in zip(fused["poses"], poses):
+        assert torch.equal(got, want)
+    np.testing.assert_allclose(fused["depth"].numpy(), depth.numpy(), rtol=2e-7, atol=0)
+    sep = emu.photo(k, tb.images, fused["depth"], poses, noise, scales, grad_loss=2.5)
+    assert torch.equal(fused["recon"], sep["recon"])
+    assert all(torch.equal(a, b) for a, b in zip(fused["argmin"], sep["argmin"]))
+    want_gdisp = -(sep["grad_depth"] * np.float32(span) * fused["depth"] * fused["depth"])
+    np.testing.assert_allclose(fused["grad_disp"].numpy(), want_gdisp.numpy(), rtol=1e-6, atol=1e-12)
+    for kk in range(2):
+        _, ga, gt = emu.pose(aa[kk], tr[kk], kk == 0, grad_out=sep["grad_pose"][kk])
+        np.testing.assert_allclose(fused["grad_pose_params"][2 * kk].numpy(), ga.numpy(), rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(fused["grad_pose_params"][2 * kk + 1].numpy(), gt.numpy(), rtol=1e-5, atol=1e-9)
+    # and against the oracle: loss of the reference's own op sequence on the same head outputs
+    ref_depth = po.disp_to_depth(tb.disp.double())
+    ref_poses = [po.transformation_from_parameters(aa[0].double().view(2, 1, 3), tr[0].double().view(2, 1, 3), True),
+                 po.transformation_from_parameters(aa[1].double().view(2, 1, 3), tr[1].double().view(2, 1, 3), False)]
+    want = po.reconstruction_loss(tb.intrinsics.numpy(), [i.double() for i in tb.images], ref_depth, ref_poses, noise, scales,
+                                  level_intrinsics=list(k))
+    assert_loss_close(fused["recon"], want, "recon from heads", rtol=2e-5)
