@@ -231,26 +231,36 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
   float v[G ? 33 : 1];
 #pragma unroll
   for (int i = 0; i < (G ? 33 : 1); ++i) v[i] = 0.f;
-  if (p.lv[c.lvl].use_tma) {
-    // phase S by TMA: one thread arms the mbarrier with the byte count of the four boxes and
-    // issues them; every thread waits for the data to land
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + Geo::O_MBAR);
-    if (threadIdx.x == 0) cdp_mbar_init(bar, 1);
+  const bool tma = p.lv[c.lvl].use_tma != 0;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + Geo::O_MBAR);
+  CdpTileConst kc;
+  if (tma) {
+    // phase S by TMA: one thread arms the mbarriers with the byte counts and issues the four box
+    // loads; every thread waits for the data it needs next (barrier 0: depth + sources for phase A,
+    // barrier 1: target for phase B1) -- after fetching its own per-tile constants
+    if (threadIdx.x == 0) { cdp_mbar_init(bar, 1); cdp_mbar_init(bar + 1, 1); }
     __syncthreads();
     if (threadIdx.x == 0) {
-      cdp_mbar_expect_tx(bar, Geo::TMA_BYTES);
       const int ox = c.x0 - Geo::TXO, oy = c.y0 - Geo::TYO;  // (multiples of 4 in x: 16-byte aligned box starts)
+      cdp_mbar_expect_tx(bar, Geo::TMA_BYTES_A);
       cdp_tma_load_3d(sm + Geo::O_DEPTH, &tm.m[c.lvl][1], bar, ox, oy, c.b);
       cdp_tma_load_3d(sm + Geo::O_SRC, &tm.m[c.lvl][2], bar, ox - Geo::SBM, oy - Geo::SBM, c.b * 3);
       cdp_tma_load_3d(sm + Geo::O_SRC + Geo::SRC_STRIDE, &tm.m[c.lvl][3], bar, ox - Geo::SBM, oy - Geo::SBM, c.b * 3);
-      cdp_tma_load_3d(sm + Geo::O_TGT, &tm.m[c.lvl][0], bar, ox, oy, c.b * 3);
+      cdp_mbar_expect_tx(bar + 1, Geo::TMA_BYTES_TGT);
+      cdp_tma_load_3d(sm + Geo::O_TGT, &tm.m[c.lvl][0], bar + 1, ox, oy, c.b * 3);
     }
+    cdp_tile_const(p, c, kc);
     cdp_mbar_wait(bar, 0);
+    // (the reflected ring of the target box is written in phase A: needs the target box too on border tiles)
+    if (c.x0 == 0 || c.y0 == 0 || c.x0 - Geo::TXO + Geo::TBW > p.lv[c.lvl].W || c.y0 - Geo::TYO + Geo::TBH > p.lv[c.lvl].H)
+      cdp_mbar_wait(bar + 1, 0);
   } else {
+    cdp_tile_const(p, c, kc);
     cdp_photo_stage<G>(p, c, threadIdx.x, blockDim.x, sm);
     __syncthreads();
   }
-  cdp_photo_phase_a<G, M>(p, c, threadIdx.x, blockDim.x, sm);
+  cdp_photo_phase_a<G, M>(p, c, threadIdx.x, blockDim.x, sm, kc);
+  if (tma) cdp_mbar_wait(bar + 1, 0);
   __syncthreads();
   cdp_photo_phase_b1<G>(p, c, threadIdx.x, blockDim.x, sm, v[0]);
   if constexpr (G) {
@@ -263,20 +273,21 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
     // same bytes by a proxy fence on every thread + the block barrier.
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (p.lv[c.lvl].use_tma) {
-      uint64_t* bar = reinterpret_cast<uint64_t*>(sm + Geo::O_MBAR);
+    if (tma) {
       if (threadIdx.x == 0) {
         const int ox = c.x0 - Geo::TXO - Geo::SBM, oy = c.y0 - Geo::TYO - Geo::SBM;
         cdp_mbar_expect_tx(bar, (unsigned)(2 * 3 * Geo::SBN * sizeof(float)));
         cdp_tma_load_3d(sm + Geo::O_SRC, &tm.m[c.lvl][2], bar, ox, oy, c.b * 3);
         cdp_tma_load_3d(sm + Geo::O_SRC + Geo::SRC_STRIDE, &tm.m[c.lvl][3], bar, ox, oy, c.b * 3);
       }
-      cdp_mbar_wait(bar, 1);  // second use of the barrier: phase parity 1
+      cdp_tile_const(p, c, kc);  // (reloaded rather than kept in 38 registers through B1 / B2 / C1)
+      cdp_mbar_wait(bar, 1);     // second use of barrier 0: phase parity 1
     } else {
+      cdp_tile_const(p, c, kc);
       cdp_photo_restage_sources(p, c, threadIdx.x, blockDim.x, sm);
       __syncthreads();
     }
-    cdp_photo_phase_c2<M>(p, c, threadIdx.x, blockDim.x, sm, &v[1]);
+    cdp_photo_phase_c2<M>(p, c, threadIdx.x, blockDim.x, sm, &v[1], kc);
   }
   v[0] *= p.lv[c.lvl].weight;
   float* rec = p.partials + ((size_t)c.b * p.blocks_per_image + blockIdx.x) * CDP_PARTIAL_STRIDE;

@@ -69,9 +69,12 @@ struct CdpTileGeom {
   static constexpr int O_COEF = O_SRC;
   static constexpr int SRC_FLOATS = (SRC_STRIDE + 3 * SBN > 9 * TBN) ? SRC_STRIDE + 3 * SBN : 9 * TBN;
   static constexpr int O_K = align32(O_SRC + SRC_FLOATS);        // winner bytes [TBN]
-  static constexpr int O_MBAR = O_K + align32((TBN + 3) / 4);    // one 8-byte mbarrier
+  static constexpr int O_MBAR = O_K + align32((TBN + 3) / 4);    // two 8-byte mbarriers
   static constexpr size_t SMEM_BYTES = (size_t)(O_MBAR + 4) * sizeof(float);
-  static constexpr unsigned TMA_BYTES = (unsigned)((3 * TBN + TBN + 2 * 3 * SBN) * sizeof(float));
+  // barrier 0: depth + both source boxes (what phase A reads; re-armed for the sources before C2);
+  // barrier 1: target box (first read in phase B1)
+  static constexpr unsigned TMA_BYTES_A = (unsigned)((TBN + 2 * 3 * SBN) * sizeof(float));
+  static constexpr unsigned TMA_BYTES_TGT = (unsigned)(3 * TBN * sizeof(float));
   // The B1/B2 strip walk always reads CDP_STRIP + 2 rows, also for the last, partial strip: the
   // rows past the box belong to the following plane (values discarded); in the source boxes they
   // must stay inside the margin rows.
@@ -104,6 +107,21 @@ CDP_HD CdpCam cdp_tile_cam(const CdpPhotoParams& p, const CdpTileCtx& c) {
   // per-level intrinsics table (rows are 16-byte aligned)
   const float4 k = CDP_LDG(reinterpret_cast<const float4*>(p.K_tab) + (size_t)c.lvl * p.batch_total + c.b);
   return cdp_make_cam(k.x, k.y, k.z, k.w);
+}
+
+// Per-tile constants of the warp: intrinsics of (level, sample) and both poses, lane-packed.  Loaded
+// by the kernel BEFORE it waits for the TMA boxes, so that these global-memory round trips overlap
+// the box loads instead of following them.
+struct CdpTileConst {
+  CdpCam cam;
+  CdpPose2 T;
+};
+CDP_HD void cdp_tile_const(const CdpPhotoParams& p, const CdpTileCtx& c, CdpTileConst& k) {
+  k.cam = cdp_tile_cam(p, c);
+  CdpPose t0, t1;
+  cdp_load_pose_aligned(p.pose0 + (size_t)c.b * 16, t0);  // cdp_photo_fwd requires 16-byte aligned poses
+  cdp_load_pose_aligned(p.pose1 + (size_t)c.b * 16, t1);
+  cdp_pack_pose(t0, t1, k.T);
 }
 
 // Entry (level s, sample b) of the per-level intrinsics table: the scaling of
@@ -226,7 +244,8 @@ CDP_HD float2 cdp_lerp2(float2 nw, float2 ne, float2 sw, float2 se, float2 fx, f
 }
 
 template <bool G, bool M>
-CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm) {
+CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm,
+                              const CdpTileConst& kc) {
   typedef CdpTileGeom<G> Geo;
   const CdpLevel& lv = p.lv[c.lvl];
   const int W = lv.W, H = lv.H;
@@ -240,14 +259,8 @@ CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int 
                      W, H, tid, nthreads);
   }
   // 2. warp + gather
-  const CdpCam cam = cdp_tile_cam(p, c);
-  CdpPose2 T;
-  {
-    CdpPose t0, t1;
-    cdp_load_pose_aligned(p.pose0 + (size_t)c.b * 16, t0);  // cdp_photo_fwd requires 16-byte aligned poses
-    cdp_load_pose_aligned(p.pose1 + (size_t)c.b * 16, t1);
-    cdp_pack_pose(t0, t1, T);
-  }
+  const CdpCam& cam = kc.cam;
+  const CdpPose2& T = kc.T;
   const float* src0 = lv.src0 + (size_t)c.b * 3 * plane;
   const float* src1 = lv.src1 + (size_t)c.b * 3 * plane;
   const float* sdepth = sm + Geo::O_DEPTH;
@@ -698,19 +711,13 @@ CDP_HD void cdp_photo_phase_c1(const CdpPhotoParams& p, const CdpTileCtx& c, int
 // dL/d depth_s (written) and dL/dT (accumulated), both sources in the two lanes of packed fp32.
 template <bool M>
 CDP_HD void cdp_photo_phase_c2(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads,
-                               const float* sm, float* dT /*[32]: source-major 4x4 blocks*/) {
+                               const float* sm, float* dT /*[32]: source-major 4x4 blocks*/, const CdpTileConst& kc) {
   typedef CdpTileGeom<true> Geo;
   const CdpLevel& lv = p.lv[c.lvl];
   const int W = lv.W, H = lv.H;
   const size_t plane = (size_t)W * H;
-  const CdpCam cam = cdp_tile_cam(p, c);
-  CdpPose2 T;
-  {
-    CdpPose t0, t1;
-    cdp_load_pose_aligned(p.pose0 + (size_t)c.b * 16, t0);
-    cdp_load_pose_aligned(p.pose1 + (size_t)c.b * 16, t1);
-    cdp_pack_pose(t0, t1, T);
-  }
+  const CdpCam& cam = kc.cam;
+  const CdpPose2& T = kc.T;
   const float* src0 = lv.src0 + (size_t)c.b * 3 * plane;
   const float* src1 = lv.src1 + (size_t)c.b * 3 * plane;
   const float* sbox0 = sm + Geo::O_SRC;

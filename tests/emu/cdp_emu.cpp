@@ -42,13 +42,15 @@ static void emu_photo_block(const CdpPhotoParams& kp, int bx, int by) {
   std::vector<float> v((size_t)nt * 33, 0.f);
   // phase S: the box fill the GPU does with TMA (zero fill outside the image), here with plain loads
   for (int t = 0; t < nt; ++t) cdp_photo_stage<G>(kp, c, t, nt, sm.data());
-  for (int t = 0; t < nt; ++t) cdp_photo_phase_a<G, M>(kp, c, t, nt, sm.data());
+  CdpTileConst kc;
+  cdp_tile_const(kp, c, kc);
+  for (int t = 0; t < nt; ++t) cdp_photo_phase_a<G, M>(kp, c, t, nt, sm.data(), kc);
   for (int t = 0; t < nt; ++t) cdp_photo_phase_b1<G>(kp, c, t, nt, sm.data(), v[(size_t)t * 33]);
   if (G) {
     for (int t = 0; t < nt; ++t) cdp_photo_phase_b2(kp, c, t, nt, sm.data());
     for (int t = 0; t < nt; ++t) cdp_photo_phase_c1(kp, c, t, nt, sm.data());
     for (int t = 0; t < nt; ++t) cdp_photo_restage_sources(kp, c, t, nt, sm.data());
-    for (int t = 0; t < nt; ++t) cdp_photo_phase_c2<M>(kp, c, t, nt, sm.data(), &v[(size_t)t * 33 + 1]);
+    for (int t = 0; t < nt; ++t) cdp_photo_phase_c2<M>(kp, c, t, nt, sm.data(), &v[(size_t)t * 33 + 1], kc);
   }
   float* rec = kp.partials + ((size_t)c.b * kp.blocks_per_image + bx) * CDP_PARTIAL_STRIDE;
   for (int j = 0; j < 33; ++j) {
