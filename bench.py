@@ -83,6 +83,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other configurations")
+    ap.add_argument("--shift-px", type=int, default=3,
+                    help="pixel shift between the synthetic frames (the pose explains it). The tile kernel serves "
+                         "bilinear footprints within 4-6 px of the pixel from shared memory and the rest from global memory")
     return ap.parse_args()
 
 
@@ -186,11 +189,14 @@ def global_triplets(workload: str, world: int) -> int:
     return total if spec["mode"] == "global" else total * world
 
 
+SHIFT_PX = {"value": 3}  # pixel shift between the synthetic frames (--shift-px)
+
+
 def make_group_batch(preset, batch, flip, seed, offset=0):
     """`batch` triplets of a preset; with `flip`, samples with odd GLOBAL index get the mirrored
     principal point (replay samples, datasets/preprocessing.py:47-52)."""
     from codeps_b200 import synthetic
-    tb = synthetic.make_preset_batch(preset, batch, seed=seed)
+    tb = synthetic.make_preset_batch(preset, batch, seed=seed, shift_px=SHIFT_PX["value"])
     if flip:
         k = tb.intrinsics.clone()
         odd = (torch.arange(batch) + offset) % 2 == 1
@@ -440,6 +446,7 @@ def main():
         return
 
     spec = WORKLOADS[args.workload]
+    SHIFT_PX["value"] = args.shift_px
     use_graph = not args.no_graph
     wl = LossWorkload(args.workload, rank, world, dev, noise=args.noise, intrinsics=args.intrinsics)
     preset = spec["groups"][0][0]
@@ -520,6 +527,12 @@ def main():
         extras["workloads"] = {}
         for name in EXTRA_WORKLOADS:
             extras["workloads"][name] = run_extra_workload(name, rank, world, dev, timed, use_graph)
+        # sensitivity to the image motion: 12 px instead of 3 px between the frames puts every level-0
+        # footprint outside the staged source boxes (global-memory taps), levels >= 2 stay inside
+        SHIFT_PX["value"] = 12
+        extras["workloads"]["cityscapes_b8_shift12px"] = run_extra_workload("cityscapes_b8", rank, world, dev, timed, use_graph)
+        extras["workloads"]["cityscapes_b8_shift12px"]["description"] += "; frames shifted by 12 px instead of 3"
+        SHIFT_PX["value"] = args.shift_px
         extras["torch_cuda_eager"] = run_torch_cuda_eager(args.workload, rank, world, dev, timed, value)
         try:
             import bench_adapt
@@ -557,7 +570,7 @@ def main():
                        "intrinsics": args.intrinsics, "overlap_smooth": bool(args.overlap_smooth),
                        "timed_with": "cuda_graph_replay" if use_graph else "eager_launches",
                        "l2": f"{wl.input_sets} rotating input sets, {wl.resident_bytes / 1e6:.0f} MB resident > 126 MB L2",
-                       "loss_weights": [RECON_WEIGHT, SMOOTH_WEIGHT]},
+                       "loss_weights": [RECON_WEIGHT, SMOOTH_WEIGHT], "shift_px": args.shift_px},
             "clocks": clocks.summary(),
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,
