@@ -524,6 +524,22 @@ def main():
 
     # ---- the other configurations BASELINE.json names, as short runs
     if not args.no_extras and args.workload == "cityscapes_b8":
+        import gc
+
+        def fresh():  # every extra starts from an empty caching allocator (they differ wildly in block sizes)
+            gc.collect()
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+
+        fresh()
+        try:
+            import bench_adapt
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.warmup = 12, 4
+            extras["adapt_step"] = bench_adapt.run(sub, rank, world, dev, barrier, max_over_ranks, brief=True)
+        except Exception as exc:  # e.g. torchvision missing
+            extras["adapt_step"] = {"unavailable": repr(exc)}
+        fresh()
         extras["workloads"] = {}
         for name in EXTRA_WORKLOADS:
             extras["workloads"][name] = run_extra_workload(name, rank, world, dev, timed, use_graph)
@@ -533,14 +549,8 @@ def main():
         extras["workloads"]["cityscapes_b8_shift12px"] = run_extra_workload("cityscapes_b8", rank, world, dev, timed, use_graph)
         extras["workloads"]["cityscapes_b8_shift12px"]["description"] += "; frames shifted by 12 px instead of 3"
         SHIFT_PX["value"] = args.shift_px
+        fresh()
         extras["torch_cuda_eager"] = run_torch_cuda_eager(args.workload, rank, world, dev, timed, value)
-        try:
-            import bench_adapt
-            sub = argparse.Namespace(**vars(args))
-            sub.steps, sub.warmup = 12, 3
-            extras["adapt_step"] = bench_adapt.run(sub, rank, world, dev, barrier, max_over_ranks, brief=True)
-        except Exception as exc:  # e.g. torchvision missing
-            extras["adapt_step"] = {"unavailable": repr(exc)}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu_baseline = None

@@ -177,7 +177,7 @@ def run(args, rank, world, dev, barrier, max_over_ranks, brief: bool = False):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)) / steps, (time.perf_counter() - t0) * 1e3 / steps, float(last)
 
-    steps, warmup = (args.steps, max(args.warmup, 3)) if not brief else (max(4, min(args.steps, 12)), 3)
+    steps, warmup = (args.steps, max(args.warmup, 3)) if not brief else (max(4, min(args.steps, 12)), max(args.warmup, 3))
     ms_none, _, _ = timed("none", steps, warmup)
     ms_ours, wall_ours, loss_ours = timed("ours", steps, warmup)
     ms_ref, wall_ref, loss_ref = timed("reference", max(3, steps // 2), 2)

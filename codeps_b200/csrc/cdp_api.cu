@@ -222,6 +222,15 @@ __device__ __forceinline__ void cdp_tma_load_3d(void* dst, const CUtensorMap* ma
       : "memory");
 }
 
+__device__ __forceinline__ void cdp_tma_prefetch_3d(const CUtensorMap* map, int x, int y, int z) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+#ifndef CDP_OPT_L2_PREFETCH
+#define CDP_OPT_L2_PREFETCH 296  // CTAs ahead whose boxes are prefetched into L2 (0 = off); one wave of 2 x 148 (measured: -0.4 %)
+#endif
+
 template <bool G, bool M>
 __global__ void __launch_bounds__(CDP_PHOTO_THREADS, CDP_PHOTO_MIN_CTAS)
 cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant__ CdpTmaMaps tm) {
@@ -249,6 +258,24 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
       cdp_mbar_expect_tx(bar + 1, Geo::TMA_BYTES_TGT);
       cdp_tma_load_3d(sm + Geo::O_TGT, &tm.m[c.lvl][0], bar + 1, ox, oy, c.b * 3);
     }
+#if CDP_OPT_L2_PREFETCH > 0
+    if (threadIdx.x == 32) {
+      // the boxes of the tile that will start about two waves from now: L2 prefetch, so that its
+      // TMA loads find them in L2 instead of paying the DRAM latency inside its mbarrier wait
+      const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x + CDP_OPT_L2_PREFETCH;
+      const unsigned fy = lin / gridDim.x, fx = lin - fy * gridDim.x;
+      if (fy < gridDim.y) {
+        const CdpTileCtx f = cdp_tile_ctx(p, (int)fx, (int)fy);
+        if (p.lv[f.lvl].use_tma) {
+          const int ox = f.x0 - Geo::TXO, oy = f.y0 - Geo::TYO;
+          cdp_tma_prefetch_3d(&tm.m[f.lvl][1], ox, oy, f.b);
+          cdp_tma_prefetch_3d(&tm.m[f.lvl][2], ox - Geo::SBM, oy - Geo::SBM, f.b * 3);
+          cdp_tma_prefetch_3d(&tm.m[f.lvl][3], ox - Geo::SBM, oy - Geo::SBM, f.b * 3);
+          cdp_tma_prefetch_3d(&tm.m[f.lvl][0], ox, oy, f.b * 3);
+        }
+      }
+    }
+#endif
     cdp_tile_const(p, c, kc);
     cdp_mbar_wait(bar, 0);
     // (the reflected ring of the target box is written in phase A: needs the target box too on border tiles)

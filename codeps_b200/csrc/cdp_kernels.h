@@ -124,15 +124,27 @@ struct CdpFinalizeParams {
 // Block 0 additionally strides over ALL records' loss entries into sm[1024 + tid].
 CDP_HD void cdp_finalize_phase_a(const CdpFinalizeParams& p, int b, int tid, double* sm) {
   const int r = tid >> 5, j = tid & 31;
-  double acc = 0.0;
-  for (int blk = r; blk < p.blocks_per_image; blk += 32)
-    acc += (double)p.partials[((size_t)b * p.blocks_per_image + blk) * CDP_PARTIAL_STRIDE + 1 + j];
-  sm[r * 32 + j] = acc;
+  // four independent accumulators (records r, r+32, r+64, r+96 of every group of 128): the loads of
+  // one group are in flight together instead of one L2 round trip per record; combined in a fixed order
+  const float* rec = p.partials + (size_t)b * p.blocks_per_image * CDP_PARTIAL_STRIDE + 1 + j;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (int blk = r; blk < p.blocks_per_image; blk += 128) {
+    const float v0 = rec[(size_t)blk * CDP_PARTIAL_STRIDE];
+    const float v1 = blk + 32 < p.blocks_per_image ? rec[(size_t)(blk + 32) * CDP_PARTIAL_STRIDE] : 0.f;
+    const float v2 = blk + 64 < p.blocks_per_image ? rec[(size_t)(blk + 64) * CDP_PARTIAL_STRIDE] : 0.f;
+    const float v3 = blk + 96 < p.blocks_per_image ? rec[(size_t)(blk + 96) * CDP_PARTIAL_STRIDE] : 0.f;
+    a0 += (double)v0; a1 += (double)v1; a2 += (double)v2; a3 += (double)v3;
+  }
+  sm[r * 32 + j] = (a0 + a1) + (a2 + a3);
   if (b == 0) {
-    double lacc = 0.0;
+    double l0 = 0.0, l1 = 0.0;
     const int total = p.B * p.blocks_per_image;
-    for (int i = tid; i < total; i += CDP_FINALIZE_THREADS) lacc += (double)p.partials[(size_t)i * CDP_PARTIAL_STRIDE];
-    sm[1024 + tid] = lacc;
+    for (int i = tid; i < total; i += 2 * CDP_FINALIZE_THREADS) {
+      const float v0 = p.partials[(size_t)i * CDP_PARTIAL_STRIDE];
+      const float v1 = i + CDP_FINALIZE_THREADS < total ? p.partials[(size_t)(i + CDP_FINALIZE_THREADS) * CDP_PARTIAL_STRIDE] : 0.f;
+      l0 += (double)v0; l1 += (double)v1;
+    }
+    sm[1024 + tid] = l0 + l1;
   }
 }
 // step 2: combine in index order; threads 0..31 own one pose-gradient column, threads 32..63 of
