@@ -75,7 +75,8 @@ class ReconstructionLoss:
 
     ``object_motion_maps`` (two [B,3,H,W] maps, depth.py:296-303 -> image_warper.py:133-134) are
     resized with the images, added to the transformed points inside the tile kernel, and receive
-    their gradient; ``semantic_mask`` (depth.py:284-292, no caller) raises NotImplementedError.
+    their gradient; ``semantic_mask`` (depth.py:284-292, no caller in the reference) is served by a
+    composition of the stand-alone nearest-warp and SSIM kernels (``_semantic_loss``).
 
     Additive surface (not in the reference, which discards the argmin at depth.py:323):
     ``last_argmin`` -- per level a uint8 [B,H_s,W_s] map, 0/1 = reprojection from t-1/t+1 won,
@@ -149,13 +150,37 @@ class ReconstructionLoss:
                  semantic_mask: Optional[Tuple[Tensor, Tensor, Tensor]] = None) -> Tensor:
         assert len(camera_models) == images[0].shape[0], "Batch size of camera model does not match"
         if semantic_mask is not None:
-            raise NotImplementedError("the semantic_mask branch (depth.py:284-292) is not taken by any "
-                                      "caller in the reference and is not implemented")
+            return self._semantic_loss(camera_models, depth_map, poses, semantic_mask)
         noise, noise_event, intrinsics = self._prepare(camera_models, images, depth_map)
         loss, self.last_argmin = ops.photometric_loss(
             intrinsics, images, depth_map, poses, noise, self.num_scales,
             self.alpha, seed=self.seed + self._calls, motions=object_motion_maps, noise_event=noise_event)
         return loss
+
+    def _semantic_loss(self, camera_models, depth_map, poses, semantic_mask) -> Tensor:
+        """The ``semantic_mask`` branch (/root/reference/algos/depth.py:284-292,307-308): label maps
+        [B,H,W] of frames t, t-1, t+1; per level nearest resize, nearest-neighbour warp of the two
+        neighbouring maps (``cdp_warp_image_fwd``), SSIM (``cdp_ssim_fwd``) + L1 against the target
+        map, mean over both candidates and all pixels -- no min-reprojection, no auto-mask.  No
+        caller in the reference takes it; a nearest-neighbour warp has a zero coordinate gradient,
+        so the value carries no gradient to depth or pose (as in the reference)."""
+        import torch.nn.functional as F
+        if not depth_map.is_cuda:
+            raise RuntimeError("codeps_b200 is CUDA only: depth_map is on the CPU (there is no CPU fallback)")
+        loss = torch.zeros((), dtype=torch.float32, device=depth_map.device)
+        for s in range(self.num_scales):
+            size = (self.scaled_height[s], self.scaled_width[s])
+            cams = [cam.get_scaled_model_image_size(self.scaled_width[s], self.scaled_height[s]) for cam in camera_models]
+            depth_s = F.interpolate(depth_map, size, mode="bilinear", align_corners=False)
+            target = F.interpolate(semantic_mask[0].unsqueeze(1).float(), size, mode="nearest")
+            terms = []
+            for i, frame in enumerate(semantic_mask[1:]):
+                frame_s = F.interpolate(frame.unsqueeze(1).float(), size, mode="nearest")
+                pred = self.image_warpers[s](cams, frame_s, depth_s, poses[i], interp_mode="nearest")
+                l1 = torch.abs(pred - target).mean(1, True)
+                terms.append(self.alpha * self.ssim(pred, target).mean(1, True) + (1 - self.alpha) * l1)
+            loss = loss + torch.cat(terms, 1).mean() / (2 ** s)
+        return loss / self.num_scales
 
     def forward_from_heads(self, camera_models: List[CameraModel], images: Tuple[Tensor, Tensor, Tensor],
                            disparity_map: Tensor, pose_parameters: Tuple[Tuple[Tensor, Tensor], Tuple[Tensor, Tensor]],

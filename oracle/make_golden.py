@@ -260,6 +260,28 @@ CASES = {
 }
 
 
+def semantic_fixture(ref_depth, ref_misc, out_dir):
+    """ReconstructionLoss.__call__ with semantic_mask (algos/depth.py:284-292,307-308): label maps of
+    the three frames, nearest resize + nearest warp, SSIM + L1 of the label values, no auto-mask."""
+    from codeps_b200.synthetic import make_batch
+    b, w, h, scales = 2, 96, 64, 3
+    batch = make_batch(b, w, h, (100.0, 101.0, 47.0, 31.5), seed=77, shift_px=2, flip_every_other=True)
+    gen = torch.Generator().manual_seed(78)
+    # piecewise-constant label maps (blocks of 8x8 pixels), shifted like the images
+    coarse = torch.randint(0, 19, (b, h // 8, w // 8), generator=gen)
+    lbl_t = coarse.repeat_interleave(8, 1).repeat_interleave(8, 2)
+    labels = (lbl_t, torch.roll(lbl_t, 2, dims=2), torch.roll(lbl_t, -2, dims=2))
+    cams = [ref_misc.CameraModel.from_tensor(w, h, k) for k in batch.intrinsics]
+    loss_fn = ref_depth.ReconstructionLoss(w, h, ref_depth.SSIMLoss(), scales, torch.device("cpu"))
+    loss = loss_fn(cams, batch.images, batch.depth, list(batch.poses), None, labels)
+    blob = {"width": w, "height": h, "num_scales": scales, "depth": batch.depth.numpy(), "pose0": batch.poses[0].numpy(),
+            "pose1": batch.poses[1].numpy(), "intrinsics": batch.intrinsics.numpy(),
+            "labels": torch.stack(labels).numpy(), "loss": np.float64(loss.item())}
+    path = os.path.join(out_dir, "semantic.npz")
+    np.savez_compressed(path, **blob)
+    print(f"semantic -> {path} loss={loss.item():.9f} ({os.path.getsize(path) / 1e3:.1f} kB)")
+
+
 def main():
     from codeps_b200.synthetic import make_batch
     from oracle.photo_oracle import draw_noise
@@ -271,6 +293,7 @@ def main():
     flow_fixture(ref_depth, out_dir)
     c2c_fixture(ref_misc, out_dir)
     metrics_fixture(out_dir)
+    semantic_fixture(ref_depth, ref_misc, out_dir)
     if "--heads-only" in sys.argv or "--small-only" in sys.argv:
         return
     for name, (b, w, h, k, scales, seed, noise_seed, kw) in CASES.items():

@@ -199,6 +199,28 @@ def reconstruction_loss(intrinsics, images: Sequence[torch.Tensor], depth: torch
     return (loss, per_level) if details else loss
 
 
+def semantic_reconstruction_loss(intrinsics, labels: Sequence[torch.Tensor], depth: torch.Tensor,
+                                 poses: Sequence[torch.Tensor], num_scales: int = 5, alpha: float = 0.85,
+                                 level_intrinsics=None) -> torch.Tensor:
+    """The semantic_mask branch of ReconstructionLoss.__call__ (algos/depth.py:284-292,307-308,325-326):
+    label maps [B,H,W] of frames t, t-1, t+1; per level nearest resize, nearest-neighbour warp of the
+    two neighbouring maps, _compute_loss against the target map, mean over both and all pixels."""
+    b, _, h, w = depth.shape
+    total = torch.zeros(1, dtype=depth.dtype, device=depth.device)
+    for s in range(num_scales):
+        hs, ws = h // 2**s, w // 2**s
+        k = level_intrinsics[s] if level_intrinsics is not None else scaled_intrinsics(intrinsics, (w, h), (ws, hs))
+        depth_s = F.interpolate(depth, (hs, ws), mode="bilinear", align_corners=False)
+        tgt = F.interpolate(labels[0].unsqueeze(1).to(depth.dtype), (hs, ws), mode="nearest")
+        terms = []
+        for i in range(2):
+            frame = F.interpolate(labels[1 + i].unsqueeze(1).to(depth.dtype), (hs, ws), mode="nearest")
+            pred = warp_image(frame, depth_s, poses[i], k, mode="nearest")
+            terms.append(alpha * ssim_loss_map(pred, tgt).mean(1, True) + (1 - alpha) * (pred - tgt).abs().mean(1, True))
+        total = total + torch.cat(terms, 1).mean() / 2**s
+    return total[0] / num_scales
+
+
 def smoothness_loss(target_image: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
     """EdgeAwareSmoothnessLoss.__call__ (algos/depth.py:58-107)."""
     mean_disp = disp.mean(2, True).mean(3, True)

@@ -35,6 +35,14 @@ for (w, h, b, scales) in ((132, 70, 2, 5), (64, 32, 3, 4)):
     aa = (0.01 * torch.randn(b, 1, 3, generator=gen)).to(dev).requires_grad_(True)
     tr = (0.1 * torch.randn(b, 1, 3, generator=gen)).to(dev).requires_grad_(True)
     (codeps_b200.transformation_from_parameters(aa, tr, True).sum() + codeps_b200.disp_to_depth(disp).sum()).backward()
+    # fused heads entry (disparity + 6-DoF parameters in, gradients w.r.t. them out) and the semantic_mask branch
+    aa2 = [(0.01 * torch.randn(b, 1, 3, generator=gen)).to(dev).requires_grad_(True) for _ in range(2)]
+    tr2 = [(0.02 * torch.randn(b, 1, 3, generator=gen)).to(dev).requires_grad_(True) for _ in range(2)]
+    disp2 = tb.disp.clone().requires_grad_(True)
+    l4, _depth, _poses = fn.forward_from_heads(tb.camera_models(), tb.images, disp2, ((aa2[0], tr2[0]), (aa2[1], tr2[1])))
+    l4.backward()
+    labels = tuple(torch.randint(0, 19, (b, h, w), generator=gen).to(dev) for _ in range(3))
+    fn(tb.camera_models(), tb.images, tb.depth, tb.poses, None, labels)
     tgt = torch.zeros(b, 3, h + 6, w + 10, device=dev)
     lbl = torch.randint(0, 9, (b, h, w), generator=gen).to(dev)
     cams_t = [codeps_b200.CameraModel(w + 10, h + 6, 0.7 * w, 0.7 * w, 0.5 * w + 3, 0.5 * h + 2) for _ in range(b)]
