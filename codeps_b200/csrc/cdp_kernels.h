@@ -57,21 +57,29 @@ CDP_HD void cdp_pyramid_fwd_item(const CdpPyrParams& p, int b, int item) {
     for (int t = 0; t < 6; ++t) {
       if (t >= p.nt) break;
       const int ch = t == 3 ? 1 : 3;
-      for (int c = 0; c < ch; ++c) {
+      // all loads of a tensor are issued before the first use (six 16-byte loads in flight per thread)
+      float4 a[3], d[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (c >= ch) break;
         const float* src = p.in[t] + ((size_t)b * ch + c) * in_plane;
-        float4 a = CDP_LDG(reinterpret_cast<const float4*>(src + o0));
-        float4 d = CDP_LDG(reinterpret_cast<const float4*>(src + o1));
+        a[c] = CDP_LDG(reinterpret_cast<const float4*>(src + o0));
+        d[c] = CDP_LDG(reinterpret_cast<const float4*>(src + o1));
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (c >= ch) break;
         if (t == 3 && p.depth_out) {  // disparity in, depth out (full resolution) and resized
-          a.x = cdp_disp_to_depth(a.x, p.min_disp, p.disp_span); a.y = cdp_disp_to_depth(a.y, p.min_disp, p.disp_span);
-          a.z = cdp_disp_to_depth(a.z, p.min_disp, p.disp_span); a.w = cdp_disp_to_depth(a.w, p.min_disp, p.disp_span);
-          d.x = cdp_disp_to_depth(d.x, p.min_disp, p.disp_span); d.y = cdp_disp_to_depth(d.y, p.min_disp, p.disp_span);
-          d.z = cdp_disp_to_depth(d.z, p.min_disp, p.disp_span); d.w = cdp_disp_to_depth(d.w, p.min_disp, p.disp_span);
-          *reinterpret_cast<float4*>(p.depth_out + (size_t)b * in_plane + o0) = a;
-          *reinterpret_cast<float4*>(p.depth_out + (size_t)b * in_plane + o1) = d;
+          a[c].x = cdp_disp_to_depth(a[c].x, p.min_disp, p.disp_span); a[c].y = cdp_disp_to_depth(a[c].y, p.min_disp, p.disp_span);
+          a[c].z = cdp_disp_to_depth(a[c].z, p.min_disp, p.disp_span); a[c].w = cdp_disp_to_depth(a[c].w, p.min_disp, p.disp_span);
+          d[c].x = cdp_disp_to_depth(d[c].x, p.min_disp, p.disp_span); d[c].y = cdp_disp_to_depth(d[c].y, p.min_disp, p.disp_span);
+          d[c].z = cdp_disp_to_depth(d[c].z, p.min_disp, p.disp_span); d[c].w = cdp_disp_to_depth(d[c].w, p.min_disp, p.disp_span);
+          *reinterpret_cast<float4*>(p.depth_out + (size_t)b * in_plane + o0) = a[c];
+          *reinterpret_cast<float4*>(p.depth_out + (size_t)b * in_plane + o1) = d[c];
         }
         float2 r;
-        r.x = (a.x * 0.5f + a.y * 0.5f) * 0.5f + (d.x * 0.5f + d.y * 0.5f) * 0.5f;
-        r.y = (a.z * 0.5f + a.w * 0.5f) * 0.5f + (d.z * 0.5f + d.w * 0.5f) * 0.5f;
+        r.x = (a[c].x * 0.5f + a[c].y * 0.5f) * 0.5f + (d[c].x * 0.5f + d[c].y * 0.5f) * 0.5f;
+        r.y = (a[c].z * 0.5f + a[c].w * 0.5f) * 0.5f + (d[c].z * 0.5f + d[c].w * 0.5f) * 0.5f;
         *reinterpret_cast<float2*>(p.out[t][s] + ((size_t)b * ch + c) * out_plane + y * ws + x) = r;
       }
     }
@@ -86,15 +94,22 @@ CDP_HD void cdp_pyramid_fwd_item(const CdpPyrParams& p, int b, int item) {
   for (int t = 0; t < 6; ++t) {
     if (t >= p.nt) break;
     const int ch = t == 3 ? 1 : 3;
-    for (int c = 0; c < ch; ++c) {
+    float v00[3], v01[3], v10[3], v11[3];  // (all taps of a tensor requested before the first use)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c >= ch) break;
       const float* src = p.in[t] + ((size_t)b * ch + c) * in_plane;
-      float v00 = CDP_LDG(src + o00), v01 = CDP_LDG(src + o01), v10 = CDP_LDG(src + o10), v11 = CDP_LDG(src + o11);
+      v00[c] = CDP_LDG(src + o00); v01[c] = CDP_LDG(src + o01); v10[c] = CDP_LDG(src + o10); v11[c] = CDP_LDG(src + o11);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c >= ch) break;
       if (t == 3 && p.depth_out) {  // the taps are disparities: resize the depth they stand for
-        v00 = cdp_disp_to_depth(v00, p.min_disp, p.disp_span); v01 = cdp_disp_to_depth(v01, p.min_disp, p.disp_span);
-        v10 = cdp_disp_to_depth(v10, p.min_disp, p.disp_span); v11 = cdp_disp_to_depth(v11, p.min_disp, p.disp_span);
+        v00[c] = cdp_disp_to_depth(v00[c], p.min_disp, p.disp_span); v01[c] = cdp_disp_to_depth(v01[c], p.min_disp, p.disp_span);
+        v10[c] = cdp_disp_to_depth(v10[c], p.min_disp, p.disp_span); v11[c] = cdp_disp_to_depth(v11[c], p.min_disp, p.disp_span);
       }
-      const float top = v00 * tx.w0 + v01 * tx.w1;
-      const float bot = v10 * tx.w0 + v11 * tx.w1;
+      const float top = v00[c] * tx.w0 + v01[c] * tx.w1;
+      const float bot = v10[c] * tx.w0 + v11[c] * tx.w1;
       p.out[t][s][((size_t)b * ch + c) * out_plane + local] = top * ty.w0 + bot * ty.w1;
     }
   }
