@@ -34,6 +34,21 @@
 #ifndef CDP_STRIP
 #define CDP_STRIP 5  // pixels per thread strip in phases B1/B2
 #endif
+#ifndef CDP_OPT_SSIM_RAW
+#define CDP_OPT_SSIM_RAW 0  // phase B1: SSIM ratio from the raw window sums (9 instead of 13 packed operations per pair)
+#endif
+#ifndef CDP_OPT_SSIM_RAW_B2
+#define CDP_OPT_SSIM_RAW_B2 1  // phase B2: adjoint coefficients from the raw window sums
+#endif
+#ifndef CDP_OPT_NOISE_LATE
+#define CDP_OPT_NOISE_LATE 1  // phase B1: 1 = tie-break noise loaded after the strip walk instead of before it
+#endif
+#ifndef CDP_EXP_A_SKIP_TAIL
+#define CDP_EXP_A_SKIP_TAIL 0  // timing experiment only (wrong results): phase A drops its ragged last iteration
+#endif
+#ifndef CDP_OPT_INTERIOR
+#define CDP_OPT_INTERIOR 1  // tiles whose source boxes lie inside the image skip the reflection / border-clip logic
+#endif
 #ifndef CDP_SRC_MARGIN
 #define CDP_SRC_MARGIN 4  // gather margin of the staged source boxes (pixels beyond the target box)
 #endif
@@ -243,6 +258,42 @@ CDP_HD float2 cdp_lerp2(float2 nw, float2 ne, float2 sw, float2 se, float2 fx, f
   return cdp_fma2(fy, cdp_fma2(top, neg1, bot), top);
 }
 
+// Tap cell of one axis when the border clip is known to be inactive (see cdp_tile_interior):
+// box-relative lower tap index and fraction; the same values cdp_tap_axis_full produces there.
+CDP_HD void cdp_tap_axis_interior(int rel, float d, int& b0, float& frac) {
+  const float fl = floorf(d);
+  b0 = rel + (int)fl;
+  frac = d - fl;
+}
+
+// A tile is "interior" when its source boxes lie inside [1, n-2] on both axes.  Then every staged
+// position is an image pixel (no reflection), and a 2x2 footprint that lies inside the box has its
+// lower tap in [1, n-3], i.e. the sample position is strictly inside (0, n-1): the border clip of
+// grid_sample and the clamps of cdp_tap_axis_full are no-ops and the gradient mask is 1.  Footprints
+// that leave the box (and NaN displacements, whose integer conversion is 0) take the general path.
+template <bool G>
+CDP_HD bool cdp_tile_interior(const CdpLevel& lv, const CdpTileCtx& c) {
+  typedef CdpTileGeom<G> Geo;
+  const int box_x = c.x0 - Geo::TXO - Geo::SBM, box_y = c.y0 - Geo::TYO - Geo::SBM;
+  return CDP_OPT_INTERIOR && box_x >= 1 && box_y >= 1 && box_x + Geo::SBW <= lv.W - 1 && box_y + Geo::SBH <= lv.H - 1;
+}
+
+// Both sources' tap cells relative to the source boxes; returns true when both footprints lie
+// inside the boxes (interior tiles only).
+template <bool G>
+CDP_HD bool cdp_taps_interior(int relx, int rely, const CdpWarp2& w, int& bx0, int& by0, int& bx1, int& by1,
+                              float2& fx, float2& fy) {
+  typedef CdpTileGeom<G> Geo;
+  cdp_tap_axis_interior(relx, w.dx.x, bx0, fx.x);
+  cdp_tap_axis_interior(rely, w.dy.x, by0, fy.x);
+  cdp_tap_axis_interior(relx, w.dx.y, bx1, fx.y);
+  cdp_tap_axis_interior(rely, w.dy.y, by1, fy.y);
+  const float2 t = cdp_add2(fx, fy);
+  const bool finite = t.x + t.y >= 0.f;  // false for NaN
+  return finite && (unsigned)bx0 <= (unsigned)(Geo::SBW - 2) && (unsigned)by0 <= (unsigned)(Geo::SBH - 2) &&
+         (unsigned)bx1 <= (unsigned)(Geo::SBW - 2) && (unsigned)by1 <= (unsigned)(Geo::SBH - 2);
+}
+
 template <bool G, bool M>
 CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm,
                               const CdpTileConst& kc) {
@@ -267,12 +318,16 @@ CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int 
   const float* sbox0 = sm + Geo::O_SRC;
   const float* sbox1 = sm + Geo::O_SRC + Geo::SRC_STRIDE;
   const int box_x = ox - Geo::SBM, box_y = oy - Geo::SBM;  // image position of source box element (0, 0)
-  for (int idx = tid; idx < Geo::RN; idx += nthreads) {
+  const bool interior = cdp_tile_interior<G>(lv, c);
+  for (int idx = tid; idx < (CDP_EXP_A_SKIP_TAIL ? Geo::RN / 256 * 256 : Geo::RN); idx += nthreads) {
     const int ry = idx / Geo::RW, rx = idx - ry * Geo::RW;
     const int tx = rx + Geo::OFFX, ty = ry + Geo::OFFY;
     const int px = ox + tx, py = oy + ty;
-    if (px < -1 || px > W || py < -1 || py > H) continue;  // never read
-    const int u = cdp_reflect(px, W), v = cdp_reflect(py, H);
+    int u = px, v = py;
+    if (!interior) {
+      if (px < -1 || px > W || py < -1 || py > H) continue;  // never read
+      u = cdp_reflect(px, W); v = cdp_reflect(py, H);
+    }
     const float depth = sdepth[(v - oy) * Geo::TBW + u - ox];
     float2 mo[3];
     if (M) {  // object-motion maps (make_sflow): added to the transformed point
@@ -289,16 +344,21 @@ CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int 
       if (!w.regular[0]) cdp_warp_lane_literal(0, (float)u, (float)v, depth, cam, T, M ? mo : nullptr, w);
       if (!w.regular[1]) cdp_warp_lane_literal(1, (float)u, (float)v, depth, cam, T, M ? mo : nullptr, w);
     }
-    int ax0, ay0, ax1, ay1;
+    int ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0, bx0, by0, bx1, by1;
     float2 fx, fy;
-    float unused;
-    cdp_tap_axis_full(u, w.dx.x, w.ix.x, W, ax0, fx.x, unused);
-    cdp_tap_axis_full(v, w.dy.x, w.iy.x, H, ay0, fy.x, unused);
-    cdp_tap_axis_full(u, w.dx.y, w.ix.y, W, ax1, fx.y, unused);
-    cdp_tap_axis_full(v, w.dy.y, w.iy.y, H, ay1, fy.y, unused);
-    const int bx0 = ax0 - box_x, by0 = ay0 - box_y, bx1 = ax1 - box_x, by1 = ay1 - box_y;
-    const bool in0 = (unsigned)bx0 <= (unsigned)(Geo::SBW - 2) && (unsigned)by0 <= (unsigned)(Geo::SBH - 2);
-    const bool in1 = (unsigned)bx1 <= (unsigned)(Geo::SBW - 2) && (unsigned)by1 <= (unsigned)(Geo::SBH - 2);
+    bool in0, in1;
+    if (interior && cdp_taps_interior<G>(tx + Geo::SBM, ty + Geo::SBM, w, bx0, by0, bx1, by1, fx, fy)) {
+      in0 = in1 = true;
+    } else {
+      float unused;
+      cdp_tap_axis_full(u, w.dx.x, w.ix.x, W, ax0, fx.x, unused);
+      cdp_tap_axis_full(v, w.dy.x, w.iy.x, H, ay0, fy.x, unused);
+      cdp_tap_axis_full(u, w.dx.y, w.ix.y, W, ax1, fx.y, unused);
+      cdp_tap_axis_full(v, w.dy.y, w.iy.y, H, ay1, fy.y, unused);
+      bx0 = ax0 - box_x; by0 = ay0 - box_y; bx1 = ax1 - box_x; by1 = ay1 - box_y;
+      in0 = (unsigned)bx0 <= (unsigned)(Geo::SBW - 2) && (unsigned)by0 <= (unsigned)(Geo::SBH - 2);
+      in1 = (unsigned)bx1 <= (unsigned)(Geo::SBW - 2) && (unsigned)by1 <= (unsigned)(Geo::SBH - 2);
+    }
     const int ti = ty * Geo::TBW + tx;
     if (in0 && in1) {
       // both 2x2 footprints lie inside the staged source boxes: 24 shared-memory loads at
@@ -362,21 +422,62 @@ CDP_HD void cdp_row_pair(const float2 x[3], const float y[3], CdpRowPair& o) {
 
 // SSIM loss of a candidate pair from the 3x3 sums of strip-centred values (algos/depth.py:141-153).
 // ct = constant that turns strip-centred values back into true image values (means only).
-CDP_HD float2 cdp_ssim_pair_loss(float2 sx, float2 sxx, float2 sxy, float sy, float syy, float ct) {
+//
+// The second factor n2 / d2 = (2 cov + C2) / (var_x + var_y + C2) is a ratio, so it is formed from the
+// raw sums scaled by 81 instead of from means and variances:
+//     81 (2 cov + C2)          = 18 Sxy - 2 Sx Sy + 81 C2
+//    -81 (var_x + var_y + C2)  = Sx^2 - 9 Sxx + (Sy^2 - 9 Syy - 81 C2)
+// (two FMAs each, the same cancellation as E[x^2] - mean^2 with one rounding fewer; the minus sign
+// of the denominator is undone in the final FMA).  9 packed operations per pair instead of 13.
+#if CDP_OPT_SSIM_RAW
+struct CdpSsimTgt {  // target-side terms shared by the two candidate pairs of a pixel
+  float two_my, myy_c1, m2sy, nkd;
+};
+CDP_HD void cdp_ssim_tgt(float sy, float syy, float ct, CdpSsimTgt& o) {
+  const float my = cdp_fmaf(sy, 1.0f / 9.0f, ct);
+  o.two_my = my + my;
+  o.myy_c1 = cdp_fmaf(my, my, CDP_SSIM_C1);
+  o.m2sy = -2.0f * sy;
+  o.nkd = cdp_fmaf(sy, sy, cdp_fmaf(syy, -9.0f, -81.0f * CDP_SSIM_C2));
+}
+CDP_HD float2 cdp_ssim_pair_loss(float2 sx, float2 sxx, float2 sxy, const CdpSsimTgt& t, float ct) {
+  const float2 mx = cdp_fma2(sx, cdp_set2(1.0f / 9.0f), cdp_set2(ct));
+  const float2 n1 = cdp_fma2(mx, cdp_set2(t.two_my), cdp_set2(CDP_SSIM_C1));
+  const float2 d1 = cdp_fma2(mx, mx, cdp_set2(t.myy_c1));
+  const float2 n2 = cdp_fma2(sx, cdp_set2(t.m2sy), cdp_fma2(sxy, cdp_set2(18.0f), cdp_set2(81.0f * CDP_SSIM_C2)));
+  const float2 nd2 = cdp_fma2(sx, sx, cdp_fma2(sxx, cdp_set2(-9.0f), cdp_set2(t.nkd)));
+  const float2 num = cdp_mul2(n1, n2), nden = cdp_mul2(d1, nd2);
+  float2 nS;  // -SSIM
+  nS.x = cdp_fdiv(num.x, nden.x);
+  nS.y = cdp_fdiv(num.y, nden.y);
+  float2 l;  // clamp((1 - S) / 2, 0, 1): one saturating FMA per lane (NaN -> 0 like fmin(fmax(NaN, 0), 1))
+  l.x = cdp_saturate(cdp_fmaf(nS.x, 0.5f, 0.5f));
+  l.y = cdp_saturate(cdp_fmaf(nS.y, 0.5f, 0.5f));
+  return l;
+}
+#else
+// (means / variances form: 13 packed operations per pair)
+struct CdpSsimTgt {
+  float myc, vy_c2, two_my, myy_c1;
+};
+CDP_HD void cdp_ssim_tgt(float sy, float syy, float ct, CdpSsimTgt& o) {
   const float ninth = 1.0f / 9.0f;
-  const float2 n9 = cdp_set2(ninth);
+  o.myc = sy * ninth;
+  o.vy_c2 = (syy * ninth - o.myc * o.myc) + CDP_SSIM_C2;
+  const float my = o.myc + ct;
+  o.two_my = 2.0f * my;
+  o.myy_c1 = my * my + CDP_SSIM_C1;
+}
+CDP_HD float2 cdp_ssim_pair_loss(float2 sx, float2 sxx, float2 sxy, const CdpSsimTgt& t, float ct) {
+  const float2 n9 = cdp_set2(1.0f / 9.0f);
   const float2 mxc = cdp_mul2(sx, n9);
-  const float myc = sy * ninth;
-  const float vy_c2 = (syy * ninth - myc * myc) + CDP_SSIM_C2;
-  const float my = myc + ct;
-  const float myy_c1 = my * my + CDP_SSIM_C1;
   const float2 mx = cdp_add2(mxc, cdp_set2(ct));
   const float2 vx = cdp_fma2(cdp_mul2(mxc, mxc), cdp_set2(-1.0f), cdp_mul2(sxx, n9));
-  const float2 cov = cdp_fma2(mxc, cdp_set2(-myc), cdp_mul2(sxy, n9));
-  const float2 n1 = cdp_fma2(mx, cdp_set2(2.0f * my), cdp_set2(CDP_SSIM_C1));
+  const float2 cov = cdp_fma2(mxc, cdp_set2(-t.myc), cdp_mul2(sxy, n9));
+  const float2 n1 = cdp_fma2(mx, cdp_set2(t.two_my), cdp_set2(CDP_SSIM_C1));
   const float2 n2 = cdp_fma2(cov, cdp_set2(2.0f), cdp_set2(CDP_SSIM_C2));
-  const float2 d1 = cdp_fma2(mx, mx, cdp_set2(myy_c1));
-  const float2 d2 = cdp_add2(vx, cdp_set2(vy_c2));
+  const float2 d1 = cdp_fma2(mx, mx, cdp_set2(t.myy_c1));
+  const float2 d2 = cdp_add2(vx, cdp_set2(t.vy_c2));
   const float2 num = cdp_mul2(n1, n2), den = cdp_mul2(d1, d2);
   float2 S;
   S.x = cdp_fdiv(num.x, den.x);
@@ -386,6 +487,7 @@ CDP_HD float2 cdp_ssim_pair_loss(float2 sx, float2 sxx, float2 sxy, float sy, fl
   l.y = cdp_saturate(cdp_fmaf(S.y, -0.5f, 0.5f));
   return l;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Phase B1: candidate losses, noise, min / argmin (algos/depth.py:294-323)
@@ -413,6 +515,7 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
     const bool col_ok = qx >= 0 && qx < W;
     // tie-break noise of the strip's pixels, requested early so the loads overlap the strip walk
     float2 nz[CDP_STRIP];
+#if !CDP_OPT_NOISE_LATE
 #pragma unroll
     for (int o = 0; o < CDP_STRIP; ++o) {
       const int qy = qy0 + o;
@@ -423,6 +526,7 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
         nz[o].y = CDP_LDG(lv.noise + ((size_t)c.b * 2 + 1) * nplane + qy * W + qx);
       }
     }
+#endif
     const int qc = qy0 + CDP_STRIP / 2 < 0 ? 0 : (qy0 + CDP_STRIP / 2 > H - 1 ? H - 1 : qy0 + CDP_STRIP / 2);
     const int cs_idx = (qc - c.y0 + Geo::TYO) * Geo::TBW + bx + 1 + Geo::OFFX;
     if (col_ok && qy0 < H && qy0 + CDP_STRIP > 0) {
@@ -461,13 +565,14 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
           cdp_row_pair(w, y, hw[r % 3]);
           if (r >= 2) {
             const int o = r - 2;  // output row: window rows r-2, r-1, r; centre row r-1
-            const float sy = hy[0].s + hy[1].s + hy[2].s, syy = hy[0].ss + hy[1].ss + hy[2].ss;
+            CdpSsimTgt st;
+            cdp_ssim_tgt(hy[0].s + hy[1].s + hy[2].s, hy[0].ss + hy[1].ss + hy[2].ss, cs, st);
             const float2 l_id = cdp_ssim_pair_loss(cdp_add2(cdp_add2(hs[0].s, hs[1].s), hs[2].s),
                                                    cdp_add2(cdp_add2(hs[0].ss, hs[1].ss), hs[2].ss),
-                                                   cdp_add2(cdp_add2(hs[0].sy, hs[1].sy), hs[2].sy), sy, syy, cs);
+                                                   cdp_add2(cdp_add2(hs[0].sy, hs[1].sy), hs[2].sy), st, cs);
             const float2 l_pe = cdp_ssim_pair_loss(cdp_add2(cdp_add2(hw[0].s, hw[1].s), hw[2].s),
                                                    cdp_add2(cdp_add2(hw[0].ss, hw[1].ss), hw[2].ss),
-                                                   cdp_add2(cdp_add2(hw[0].sy, hw[1].sy), hw[2].sy), sy, syy, cs);
+                                                   cdp_add2(cdp_add2(hw[0].sy, hw[1].sy), hw[2].sy), st, cs);
             float2 d_id = cdp_add2(sc_prev, cdp_set2(-yc_prev)), d_pe = cdp_add2(wc_prev, cdp_set2(-yc_prev));
             d_id.x = fabsf(d_id.x); d_id.y = fabsf(d_id.y);
             d_pe.x = fabsf(d_pe.x); d_pe.y = fabsf(d_pe.y);
@@ -478,6 +583,19 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
         }
       }
     }
+#if CDP_OPT_NOISE_LATE
+    // (all loads of the strip issued together, after the walk: ten registers fewer live through it)
+#pragma unroll
+    for (int o = 0; o < CDP_STRIP; ++o) {
+      const int qy = qy0 + o;
+      nz[o] = cdp_set2(0.f);
+      if (lv.noise && col_ok && qy >= 0 && qy < H && by0 + o < Geo::BH) {
+        const size_t nplane = (size_t)W * H;
+        nz[o].x = CDP_LDG(lv.noise + ((size_t)c.b * 2 + 0) * nplane + qy * W + qx);
+        nz[o].y = CDP_LDG(lv.noise + ((size_t)c.b * 2 + 1) * nplane + qy * W + qx);
+      }
+    }
+#endif
     // min-reprojection with identity auto-mask for the strip's pixels
 #pragma unroll
     for (int o = 0; o < CDP_STRIP; ++o) {
@@ -505,6 +623,30 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
       if (G) kplane[ridx] = (uint8_t)kb;
     }
   }
+}
+
+// SSIM adjoint coefficients (cdp_ssim_terms + cdp_ssim_coeffs_abc of cdp_math.h) from the raw 3x3
+// sums of values centred on c, for values measured in the frame centred on `centre`:
+//     d loss(q) / d x(p) = m/9 * (A + 2 (x(p) - centre) B + (y(p) - centre) C).
+// n2 / d2 is formed from the sums scaled by 81 as in cdp_ssim_pair_loss; 1 / d2 = 81 / D2.
+CDP_HD void cdp_ssim_abc_raw(float sx, float sxx, float sxy, float sy, float syy, float c, float centre,
+                             float& A, float& B, float& C) {
+  const float ninth = 1.0f / 9.0f;
+  const float mx = cdp_fmaf(sx, ninth, c), my = cdp_fmaf(sy, ninth, c);  // true means
+  const float n1 = cdp_fmaf(mx + mx, my, CDP_SSIM_C1);
+  const float d1 = cdp_fmaf(mx, mx, cdp_fmaf(my, my, CDP_SSIM_C1));
+  const float N2 = cdp_fmaf(sx, -2.0f * sy, cdp_fmaf(sxy, 18.0f, 81.0f * CDP_SSIM_C2));
+  const float D2 = cdp_fmaf(-sx, sx, cdp_fmaf(sxx, 9.0f, cdp_fmaf(-sy, sy, cdp_fmaf(syy, 9.0f, 81.0f * CDP_SSIM_C2))));
+  const float id1 = cdp_rcp(d1), iD2 = cdp_rcp(D2);
+  const float r1 = n1 * id1, r2 = N2 * iD2;  // the two SSIM factors
+  const float S = r1 * r2;
+  const float raw = cdp_fmaf(S, -0.5f, 0.5f);
+  const float g = (raw >= 0.f && raw <= 1.f) ? 40.5f * iD2 : 0.f;  // -dl / d2 (clamp gradient is inclusive), dl = -0.5
+  B = g * S;                  // dl * (-S / d2)
+  C = -2.0f * (g * r1);       // dl * 2 n1 / (d1 d2)
+  const float h = (raw >= 0.f && raw <= 1.f) ? -id1 : 0.f;  // 2 dl / d1
+  const float A1 = h * cdp_fmaf(my, r2, -(mx * S));
+  A = cdp_fmaf(-2.0f * (mx - centre), B, cdp_fmaf(-(my - centre), C, A1));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -537,7 +679,6 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
       const float* ty = sm + Geo::O_TGT + ch * Geo::TBN;
       const float2* tw = cdp_warp_plane<true>(sm, ch);
       const float cs = ty[cs_idx];
-      const float csc = cs - centre[ch];  // strip constant in the tile-centred frame
       const float2 cs2 = cdp_set2(-cs);
       CdpRowTgt hy[3];
       CdpRowPair hw[3];
@@ -557,10 +698,15 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
           const int o = r - 2;
           if (kk[o] < 2) {
             const bool first = kk[o] == 0;
-            const float ninth = 1.0f / 9.0f;
             const float2 sx2 = cdp_add2(cdp_add2(hw[0].s, hw[1].s), hw[2].s);
             const float2 sxx2 = cdp_add2(cdp_add2(hw[0].ss, hw[1].ss), hw[2].ss);
             const float2 sxy2 = cdp_add2(cdp_add2(hw[0].sy, hw[1].sy), hw[2].sy);
+            float A, B, C;
+#if CDP_OPT_SSIM_RAW_B2
+            cdp_ssim_abc_raw(first ? sx2.x : sx2.y, first ? sxx2.x : sxx2.y, first ? sxy2.x : sxy2.y,
+                             hy[0].s + hy[1].s + hy[2].s, hy[0].ss + hy[1].ss + hy[2].ss, cs, centre[ch], A, B, C);
+#else
+            const float ninth = 1.0f / 9.0f;
             const float mxc = (first ? sx2.x : sx2.y) * ninth;
             const float exx = (first ? sxx2.x : sxx2.y) * ninth;
             const float exy = (first ? sxy2.x : sxy2.y) * ninth;
@@ -568,9 +714,10 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
             const float eyy = (hy[0].ss + hy[1].ss + hy[2].ss) * ninth;
             CdpSsimTerms t;
             cdp_ssim_terms(mxc, myc, exx, eyy, exy, cs, t);
-            float A, B, C;
             // means in the tile-centred frame are mxc + csc, myc + csc
+            const float csc = cs - centre[ch];  // strip constant in the tile-centred frame
             cdp_ssim_coeffs_abc(t, mxc + csc, myc + csc, A, B, C);
+#endif
             const int ridx = r00 + o * Geo::TBW;
             sm[Geo::O_COEF + (ch * 3 + 0) * Geo::TBN + ridx] = A;
             sm[Geo::O_COEF + (ch * 3 + 1) * Geo::TBN + ridx] = B;
@@ -723,6 +870,7 @@ CDP_HD void cdp_photo_phase_c2(const CdpPhotoParams& p, const CdpTileCtx& c, int
   const float* sbox0 = sm + Geo::O_SRC;
   const float* sbox1 = sm + Geo::O_SRC + Geo::SRC_STRIDE;
   const int box_x = c.x0 - Geo::TXO - Geo::SBM, box_y = c.y0 - Geo::TYO - Geo::SBM;
+  const bool interior = cdp_tile_interior<true>(lv, c);
   float2 dT2[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) dT2[i] = cdp_set2(0.f);
@@ -757,15 +905,21 @@ CDP_HD void cdp_photo_phase_c2(const CdpPhotoParams& p, const CdpTileCtx& c, int
     }
     CdpWarp2 w;
     cdp_warp_point2((float)px, (float)py, depth, cam, T, M ? mo : nullptr, w);
-    int ax0, ay0, ax1, ay1;
+    int ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0, bx0, by0, bx1, by1;
     float2 fx, fy, mx, my;
-    cdp_tap_axis_full(px, w.dx.x, w.ix.x, W, ax0, fx.x, mx.x);
-    cdp_tap_axis_full(py, w.dy.x, w.iy.x, H, ay0, fy.x, my.x);
-    cdp_tap_axis_full(px, w.dx.y, w.ix.y, W, ax1, fx.y, mx.y);
-    cdp_tap_axis_full(py, w.dy.y, w.iy.y, H, ay1, fy.y, my.y);
-    const int bx0 = ax0 - box_x, by0 = ay0 - box_y, bx1 = ax1 - box_x, by1 = ay1 - box_y;
-    const bool in0 = (unsigned)bx0 <= (unsigned)(Geo::SBW - 2) && (unsigned)by0 <= (unsigned)(Geo::SBH - 2);
-    const bool in1 = (unsigned)bx1 <= (unsigned)(Geo::SBW - 2) && (unsigned)by1 <= (unsigned)(Geo::SBH - 2);
+    bool in0, in1;
+    if (interior && cdp_taps_interior<true>(lx + Geo::TXO + Geo::SBM, ly + Geo::TYO + Geo::SBM, w, bx0, by0, bx1, by1, fx, fy)) {
+      in0 = in1 = true;
+      mx = my = cdp_set2(1.0f);
+    } else {
+      cdp_tap_axis_full(px, w.dx.x, w.ix.x, W, ax0, fx.x, mx.x);
+      cdp_tap_axis_full(py, w.dy.x, w.iy.x, H, ay0, fy.x, my.x);
+      cdp_tap_axis_full(px, w.dx.y, w.ix.y, W, ax1, fx.y, mx.y);
+      cdp_tap_axis_full(py, w.dy.y, w.iy.y, H, ay1, fy.y, my.y);
+      bx0 = ax0 - box_x; by0 = ay0 - box_y; bx1 = ax1 - box_x; by1 = ay1 - box_y;
+      in0 = (unsigned)bx0 <= (unsigned)(Geo::SBW - 2) && (unsigned)by0 <= (unsigned)(Geo::SBH - 2);
+      in1 = (unsigned)bx1 <= (unsigned)(Geo::SBW - 2) && (unsigned)by1 <= (unsigned)(Geo::SBH - 2);
+    }
     float2 gix = cdp_set2(0.f), giy = cdp_set2(0.f);
     const float2 neg1 = cdp_set2(-1.0f);
     const float2 wy0 = cdp_fma2(fy, neg1, cdp_set2(1.0f)), wx0 = cdp_fma2(fx, neg1, cdp_set2(1.0f));
