@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_size_t, c_uint8, c_uin
 MAX_LEVELS = 6
 MAX_BATCH_PER_LAUNCH = 32
 MAX_FLOW_MAPS = 4    # CDP_MAX_FLOW_MAPS
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _fp = POINTER(c_float)
 
@@ -45,6 +45,7 @@ class PhotoArgs(ctypes.Structure):
         ("intrinsics_dev", c_void_p),
         ("noise_ready", c_void_p),
         ("heads", POINTER(PhotoHeads)),
+        ("noise_seed_dev", c_void_p),
     ]
 
 
@@ -65,6 +66,7 @@ SIGNATURES = {
     "cdp_photo_bwd_heads": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_void_p,
                                       POINTER(PhotoHeads), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int32, c_void_p, c_void_p, c_void_p]),
+    "cdp_tiebreak_noise": (c_int32, [c_int32, c_int32, c_int32, c_int32, ctypes.c_uint64, c_void_p, c_void_p]),
     "cdp_photo_fwd_launches": (c_int32, [c_int32, c_int32]),
     "cdp_photo_bwd_launches": (c_int32, [c_int32, c_int32, c_int32]),
     "cdp_smooth_saved_bytes": (c_size_t, [c_int32] * 3),

@@ -589,6 +589,31 @@ static void cdp_make_tma_maps(const CdpPlan& plan, CdpPhotoParams* kp, CdpTmaMap
 
 static int cdp_batch_chunks(int32_t batch) { return (batch + CDP_MAX_BATCH_PER_LAUNCH - 1) / CDP_MAX_BATCH_PER_LAUNCH; }
 
+__global__ void __launch_bounds__(256)
+cdp_tiebreak_noise_kernel(int B, int H, int W, int level, uint64_t seed, float* out) {
+  const size_t plane = (size_t)H * W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane * B) return;
+  const int b = (int)(i / plane);
+  const uint32_t pix = (uint32_t)(i - (size_t)b * plane);
+  float n0, n1;
+  cdp_noise_pair(seed, pix, (uint32_t)level, (uint32_t)b, n0, n1);
+  out[((size_t)b * 2 + 0) * plane + pix] = n0;
+  out[((size_t)b * 2 + 1) * plane + pix] = n1;
+}
+
+extern "C" int cdp_tiebreak_noise(int32_t batch, int32_t level_height, int32_t level_width, int32_t level,
+                                  uint64_t noise_seed, float* out, cdp_stream_t stream_) {
+  CDP_REQUIRE(batch > 0 && level_height > 0 && level_width > 0 && level >= 0 && level < CDP_MAX_LEVELS, "invalid shape");
+  CDP_REQUIRE(out != nullptr, "null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t n = (size_t)batch * level_height * level_width;
+  CDP_REQUIRE(n < ((size_t)1 << 31) * 256, "too many elements for one launch");
+  cdp_tiebreak_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(batch, level_height, level_width, level, noise_seed, out);
+  CDP_LAUNCH_CHECK("cdp_tiebreak_noise_kernel");
+  return CDP_OK;
+}
+
 extern "C" int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels) {
   // pyramid (+ intrinsics table), or intrinsics table kernels per 32 samples; tile kernel; reduction
   const bool table_in_pyramid = num_levels > 1 && batch <= CDP_MAX_BATCH_PER_LAUNCH;

@@ -110,6 +110,7 @@ struct CdpPhotoParams {
   const float* pose1;
   float* partials;  // [B][blocks_per_image][CDP_PARTIAL_STRIDE]
   uint64_t seed;
+  const uint64_t* seed_dev;  // if set: the seed is read from here (cdp_photo_args.noise_seed_dev)
   int32_t num_levels;
   int32_t batch_begin;  // first sample handled by this launch
   int32_t batch_total;  // B (row stride of K_tab)

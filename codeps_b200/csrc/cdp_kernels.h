@@ -130,6 +130,7 @@ struct CdpFinalizeParams {
   const float* partials;  // [B][blocks_per_image][CDP_PARTIAL_STRIDE]
   float* loss;            // [1]
   float* pose_unit;       // [2][B][16] or null
+  uint64_t* seed_dev;     // device seed counter of the built-in tie-break generator: bumped once per call (or null)
   int32_t B, blocks_per_image;
 };
 
@@ -182,6 +183,7 @@ CDP_HD void cdp_finalize_phase_c(const CdpFinalizeParams& p, int b, int tid, con
     double acc = 0.0;
     for (int i = 0; i < 32; ++i) acc += sm[2048 + i];
     p.loss[0] = (float)acc;
+    if (p.seed_dev) *p.seed_dev += 1;  // next call (or graph replay) of the built-in generator draws fresh noise
   }
 }
 

@@ -433,13 +433,16 @@ CDP_HD float cdp_reflect_mult(int p, int d, int n) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Counter-based tie-break noise (used only when the caller passes no noise tensors, i.e.
-// ReconstructionLoss(noise="fused")): the identity candidates get 1e-5 * n with n ~ N(0, 1) only
-// to break exact ties (algos/depth.py:316-318), so a cheap generator is enough: two rounds of a
-// 32-bit multiply-xorshift mix of (pixel, level, sample, seed) per draw and an Irwin-Hall sum of
-// its four bytes (mean 0, variance 1, support +-3.45 sigma).  ~20 instructions per pixel instead
-// of ~100 for Philox-4x32-10 + Box-Muller, which made the fused mode slower than reading
-// torch.randn from HBM (round-1 measurement).  Documented deviation: not torch's random stream.
+// Counter-based tie-break noise (used when the caller passes no noise tensors, i.e.
+// ReconstructionLoss(noise="fused")): the identity candidates get 1e-5 * n, n ~ N(0, 1)
+// (algos/depth.py:316-318).  Per pixel one 64-bit draw -- two rounds of a 32-bit multiply-xorshift
+// mix of (pixel, level, sample, seed) per word -- and ONE Box-Muller transform, whose two outputs
+// are exactly the two normals a pixel needs (one per identity candidate): u1 in (0, 1) with 24 bits,
+// r = sqrt(-2 ln u1) <= 5.9, angle = 2 pi u2.  On the GPU the transcendental steps are the
+// hardware approximations (lg2 / sqrt / sin / cos, ~1e-6 absolute): ~30 instructions per pixel,
+// no noise tensors in HBM and no generator launches.  cdp_tiebreak_noise (codeps_photo.h) writes
+// the same draws into a tensor so that tests can hand them to the oracle.  Not torch's Philox
+// stream: a loss built with noise="torch" draws torch.randn per level like the reference.
 // ------------------------------------------------------------------------------------------
 CDP_HD uint32_t cdp_mix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu;
@@ -447,15 +450,24 @@ CDP_HD uint32_t cdp_mix32(uint32_t h) {
   h ^= h >> 16;
   return h;
 }
-CDP_HD float cdp_irwin_hall4(uint32_t r) {
-  const int sum = (int)(r & 255u) + (int)((r >> 8) & 255u) + (int)((r >> 16) & 255u) + (int)(r >> 24);
-  // four uniform bytes: mean 510, variance 4 * (256^2 - 1) / 12 = 21845
-  return ((float)sum - 510.0f) * 0.0067658285f;
+CDP_HD void cdp_box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  const float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-08f;  // (k + 1/2) 2^-24 in (0, 1)
+  const float turn = (float)(b >> 8) * 5.9604644775390625e-08f;         // [0, 1)
+#if defined(__CUDA_ARCH__)
+  float r, sn, cs;
+  const float x = -1.3862943611198906f * __log2f(u1);  // -2 ln u1 = -2 ln 2 * log2 u1 >= 6e-8
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  const float ang = 6.283185307179586f * turn;
+  sn = __sinf(ang); cs = __cosf(ang);
+#else
+  const float r = sqrtf(-2.0f * logf(u1));
+  const float sn = sinf(6.283185307179586f * turn), cs = cosf(6.283185307179586f * turn);
+#endif
+  n0 = r * cs; n1 = r * sn;
 }
 CDP_HD void cdp_noise_pair(uint64_t seed, uint32_t pixel, uint32_t level, uint32_t sample,
                            float& n0, float& n1) {
   const uint32_t key = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B9u) ^ (level * 0x632BE5ABu) ^ (sample * 0x7F4A7C15u);
   const uint32_t a = cdp_mix32(pixel * 0x9E3779B1u + key);
-  n0 = cdp_irwin_hall4(a);
-  n1 = cdp_irwin_hall4(cdp_mix32(a ^ 0x68E31DA4u));
+  cdp_box_muller(a, cdp_mix32(a ^ 0x68E31DA4u), n0, n1);
 }

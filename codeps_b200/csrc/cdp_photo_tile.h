@@ -501,6 +501,7 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
   uint8_t* kplane = reinterpret_cast<uint8_t*>(sm + Geo::O_K);
   // (computed per thread on purpose: reading them from the parameter bank instead measured 1.7 % slower)
   const float a3 = p.alpha * (1.0f / 3.0f), b3 = (float)(1.0 - (double)p.alpha) * (1.0f / 3.0f);
+  const uint64_t seed = (!lv.noise && p.seed_dev) ? *p.seed_dev : p.seed;  // built-in generator: device counter or host value
   for (int item = tid; item < Geo::NITEMS; item += nthreads) {
     const int strip = item / Geo::BW, bx = item - strip * Geo::BW;
     const int by0 = strip * CDP_STRIP;
@@ -608,7 +609,7 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
         continue;
       }
       float n0 = nz[o].x, n1 = nz[o].y;
-      if (!lv.noise) cdp_noise_pair(p.seed, (uint32_t)(qy * W + qx), (uint32_t)c.lvl, (uint32_t)c.b, n0, n1);
+      if (!lv.noise) cdp_noise_pair(seed, (uint32_t)(qy * W + qx), (uint32_t)c.lvl, (uint32_t)c.b, n0, n1);
       const float id0 = acc_id[o].x + n0 * CDP_NOISE_SCALE, id1 = acc_id[o].y + n1 * CDP_NOISE_SCALE;
       float best = acc_pe[o].x;
       int kb = 0;

@@ -88,6 +88,7 @@ static inline void cdp_fill_photo_params(const CdpPlan& plan, const cdp_photo_ar
   kp->pose0 = a->pose0; kp->pose1 = a->pose1;
   kp->partials = scratch + plan.off_partials;
   kp->seed = a->noise_seed;
+  kp->seed_dev = a->noise_seed_dev;
   kp->num_levels = plan.L; kp->batch_begin = b0; kp->blocks_per_image = plan.blocks_per_image;
   kp->alpha = a->alpha;
 }
@@ -115,6 +116,9 @@ static inline void cdp_fill_finalize_params(const CdpPlan& plan, const cdp_photo
   fp->partials = scratch + plan.off_partials;
   fp->loss = a->loss;
   fp->pose_unit = a->with_grad ? saved + plan.off_pose_unit : nullptr;
+  bool own_noise = true;
+  for (int s = 0; s < plan.L; ++s) own_noise = own_noise && a->noise[s] == nullptr;
+  fp->seed_dev = own_noise ? a->noise_seed_dev : nullptr;
   fp->B = plan.B; fp->blocks_per_image = plan.blocks_per_image;
 }
 

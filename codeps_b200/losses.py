@@ -82,13 +82,19 @@ class ReconstructionLoss:
     ``last_argmin`` -- per level a uint8 [B,H_s,W_s] map, 0/1 = reprojection from t-1/t+1 won,
     2/3 = an identity candidate won, i.e. the pixel is auto-masked.
 
-    ``noise``: "torch" (default) draws ``torch.randn(B,2,H_s,W_s)`` per level exactly like the
-    reference (depth.py:317), so a seeded run consumes the same random stream; "fused" uses the
-    kernel's counter-based generator (no extra launches or traffic; different random numbers).
+    ``noise``: "fused" (default) draws the tie-break noise of depth.py:316-318 inside the tile kernel
+    from a counter-based generator (hash + Box-Muller: i.i.d. N(0, 1) per pixel and identity candidate;
+    no generator launches, no noise tensors in HBM).  Its seed is a device counter that starts at
+    ``seed`` (default: ``torch.initial_seed()`` when the object is built, so ``torch.manual_seed``
+    controls it) and advances by one per call -- also per replay of a CUDA graph that captured the
+    call.  "torch" draws ``torch.randn(B,2,H_s,W_s)`` per level exactly like the reference, so a seeded
+    run consumes torch's random stream the same way the reference does (five more launches and
+    16 bytes of traffic per level-pixel: 7 % of a step at 1024x512).  ``keep_noise`` keeps the draws
+    of the last call in ``last_noise`` in either mode.
     """
 
     def __init__(self, ref_img_width, ref_img_height, ssim: SSIMLoss, num_scales: int, device: torch.device,
-                 alpha: float = .85, noise: str = "torch", seed: int = 0):
+                 alpha: float = .85, noise: str = "fused", seed: Optional[int] = None):
         if noise not in ("torch", "fused"):
             raise ValueError("noise must be 'torch' or 'fused'")
         self.ssim = ssim
@@ -96,8 +102,9 @@ class ReconstructionLoss:
         self.num_scales = num_scales
         self.alpha = alpha
         self.noise = noise
-        self.seed = seed
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
         self._calls = 0
+        self._seed_counters = {}  # device index -> one-element int64 tensor (noise="fused")
         self.image_warpers = {}
         self.scaled_width = {}
         self.scaled_height = {}
@@ -154,7 +161,8 @@ class ReconstructionLoss:
         noise, noise_event, intrinsics = self._prepare(camera_models, images, depth_map)
         loss, self.last_argmin = ops.photometric_loss(
             intrinsics, images, depth_map, poses, noise, self.num_scales,
-            self.alpha, seed=self.seed + self._calls, motions=object_motion_maps, noise_event=noise_event)
+            self.alpha, seed=self._seed_for(depth_map), motions=object_motion_maps, noise_event=noise_event)
+        self._after_call(images[0])
         return loss
 
     def _semantic_loss(self, camera_models, depth_map, poses, semantic_mask) -> Tensor:
@@ -199,8 +207,9 @@ class ReconstructionLoss:
         noise, noise_event, intrinsics = self._prepare(camera_models, images, disparity_map)
         loss, self.last_argmin, depth, transformations = ops.photometric_loss_from_heads(
             intrinsics, images, disparity_map, pose_parameters, noise, self.num_scales, self.alpha,
-            seed=self.seed + self._calls, min_depth=min_depth, max_depth=max_depth, motions=object_motion_maps,
+            seed=self._seed_for(disparity_map), min_depth=min_depth, max_depth=max_depth, motions=object_motion_maps,
             noise_event=noise_event)
+        self._after_call(images[0])
         return loss, depth, transformations
 
     def _prepare(self, camera_models, images, depth_map):
@@ -234,6 +243,39 @@ class ReconstructionLoss:
         if intrinsics is None:
             intrinsics = self._level_intrinsics(camera_models)
         return noise, noise_event, intrinsics
+
+    def _seed_for(self, like: Tensor):
+        """noise="fused": the device seed counter of ``like``'s device (created on first use); else the
+        host seed (unused by the kernels when noise tensors are passed)."""
+        if self.noise != "fused" or not like.is_cuda:
+            return self.seed
+        key = like.device.index if like.device.index is not None else torch.cuda.current_device()
+        counter = self._seed_counters.get(key)
+        if counter is None:
+            counter = self._seed_counters[key] = torch.full((1,), self.seed, dtype=torch.int64, device=like.device)
+        return counter
+
+    def noise_seed_state(self, device=None) -> int:
+        """Seed the next noise="fused" call on ``device`` will use (reads the device counter: synchronises)."""
+        device = torch.device(self.device if device is None else device)
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        counter = self._seed_counters.get(key)
+        return self.seed if counter is None else int(counter.item())
+
+    def reset_noise_seed(self, seed: Optional[int] = None) -> None:
+        """Restart the noise="fused" generator at ``seed`` (default: the construction seed) on every device."""
+        self.seed = self.seed if seed is None else int(seed) & 0x7FFFFFFFFFFFFFFF
+        for counter in self._seed_counters.values():
+            counter.fill_(self.seed)
+
+    def _after_call(self, like: Tensor):
+        """keep_noise with the built-in generator: materialise the draws the call just used (reads the
+        device counter back: a host synchronisation, debugging / tests only)."""
+        if self.keep_noise and self.noise == "fused" and like.is_cuda and not torch.cuda.is_current_stream_capturing():
+            used = int(self._seed_for(like).item()) - 1
+            b = like.shape[0]
+            self.last_noise = ops.tiebreak_noise(b, self.scaled_height[0], self.scaled_width[0], self.num_scales, used,
+                                                 like.device)
 
     _side_streams = {}
 

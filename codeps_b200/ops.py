@@ -63,6 +63,12 @@ def _lib_for(device):
     return lib
 
 
+def _seed_counter(seed: torch.Tensor, device) -> torch.Tensor:
+    if seed.dtype != torch.int64 or seed.numel() != 1 or seed.device != device:
+        raise TypeError("a device seed counter must be a one-element int64 tensor on the loss's device")
+    return seed
+
+
 _table_cache = {}
 
 
@@ -121,7 +127,10 @@ class _PhotometricLoss(torch.autograd.Function):
         for s in range(num_levels):
             a.noise[s] = noise[s].data_ptr() if noise is not None else None
             a.argmin[s] = argmin[s].data_ptr()
-        a.noise_seed = int(seed)
+        if isinstance(seed, torch.Tensor):  # device counter: fresh draws on every CUDA-graph replay
+            a.noise_seed_dev = _seed_counter(seed, device).data_ptr()
+        else:
+            a.noise_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         if noise_event is not None:  # the noise was produced on another stream
             a.noise_ready = noise_event.cuda_event
         a.resize_tables = tables.data_ptr()
@@ -203,7 +212,10 @@ class _PhotometricLossHeads(torch.autograd.Function):
         for s in range(num_levels):
             a.noise[s] = noise[s].data_ptr() if noise is not None else None
             a.argmin[s] = argmin[s].data_ptr()
-        a.noise_seed = int(seed)
+        if isinstance(seed, torch.Tensor):  # device counter: fresh draws on every CUDA-graph replay
+            a.noise_seed_dev = _seed_counter(seed, device).data_ptr()
+        else:
+            a.noise_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         if noise_event is not None:
             a.noise_ready = noise_event.cuda_event
         a.resize_tables = tables.data_ptr()
@@ -313,6 +325,21 @@ def photometric_loss_from_heads(intrinsics, images: Sequence[torch.Tensor], disp
     return loss, state.argmin, depth, (pose0, pose1)
 
 
+def tiebreak_noise(batch: int, height: int, width: int, num_levels: int, seed: int, device) -> List[torch.Tensor]:
+    """The draws of the built-in tie-break generator: per level [B,2,H_s,W_s] standard-normal values,
+    exactly what ``photometric_loss(..., noise=None, seed=seed)`` adds (times 1e-5) to the identity
+    candidates.  Passing them back as ``noise=`` reproduces that evaluation (tests, inspection)."""
+    lib = _lib_for(device)
+    out = []
+    with torch.cuda.device(device):
+        for s in range(num_levels):
+            t = torch.empty((batch, 2, height >> s, width >> s), dtype=torch.float32, device=device)
+            check(lib.cdp_tiebreak_noise(batch, height >> s, width >> s, s, seed & 0xFFFFFFFFFFFFFFFF, _ptr(t), _stream(device)),
+                  "cdp_tiebreak_noise")
+            out.append(t)
+    return out
+
+
 def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], depth: torch.Tensor,
                      poses: Sequence[torch.Tensor], noise: Optional[Sequence[torch.Tensor]],
                      num_levels: int, alpha: float = 0.85, seed: int = 0,
@@ -325,7 +352,8 @@ def photometric_loss(intrinsics: np.ndarray, images: Sequence[torch.Tensor], dep
     float32 tensor [B, 4] with the full-resolution values (rescaled per level inside the kernel; no
     host copy of the calibration is needed then).
     noise: per level [B,2,H_s,W_s] standard-normal tie-break draws, or None to use the kernel's
-    counter-based generator with ``seed``.  ``noise_event``: event recorded after the noise was
+    counter-based generator with ``seed`` -- an int, or a one-element int64 CUDA tensor that the
+    library reads on the device and increments after the call (fresh draws per CUDA-graph replay).  ``noise_event``: event recorded after the noise was
     written on another stream; the library makes the current stream wait on it right before the
     tile kernel, so the noise generation overlaps the pyramid kernel.
     Returns (loss, per-level argmin maps)."""

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CDP_ABI_VERSION 5
+#define CDP_ABI_VERSION 6
 #define CDP_MAX_LEVELS 6           /* pyramid levels per call (reference uses 5) */
 #define CDP_MAX_BATCH_PER_LAUNCH 32 /* intrinsics travel in kernel-parameter (constant) space */
 
@@ -135,6 +135,11 @@ typedef struct cdp_photo_args {
   void* noise_ready;
   /* Optional: fused head conversions (see cdp_photo_heads); depth / pose0 / pose1 are then outputs. */
   const cdp_photo_heads* heads;
+  /* Optional DEVICE counter for the built-in generator (noise all NULL): if set, the kernels use
+   * *noise_seed_dev instead of noise_seed and add 1 to it once the call's tile kernel has finished,
+   * so that a CUDA graph that captured this call draws fresh noise on every replay (a host-side
+   * seed would be frozen into the graph). */
+  uint64_t* noise_seed_dev;
 } cdp_photo_args;
 
 size_t cdp_photo_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t num_levels,
@@ -160,6 +165,12 @@ int cdp_photo_bwd_heads(int32_t batch, int32_t height, int32_t width, int32_t nu
                         float* grad_axisangle1, float* grad_translation1,
                         int32_t with_motion, float* grad_motion0, float* grad_motion1, cdp_stream_t stream);
 /* Number of kernels one cdp_photo_fwd / cdp_photo_bwd call launches (for launch accounting). */
+/* The draws of the built-in tie-break generator (cdp_photo_args.noise all NULL) for one level:
+ * out = [B,2,H_s,W_s] standard normal values, exactly what cdp_photo_fwd adds (times 1e-5) to the two
+ * identity candidates of that level when called with the same noise_seed.  Test / inspection aid:
+ * lets a caller reproduce a noise="fused" evaluation with explicit noise tensors. */
+int cdp_tiebreak_noise(int32_t batch, int32_t level_height, int32_t level_width, int32_t level,
+                       uint64_t noise_seed, float* out, cdp_stream_t stream);
 int cdp_photo_fwd_launches(int32_t batch, int32_t num_levels);
 int cdp_photo_bwd_launches(int32_t batch, int32_t num_levels, int32_t with_motion);
 

@@ -171,12 +171,12 @@ def test_full_size_against_oracle(preset, batch, cuda_device):
 
 
 def test_seeded_torch_noise_matches_reference_stream(cuda_device):
-    """Default mode draws torch.randn(B,2,H_s,W_s) per level like algos/depth.py:317, so a seeded
+    """noise="torch" draws torch.randn(B,2,H_s,W_s) per level like algos/depth.py:317, so a seeded
     call consumes exactly the stream the reference would on the same device."""
     tb = make_batch(2, 160, 96, (150.0, 151.0, 80.0, 47.0), seed=3)
     scales = 4
     dev = cuda_device
-    loss_fn = codeps_b200.ReconstructionLoss(tb.width, tb.height, codeps_b200.SSIMLoss(), scales, dev)
+    loss_fn = codeps_b200.ReconstructionLoss(tb.width, tb.height, codeps_b200.SSIMLoss(), scales, dev, noise="torch")
     gpu = tb.to(dev)
     torch.manual_seed(77)
     recon = loss_fn(gpu.camera_models(), gpu.images, gpu.depth, gpu.poses)
@@ -259,8 +259,9 @@ def test_batch_chunking_over_32_samples(cuda_device):
 def test_fused_noise_mode_and_no_grad(cuda_device):
     dev = cuda_device
     tb = make_preset_batch("cityscapes", 2, seed=15).to(dev)
-    fused = codeps_b200.ReconstructionLoss(tb.width, tb.height, codeps_b200.SSIMLoss(), 5, dev, noise="fused")
-    default = codeps_b200.ReconstructionLoss(tb.width, tb.height, codeps_b200.SSIMLoss(), 5, dev)
+    fused = codeps_b200.ReconstructionLoss(tb.width, tb.height, codeps_b200.SSIMLoss(), 5, dev)
+    assert fused.noise == "fused"  # the default
+    default = codeps_b200.ReconstructionLoss(tb.width, tb.height, codeps_b200.SSIMLoss(), 5, dev, noise="torch")
     with torch.no_grad():
         a = fused(tb.camera_models(), tb.images, tb.depth, tb.poses)
         b = default(tb.camera_models(), tb.images, tb.depth, tb.poses)
@@ -270,6 +271,61 @@ def test_fused_noise_mode_and_no_grad(cuda_device):
     c.backward()
     assert depth.grad is not None and torch.isfinite(depth.grad).all()
     assert abs(float(c) - float(b)) <= 1e-4 * abs(float(b))
+
+
+def test_builtin_generator_draws_are_standard_normal_and_reproducible(cuda_device):
+    """The default tie-break noise (counter-based generator inside the tile kernel): cdp_tiebreak_noise
+    materialises its draws.  They must be i.i.d. N(0, 1) (moments, a Kolmogorov-Smirnov distance, no
+    correlation between the two identity candidates, between neighbouring pixels, levels, samples or
+    consecutive seeds), and an evaluation fed with them as explicit noise tensors must equal the
+    fused evaluation bit for bit -- i.e. the fused mode IS the reference algorithm with these draws."""
+    dev = cuda_device
+    b, h, w, scales = 2, 256, 512, 3
+    draws = ops.tiebreak_noise(b, h, w, scales, 12345, dev)
+    assert [tuple(d.shape) for d in draws] == [(b, 2, h >> s, w >> s) for s in range(scales)]
+    x = draws[0].double().flatten()
+    n = x.numel()
+    assert abs(float(x.mean())) < 5.0 / n ** 0.5 and abs(float(x.var()) - 1.0) < 5.0 * (2.0 / n) ** 0.5
+    assert abs(float((x ** 3).mean())) < 5.0 * (15.0 / n) ** 0.5          # skewness 0
+    assert abs(float((x ** 4).mean()) - 3.0) < 5.0 * (96.0 / n) ** 0.5    # kurtosis 3
+    xs = torch.sort(x).values
+    cdf = 0.5 * (1.0 + torch.erf(xs / 2 ** 0.5))
+    emp = torch.arange(1, n + 1, dtype=torch.float64, device=dev) / n
+    assert float((cdf - emp).abs().max()) < 1.95 / n ** 0.5               # KS test at the 0.1 % level
+    assert float(x.abs().max()) > 4.0                                     # tails are there (5.9 sigma possible)
+
+    def corr(a, c):
+        return abs(float((a.double().flatten() * c.double().flatten()).mean()))
+    lim = 5.0 / (b * h * w) ** 0.5
+    d0 = draws[0]
+    assert corr(d0[:, 0], d0[:, 1]) < lim                                  # the two candidates of a pixel
+    assert corr(d0[:, :, :, 1:], d0[:, :, :, :-1]) < lim and corr(d0[:, :, 1:], d0[:, :, :-1]) < lim
+    assert corr(d0[0], d0[1]) < 2 * lim                                    # samples
+    assert corr(d0[:, :, : h >> 1, : w >> 1], draws[1]) < 2 * lim          # levels
+    other = ops.tiebreak_noise(b, h, w, 1, 12346, dev)[0]
+    assert corr(d0, other) < lim                                           # consecutive seeds
+    assert torch.equal(ops.tiebreak_noise(b, h, w, 1, 12345, dev)[0], d0)  # a pure function of the seed
+
+    tb = make_preset_batch("semkitti", 2, seed=19).to(dev)
+    fn = codeps_b200.ReconstructionLoss(tb.width, tb.height, codeps_b200.SSIMLoss(), 5, dev, seed=77)
+    fn.keep_noise = True
+    depth = tb.depth.clone().requires_grad_(True)
+    poses = [p.clone().requires_grad_(True) for p in tb.poses]
+    loss = fn(tb.camera_models(), tb.images, depth, poses)
+    loss.backward()
+    assert fn.noise_seed_state() == 78
+    k_levels = fn._level_intrinsics(tb.camera_models())
+    depth2 = tb.depth.clone().requires_grad_(True)
+    poses2 = [p.clone().requires_grad_(True) for p in tb.poses]
+    loss2, argmin2 = ops.photometric_loss(k_levels, tb.images, depth2, poses2, fn.last_noise, 5)
+    loss2.backward()
+    assert torch.equal(loss.detach(), loss2.detach()) and torch.equal(depth.grad, depth2.grad)
+    assert all(torch.equal(p.grad, q.grad) for p, q in zip(poses, poses2))
+    assert all(torch.equal(a, c) for a, c in zip(fn.last_argmin, argmin2))
+    # ... and against the oracle with the same draws
+    want = po.reconstruction_loss(tb.intrinsics.cpu().numpy(), [i.cpu() for i in tb.images], tb.depth.cpu(),
+                                  [p.cpu() for p in tb.poses], [d.cpu() for d in fn.last_noise], 5)
+    assert_loss_close(loss.detach().cpu(), want, "fused-noise evaluation vs oracle with the generator's draws")
 
 
 def test_error_behaviour(cuda_device):
@@ -436,7 +492,7 @@ def test_side_stream_noise_equals_single_stream(cuda_device):
     dev = cuda_device
     tb = make_preset_batch("cityscapes", 2, seed=44).to(dev)
     w, h, scales = tb.width, tb.height, 5
-    fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), scales, dev)
+    fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), scales, dev, noise="torch")
     cams = tb.camera_models()
     k_levels = fn._level_intrinsics(cams)
 
@@ -528,7 +584,6 @@ def test_cuda_graph_capture_and_replay(cuda_device):
     def step():
         depth, disp = static["depth"].detach().requires_grad_(True), static["disp"].detach().requires_grad_(True)
         poses = [p.detach().requires_grad_(True) for p in static["poses"]]
-        recon_fn._calls = 0  # same fused-noise seed on every call
         recon = recon_fn(cams, static["images"], depth, poses)
         smooth = smooth_fn(static["images"][0], disp)
         grads = torch.autograd.grad([recon, smooth], [depth, disp] + poses)
@@ -551,9 +606,12 @@ def test_cuda_graph_capture_and_replay(cuda_device):
         static["disp"].copy_(batch.disp)
         for dst, src in zip(static["poses"], batch.poses):
             dst.copy_(src)
+        seed_used = recon_fn.noise_seed_state()  # the device counter the replay is about to read
         graph.replay()
         torch.cuda.synchronize()
+        assert recon_fn.noise_seed_state() == seed_used + 1, "a replay must advance the tie-break generator"
         replayed = [o.clone() for o in outs]
+        recon_fn.reset_noise_seed(seed_used)  # eager evaluation with the draws of the replay
         eager = step()
         torch.cuda.synchronize()
         for r, e in zip(replayed, eager):
