@@ -46,6 +46,12 @@
 #ifndef CDP_EXP_A_SKIP_TAIL
 #define CDP_EXP_A_SKIP_TAIL 0  // timing experiment only (wrong results): phase A drops its ragged last iteration
 #endif
+#ifndef CDP_A_UNROLL
+#define CDP_A_UNROLL 1  // unroll factor of the position loop of phase A
+#endif
+#ifndef CDP_C2_UNROLL
+#define CDP_C2_UNROLL 1  // unroll factor of the pixel loop of phase C2
+#endif
 #ifndef CDP_OPT_INTERIOR
 #define CDP_OPT_INTERIOR 1  // tiles whose source boxes lie inside the image skip the reflection / border-clip logic
 #endif
@@ -237,17 +243,19 @@ CDP_HD void cdp_reflect_ring(float* box, int nplanes, int bn, int bw, int bh, in
   }
 }
 
-// One source's literal-formula warp (depth clamp active or Q_w <= 0) written into lane k of w.
-CDP_HD void cdp_warp_lane_literal(int k, float u, float v, float depth, const CdpCam& cam, const CdpPose2& T,
-                                  const float2* mo, CdpWarp2& w) {
+// One source's literal-formula warp (depth clamp active or Q_w <= 0): (dx, dy, ix, iy) of source k.
+// Cold path, out of line: everything travels by value and the pose is re-read from global memory, so
+// that no variable of the hot loop has its address taken.
+CDP_COLD float4 cdp_warp_lane_literal(int k, float u, float v, float depth, CdpCam cam, const float* pose /*[16]*/,
+                                     bool with_motion, float m0, float m1, float m2) {
   CdpPose Tk;
-  cdp_unpack_pose(T, k, Tk);
-  float mk[3];
-  if (mo) { mk[0] = k ? mo[0].y : mo[0].x; mk[1] = k ? mo[1].y : mo[1].x; mk[2] = k ? mo[2].y : mo[2].x; }
+  cdp_load_pose_aligned(pose, Tk);
+  float mk[3] = {m0, m1, m2};
   CdpWarp ws;
-  cdp_warp_point(u, v, depth, cam, Tk, mo ? mk : nullptr, ws);
-  if (k == 0) { w.dx.x = ws.dx; w.dy.x = ws.dy; w.ix.x = ws.ix; w.iy.x = ws.iy; }
-  else { w.dx.y = ws.dx; w.dy.y = ws.dy; w.ix.y = ws.ix; w.iy.y = ws.iy; }
+  cdp_warp_point(u, v, depth, cam, Tk, with_motion ? mk : nullptr, ws);
+  float4 r;
+  r.x = ws.dx; r.y = ws.dy; r.z = ws.ix; r.w = ws.iy;
+  return r;
 }
 
 // bilinear blend of (source 0, source 1) tap pairs with per-lane fractions
@@ -294,6 +302,34 @@ CDP_HD bool cdp_taps_interior(int relx, int rely, const CdpWarp2& w, int& bx0, i
          (unsigned)bx1 <= (unsigned)(Geo::SBW - 2) && (unsigned)by1 <= (unsigned)(Geo::SBH - 2);
 }
 
+// Phase A, cold path: at least one of the two 2x2 footprints leaves the staged source box; that
+// source's taps come from global memory.
+template <bool G>
+CDP_COLD void cdp_phase_a_taps_far(const float* sbox0, const float* sbox1, const float* src0, const float* src1,
+                                   size_t plane, int W, bool in0, bool in1, int bx0, int by0, int bx1, int by1, int ax0,
+                                   int ay0, int ax1, int ay1, float2 fx, float2 fy, float* sm, int ti) {
+  typedef CdpTileGeom<G> Geo;
+#pragma unroll 1
+  for (int ch = 0; ch < 3; ++ch) {
+    float2 nw, ne, sw, se;
+    if (in0) {
+      const float* q = sbox0 + ch * Geo::SBN + by0 * Geo::SBW + bx0;
+      nw.x = q[0]; ne.x = q[1]; sw.x = q[Geo::SBW]; se.x = q[Geo::SBW + 1];
+    } else {
+      const float* g = src0 + ch * plane + (size_t)ay0 * W + ax0;
+      nw.x = CDP_LDG(g); ne.x = CDP_LDG(g + 1); sw.x = CDP_LDG(g + W); se.x = CDP_LDG(g + W + 1);
+    }
+    if (in1) {
+      const float* q = sbox1 + ch * Geo::SBN + by1 * Geo::SBW + bx1;
+      nw.y = q[0]; ne.y = q[1]; sw.y = q[Geo::SBW]; se.y = q[Geo::SBW + 1];
+    } else {
+      const float* g = src1 + ch * plane + (size_t)ay1 * W + ax1;
+      nw.y = CDP_LDG(g); ne.y = CDP_LDG(g + 1); sw.y = CDP_LDG(g + W); se.y = CDP_LDG(g + W + 1);
+    }
+    cdp_warp_plane<G>(sm, ch)[ti] = cdp_lerp2(nw, ne, sw, se, fx, fy);
+  }
+}
+
 template <bool G, bool M>
 CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int tid, int nthreads, float* sm,
                               const CdpTileConst& kc) {
@@ -319,6 +355,8 @@ CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int 
   const float* sbox1 = sm + Geo::O_SRC + Geo::SRC_STRIDE;
   const int box_x = ox - Geo::SBM, box_y = oy - Geo::SBM;  // image position of source box element (0, 0)
   const bool interior = cdp_tile_interior<G>(lv, c);
+  constexpr int kUnrollA = CDP_A_UNROLL;
+#pragma unroll kUnrollA
   for (int idx = tid; idx < (CDP_EXP_A_SKIP_TAIL ? Geo::RN / 256 * 256 : Geo::RN); idx += nthreads) {
     const int ry = idx / Geo::RW, rx = idx - ry * Geo::RW;
     const int tx = rx + Geo::OFFX, ty = ry + Geo::OFFY;
@@ -341,8 +379,16 @@ CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int 
     CdpWarp2 w;
     cdp_warp_point2((float)u, (float)v, depth, cam, T, M ? mo : nullptr, w);
     if (!(w.regular[0] && w.regular[1])) {  // depth clamp active or Q_w <= 0: literal formula, per source
-      if (!w.regular[0]) cdp_warp_lane_literal(0, (float)u, (float)v, depth, cam, T, M ? mo : nullptr, w);
-      if (!w.regular[1]) cdp_warp_lane_literal(1, (float)u, (float)v, depth, cam, T, M ? mo : nullptr, w);
+      if (!w.regular[0]) {
+        const float4 r = cdp_warp_lane_literal(0, (float)u, (float)v, depth, cam, p.pose0 + (size_t)c.b * 16, M,
+                                               M ? mo[0].x : 0.f, M ? mo[1].x : 0.f, M ? mo[2].x : 0.f);
+        w.dx.x = r.x; w.dy.x = r.y; w.ix.x = r.z; w.iy.x = r.w;
+      }
+      if (!w.regular[1]) {
+        const float4 r = cdp_warp_lane_literal(1, (float)u, (float)v, depth, cam, p.pose1 + (size_t)c.b * 16, M,
+                                               M ? mo[0].y : 0.f, M ? mo[1].y : 0.f, M ? mo[2].y : 0.f);
+        w.dx.y = r.x; w.dy.y = r.y; w.ix.y = r.z; w.iy.y = r.w;
+      }
     }
     int ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0, bx0, by0, bx1, by1;
     float2 fx, fy;
@@ -375,26 +421,9 @@ CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int 
         cdp_warp_plane<G>(sm, ch)[ti] = cdp_lerp2(nw, ne, sw, se, fx, fy);
       }
     } else {
-      // a footprint leaves the gather margin: global loads for that source (rolled: cold path)
-#pragma unroll 1
-      for (int ch = 0; ch < 3; ++ch) {
-        float2 nw, ne, sw, se;
-        if (in0) {
-          const float* q = sbox0 + ch * Geo::SBN + by0 * Geo::SBW + bx0;
-          nw.x = q[0]; ne.x = q[1]; sw.x = q[Geo::SBW]; se.x = q[Geo::SBW + 1];
-        } else {
-          const float* g = src0 + ch * plane + (size_t)ay0 * W + ax0;
-          nw.x = CDP_LDG(g); ne.x = CDP_LDG(g + 1); sw.x = CDP_LDG(g + W); se.x = CDP_LDG(g + W + 1);
-        }
-        if (in1) {
-          const float* q = sbox1 + ch * Geo::SBN + by1 * Geo::SBW + bx1;
-          nw.y = q[0]; ne.y = q[1]; sw.y = q[Geo::SBW]; se.y = q[Geo::SBW + 1];
-        } else {
-          const float* g = src1 + ch * plane + (size_t)ay1 * W + ax1;
-          nw.y = CDP_LDG(g); ne.y = CDP_LDG(g + 1); sw.y = CDP_LDG(g + W); se.y = CDP_LDG(g + W + 1);
-        }
-        cdp_warp_plane<G>(sm, ch)[ti] = cdp_lerp2(nw, ne, sw, se, fx, fy);
-      }
+      // a footprint leaves the gather margin: global loads for that source (cold path, out of line)
+      cdp_phase_a_taps_far<G>(sbox0, sbox1, src0, src1, plane, W, in0, in1, bx0, by0, bx1, by1, ax0, ay0, ax1, ay1, fx, fy,
+                              sm, ti);
     }
   }
 }
@@ -733,21 +762,28 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
 // ------------------------------------------------------------------------------------------
 // Phase C (with grad): both sources in the two lanes of packed fp32.
 // ------------------------------------------------------------------------------------------
-// One source of one pixel through the literal (depth clamp active / Q_w <= 0) formulas: rare.
-// gw[ch] = dL/d warped value of this source; adds to lane k of dT2, returns dL/d depth.
+// One source of one pixel through the literal (depth clamp active / Q_w <= 0) formulas: rare, out of
+// line, by value.  gw0..2 = dL/d warped value of this source per channel; returns dL/d depth and the
+// pixel's contribution to dL/dT of source k.
+struct CdpLiteralOut {
+  float gd;
+  float dT[16];
+};
 template <bool M>
-CDP_HD float cdp_phase_c_lane_literal(int k, const CdpPhotoParams& p, const CdpLevel& lv, const CdpTileCtx& c, int px,
-                                      int py, float depth, const CdpCam& cam, const float gw[3], float2* dT2) {
+CDP_COLD CdpLiteralOut cdp_phase_c_lane_literal(int k, const CdpPhotoParams& p, int lvl, int b, int px, int py,
+                                               float depth, CdpCam cam, float gw0, float gw1, float gw2) {
+  const CdpLevel& lv = p.lv[lvl];
   const int W = lv.W, H = lv.H;
   const size_t plane = (size_t)W * H;
   CdpPose T;
-  cdp_load_pose_aligned((k == 0 ? p.pose0 : p.pose1) + (size_t)c.b * 16, T);
-  const float* srck = (k == 0 ? lv.src0 : lv.src1) + (size_t)c.b * 3 * plane;
+  cdp_load_pose_aligned((k == 0 ? p.pose0 : p.pose1) + (size_t)b * 16, T);
+  const float* srck = (k == 0 ? lv.src0 : lv.src1) + (size_t)b * 3 * plane;
+  const float gw[3] = {gw0, gw1, gw2};
   float mo[3], gmo[3];
   if (M) {
     const float* motk = k == 0 ? lv.mot0 : lv.mot1;
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) mo[ch] = CDP_LDG(motk + ((size_t)c.b * 3 + ch) * plane + py * W + px);
+    for (int ch = 0; ch < 3; ++ch) mo[ch] = CDP_LDG(motk + ((size_t)b * 3 + ch) * plane + py * W + px);
   }
   CdpWarp w;
   cdp_warp_point((float)px, (float)py, depth, cam, T, M ? mo : nullptr, w);
@@ -761,20 +797,17 @@ CDP_HD float cdp_phase_c_lane_literal(int k, const CdpPhotoParams& p, const CdpL
     gix += gw[ch] * dix;
     giy += gw[ch] * diy;
   }
-  float dTk[16], gd = 0.f;
+  CdpLiteralOut o;
+  o.gd = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) dTk[i] = 0.f;
-  cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, gd, dTk, M ? gmo : nullptr);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    if (k == 0) dT2[i].x += dTk[i]; else dT2[i].y += dTk[i];
-  }
+  for (int i = 0; i < 16; ++i) o.dT[i] = 0.f;
+  cdp_warp_adjoint(gix * t.mx, giy * t.my, w, cam, T, o.gd, o.dT, M ? gmo : nullptr);
   if (M) {
-    float* dst = (k == 0 ? lv.gmot0 : lv.gmot1) + (size_t)c.b * 3 * plane + py * W + px;
+    float* dst = (k == 0 ? lv.gmot0 : lv.gmot1) + (size_t)b * 3 * plane + py * W + px;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) dst[ch * plane] = gmo[ch];
   }
-  return gd;
+  return o;
 }
 
 // Phase C1: per tile pixel, the masked, reflection-weighted 3x3 sums of the coefficient planes
@@ -854,6 +887,43 @@ CDP_HD void cdp_photo_phase_c1(const CdpPhotoParams& p, const CdpTileCtx& c, int
   }
 }
 
+// Phase C2, cold path: at least one footprint leaves the staged source box (taps of that source from
+// global memory); accumulates dL/d(ix, iy) of both sources.
+CDP_COLD float4 cdp_phase_c2_taps_far(const float* sbox0, const float* sbox1, const float* src0, const float* src1,
+                                      size_t plane, int W, bool in0, bool in1, int bx0, int by0, int bx1, int by1, int ax0,
+                                      int ay0, int ax1, int ay1, float2 fx, float2 fy, float2 gw0, float2 gw1, float2 gw2) {
+  typedef CdpTileGeom<true> Geo;
+  const float2 neg1 = cdp_set2(-1.0f);
+  const float2 wy0 = cdp_fma2(fy, neg1, cdp_set2(1.0f)), wx0 = cdp_fma2(fx, neg1, cdp_set2(1.0f));
+  float2 gix = cdp_set2(0.f), giy = cdp_set2(0.f);
+#pragma unroll 1
+  for (int ch = 0; ch < 3; ++ch) {
+    float2 nw, ne, sw, se;
+    if (in0) {
+      const float* q = sbox0 + ch * Geo::SBN + by0 * Geo::SBW + bx0;
+      nw.x = q[0]; ne.x = q[1]; sw.x = q[Geo::SBW]; se.x = q[Geo::SBW + 1];
+    } else {
+      const float* g = src0 + ch * plane + (size_t)ay0 * W + ax0;
+      nw.x = CDP_LDG(g); ne.x = CDP_LDG(g + 1); sw.x = CDP_LDG(g + W); se.x = CDP_LDG(g + W + 1);
+    }
+    if (in1) {
+      const float* q = sbox1 + ch * Geo::SBN + by1 * Geo::SBW + bx1;
+      nw.y = q[0]; ne.y = q[1]; sw.y = q[Geo::SBW]; se.y = q[Geo::SBW + 1];
+    } else {
+      const float* g = src1 + ch * plane + (size_t)ay1 * W + ax1;
+      nw.y = CDP_LDG(g); ne.y = CDP_LDG(g + 1); sw.y = CDP_LDG(g + W); se.y = CDP_LDG(g + W + 1);
+    }
+    const float2 dix = cdp_fma2(cdp_fma2(nw, neg1, ne), wy0, cdp_mul2(cdp_fma2(sw, neg1, se), fy));
+    const float2 diy = cdp_fma2(cdp_fma2(nw, neg1, sw), wx0, cdp_mul2(cdp_fma2(ne, neg1, se), fx));
+    const float2 g = ch == 0 ? gw0 : (ch == 1 ? gw1 : gw2);
+    gix = cdp_fma2(g, dix, gix);
+    giy = cdp_fma2(g, diy, giy);
+  }
+  float4 r;
+  r.x = gix.x; r.y = gix.y; r.z = giy.x; r.w = giy.y;
+  return r;
+}
+
 // Phase C2 (the source boxes are staged again: the coefficient planes that overlaid them are dead):
 // chain dL/d warped through the bilinear sampler's coordinate derivative and the projection to
 // dL/d depth_s (written) and dL/dT (accumulated), both sources in the two lanes of packed fp32.
@@ -875,6 +945,8 @@ CDP_HD void cdp_photo_phase_c2(const CdpPhotoParams& p, const CdpTileCtx& c, int
   float2 dT2[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) dT2[i] = cdp_set2(0.f);
+  constexpr int kUnrollC2 = CDP_C2_UNROLL;
+#pragma unroll kUnrollC2
   for (int idx = tid; idx < CDP_TILE_X * CDP_TILE_Y; idx += nthreads) {
     const int ly = idx / CDP_TILE_X, lx = idx - ly * CDP_TILE_X;
     const int px = c.x0 + lx, py = c.y0 + ly;
@@ -940,29 +1012,9 @@ CDP_HD void cdp_photo_phase_c2(const CdpPhotoParams& p, const CdpTileCtx& c, int
         giy = cdp_fma2(gw[ch], diy, giy);
       }
     } else {
-#pragma unroll 1
-      for (int ch = 0; ch < 3; ++ch) {
-        float2 nw, ne, sw, se;
-        if (in0) {
-          const float* q = sbox0 + ch * Geo::SBN + by0 * Geo::SBW + bx0;
-          nw.x = q[0]; ne.x = q[1]; sw.x = q[Geo::SBW]; se.x = q[Geo::SBW + 1];
-        } else {
-          const float* g = src0 + ch * plane + (size_t)ay0 * W + ax0;
-          nw.x = CDP_LDG(g); ne.x = CDP_LDG(g + 1); sw.x = CDP_LDG(g + W); se.x = CDP_LDG(g + W + 1);
-        }
-        if (in1) {
-          const float* q = sbox1 + ch * Geo::SBN + by1 * Geo::SBW + bx1;
-          nw.y = q[0]; ne.y = q[1]; sw.y = q[Geo::SBW]; se.y = q[Geo::SBW + 1];
-        } else {
-          const float* g = src1 + ch * plane + (size_t)ay1 * W + ax1;
-          nw.y = CDP_LDG(g); ne.y = CDP_LDG(g + 1); sw.y = CDP_LDG(g + W); se.y = CDP_LDG(g + W + 1);
-        }
-        const float2 dix = cdp_fma2(cdp_fma2(nw, neg1, ne), wy0, cdp_mul2(cdp_fma2(sw, neg1, se), fy));
-        const float2 diy = cdp_fma2(cdp_fma2(nw, neg1, sw), wx0, cdp_mul2(cdp_fma2(ne, neg1, se), fx));
-        const float2 g = ch == 0 ? gw[0] : (ch == 1 ? gw[1] : gw[2]);
-        gix = cdp_fma2(g, dix, gix);
-        giy = cdp_fma2(g, diy, giy);
-      }
+      const float4 r = cdp_phase_c2_taps_far(sbox0, sbox1, src0, src1, plane, W, in0, in1, bx0, by0, bx1, by1, ax0, ay0, ax1,
+                                             ay1, fx, fy, gw[0], gw[1], gw[2]);
+      gix.x = r.x; gix.y = r.y; giy.x = r.z; giy.y = r.w;
     }
     float2 gQ[3];
     float2 gdep = cdp_warp_adjoint2(cdp_mul2(gix, mx), cdp_mul2(giy, my), w, cam, T, dT2, gQ);
@@ -972,11 +1024,13 @@ CDP_HD void cdp_photo_phase_c2(const CdpPhotoParams& p, const CdpTileCtx& c, int
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         if (w.regular[k]) continue;
-        float gwk[3];
+        const CdpLiteralOut lit = cdp_phase_c_lane_literal<M>(k, p, c.lvl, c.b, px, py, depth, cam, k == 0 ? gw[0].x : gw[0].y,
+                                                              k == 0 ? gw[1].x : gw[1].y, k == 0 ? gw[2].x : gw[2].y);
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) gwk[ch] = k == 0 ? gw[ch].x : gw[ch].y;
-        const float lit = cdp_phase_c_lane_literal<M>(k, p, lv, c, px, py, depth, cam, gwk, dT2);
-        if (k == 0) gdep.x = lit; else gdep.y = lit;
+        for (int i = 0; i < 16; ++i) {
+          if (k == 0) dT2[i].x += lit.dT[i]; else dT2[i].y += lit.dT[i];
+        }
+        if (k == 0) gdep.x = lit.gd; else gdep.y = lit.gd;
       }
     }
     if (M) {

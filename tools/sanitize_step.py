@@ -4,7 +4,7 @@ sys.path.insert(0, "/root/repo")
 import codeps_b200
 from codeps_b200 import synthetic
 dev = torch.device("cuda:0")
-for (w, h, b, scales) in ((132, 70, 2, 5), (64, 32, 3, 4)):
+for (w, h, b, scales) in ((132, 70, 2, 5), (64, 32, 3, 4), (160, 128, 2, 2)):  # the last one has interior tiles
     tb = synthetic.make_batch(b, w, h, (0.8 * w, 0.8 * w, 0.5 * w, 0.5 * h), seed=1, flip_every_other=True).to(dev)
     fn = codeps_b200.ReconstructionLoss(w, h, codeps_b200.SSIMLoss(), scales, dev, noise=("fused" if "--fused" in sys.argv else "torch"))
     sm = codeps_b200.EdgeAwareSmoothnessLoss()
