@@ -35,7 +35,7 @@
 #define CDP_STRIP 5  // pixels per thread strip in phases B1/B2
 #endif
 #ifndef CDP_OPT_SSIM_RAW
-#define CDP_OPT_SSIM_RAW 0  // phase B1: SSIM ratio from the raw window sums (9 instead of 13 packed operations per pair)
+#define CDP_OPT_SSIM_RAW 1  // phase B1: SSIM ratio from the raw window sums (9 instead of 13 packed operations per pair)
 #endif
 #ifndef CDP_OPT_SSIM_RAW_B2
 #define CDP_OPT_SSIM_RAW_B2 1  // phase B2: adjoint coefficients from the raw window sums
@@ -51,6 +51,9 @@
 #endif
 #ifndef CDP_C2_UNROLL
 #define CDP_C2_UNROLL 1  // unroll factor of the pixel loop of phase C2
+#endif
+#ifndef CDP_OPT_PAIR_SHARE
+#define CDP_OPT_PAIR_SHARE 1  // phase B1: consecutive outputs of a strip share the sum of their two common window rows
 #endif
 #ifndef CDP_OPT_INTERIOR
 #define CDP_OPT_INTERIOR 1  // tiles whose source boxes lie inside the image skip the reflection / border-clip logic
@@ -449,6 +452,11 @@ CDP_HD void cdp_row_pair(const float2 x[3], const float y[3], CdpRowPair& o) {
   o.sy = cdp_fma2(x[2], cdp_set2(y[2]), cdp_fma2(x[1], cdp_set2(y[1]), cdp_mul2(x[0], cdp_set2(y[0]))));
 }
 
+CDP_HD void cdp_rows_add(const CdpRowTgt& a, const CdpRowTgt& b, CdpRowTgt& o) { o.s = a.s + b.s; o.ss = a.ss + b.ss; }
+CDP_HD void cdp_rows_add(const CdpRowPair& a, const CdpRowPair& b, CdpRowPair& o) {
+  o.s = cdp_add2(a.s, b.s); o.ss = cdp_add2(a.ss, b.ss); o.sy = cdp_add2(a.sy, b.sy);
+}
+
 // SSIM loss of a candidate pair from the 3x3 sums of strip-centred values (algos/depth.py:141-153).
 // ct = constant that turns strip-centred values back into true image values (means only).
 //
@@ -572,8 +580,10 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
         // that it is always a staged value; every window value is centred on it
         const float cs = ty[cs_idx];
         const float2 cs2 = cdp_set2(-cs);
-        CdpRowTgt hy[3];
-        CdpRowPair hs[3], hw[3];
+        CdpRowTgt hy[3], py2;
+        CdpRowPair hs[3], hw[3], ps2, pw2;
+        py2.s = py2.ss = 0.f;
+        ps2.s = ps2.ss = ps2.sy = pw2.s = pw2.ss = pw2.sy = cdp_set2(0.f);
         float yc_prev = 0.f;
         float2 sc_prev = cdp_set2(0.f), wc_prev = cdp_set2(0.f);
 #pragma unroll
@@ -595,14 +605,31 @@ CDP_HD void cdp_photo_phase_b1(const CdpPhotoParams& p, const CdpTileCtx& c, int
           cdp_row_pair(w, y, hw[r % 3]);
           if (r >= 2) {
             const int o = r - 2;  // output row: window rows r-2, r-1, r; centre row r-1
+            // 3-row sums; with CDP_OPT_PAIR_SHARE the sum of the two lower rows of an even output is
+            // kept and reused by the odd output below it (3 additions per two outputs instead of 4)
+            CdpRowTgt y3;
+            CdpRowPair s3, w3;
+            if (CDP_OPT_PAIR_SHARE && (o & 1) == 0 && o + 1 < CDP_STRIP) {
+              cdp_rows_add(hy[(r + 2) % 3], hy[r % 3], py2);
+              cdp_rows_add(hs[(r + 2) % 3], hs[r % 3], ps2);
+              cdp_rows_add(hw[(r + 2) % 3], hw[r % 3], pw2);
+              cdp_rows_add(hy[(r + 1) % 3], py2, y3);
+              cdp_rows_add(hs[(r + 1) % 3], ps2, s3);
+              cdp_rows_add(hw[(r + 1) % 3], pw2, w3);
+            } else if (CDP_OPT_PAIR_SHARE && (o & 1) == 1) {
+              cdp_rows_add(py2, hy[r % 3], y3);
+              cdp_rows_add(ps2, hs[r % 3], s3);
+              cdp_rows_add(pw2, hw[r % 3], w3);
+            } else {
+              CdpRowTgt ty; CdpRowPair ts, tw2;
+              cdp_rows_add(hy[0], hy[1], ty); cdp_rows_add(ty, hy[2], y3);
+              cdp_rows_add(hs[0], hs[1], ts); cdp_rows_add(ts, hs[2], s3);
+              cdp_rows_add(hw[0], hw[1], tw2); cdp_rows_add(tw2, hw[2], w3);
+            }
             CdpSsimTgt st;
-            cdp_ssim_tgt(hy[0].s + hy[1].s + hy[2].s, hy[0].ss + hy[1].ss + hy[2].ss, cs, st);
-            const float2 l_id = cdp_ssim_pair_loss(cdp_add2(cdp_add2(hs[0].s, hs[1].s), hs[2].s),
-                                                   cdp_add2(cdp_add2(hs[0].ss, hs[1].ss), hs[2].ss),
-                                                   cdp_add2(cdp_add2(hs[0].sy, hs[1].sy), hs[2].sy), st, cs);
-            const float2 l_pe = cdp_ssim_pair_loss(cdp_add2(cdp_add2(hw[0].s, hw[1].s), hw[2].s),
-                                                   cdp_add2(cdp_add2(hw[0].ss, hw[1].ss), hw[2].ss),
-                                                   cdp_add2(cdp_add2(hw[0].sy, hw[1].sy), hw[2].sy), st, cs);
+            cdp_ssim_tgt(y3.s, y3.ss, cs, st);
+            const float2 l_id = cdp_ssim_pair_loss(s3.s, s3.ss, s3.sy, st, cs);
+            const float2 l_pe = cdp_ssim_pair_loss(w3.s, w3.ss, w3.sy, st, cs);
             float2 d_id = cdp_add2(sc_prev, cdp_set2(-yc_prev)), d_pe = cdp_add2(wc_prev, cdp_set2(-yc_prev));
             d_id.x = fabsf(d_id.x); d_id.y = fabsf(d_id.y);
             d_pe.x = fabsf(d_pe.x); d_pe.y = fabsf(d_pe.y);
