@@ -140,27 +140,34 @@ struct CdpFinalizeParams {
 // Block 0 additionally strides over ALL records' loss entries into sm[1024 + tid].
 CDP_HD void cdp_finalize_phase_a(const CdpFinalizeParams& p, int b, int tid, double* sm) {
   const int r = tid >> 5, j = tid & 31;
-  // four independent accumulators (records r, r+32, r+64, r+96 of every group of 128): the loads of
-  // one group are in flight together instead of one L2 round trip per record; combined in a fixed order
+  // eight independent accumulators (records r, r+32, ..., r+224 of every group of 256): the loads of
+  // one group are in flight together instead of one memory round trip per record (the records were
+  // written up to a kernel duration ago: most of them come from DRAM, not L2); fixed combination order
   const float* rec = p.partials + (size_t)b * p.blocks_per_image * CDP_PARTIAL_STRIDE + 1 + j;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  for (int blk = r; blk < p.blocks_per_image; blk += 128) {
-    const float v0 = rec[(size_t)blk * CDP_PARTIAL_STRIDE];
-    const float v1 = blk + 32 < p.blocks_per_image ? rec[(size_t)(blk + 32) * CDP_PARTIAL_STRIDE] : 0.f;
-    const float v2 = blk + 64 < p.blocks_per_image ? rec[(size_t)(blk + 64) * CDP_PARTIAL_STRIDE] : 0.f;
-    const float v3 = blk + 96 < p.blocks_per_image ? rec[(size_t)(blk + 96) * CDP_PARTIAL_STRIDE] : 0.f;
-    a0 += (double)v0; a1 += (double)v1; a2 += (double)v2; a3 += (double)v3;
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.0;
+  for (int blk = r; blk < p.blocks_per_image; blk += 256) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      v[k] = blk + 32 * k < p.blocks_per_image ? rec[(size_t)(blk + 32 * k) * CDP_PARTIAL_STRIDE] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += (double)v[k];
   }
-  sm[r * 32 + j] = (a0 + a1) + (a2 + a3);
+  sm[r * 32 + j] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   if (b == 0) {
-    double l0 = 0.0, l1 = 0.0;
+    double l[4] = {0.0, 0.0, 0.0, 0.0};
     const int total = p.B * p.blocks_per_image;
-    for (int i = tid; i < total; i += 2 * CDP_FINALIZE_THREADS) {
-      const float v0 = p.partials[(size_t)i * CDP_PARTIAL_STRIDE];
-      const float v1 = i + CDP_FINALIZE_THREADS < total ? p.partials[(size_t)(i + CDP_FINALIZE_THREADS) * CDP_PARTIAL_STRIDE] : 0.f;
-      l0 += (double)v0; l1 += (double)v1;
+    for (int i = tid; i < total; i += 4 * CDP_FINALIZE_THREADS) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        v[k] = i + k * CDP_FINALIZE_THREADS < total ? p.partials[(size_t)(i + k * CDP_FINALIZE_THREADS) * CDP_PARTIAL_STRIDE] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) l[k] += (double)v[k];
     }
-    sm[1024 + tid] = l0 + l1;
+    sm[1024 + tid] = (l[0] + l[1]) + (l[2] + l[3]);
   }
 }
 // step 2: combine in index order; threads 0..31 own one pose-gradient column, threads 32..63 of
