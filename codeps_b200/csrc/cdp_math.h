@@ -41,6 +41,21 @@ CDP_HD float cdp_fdiv(float a, float b) {  // a / b to ~2 ulp
   return a / b;
 #endif
 }
+// clamp(1/2 + a / b, 0, 1) for the SSIM loss, a = half the numerator: MUFU.RCP and ONE saturating FMA.
+// (__fdividef expands to a range check, two predicated rescalings, MUFU.RCP and a multiply -- five
+// issue slots per division, three of them on the fp32 pipe; the SSIM denominators are >= 7e-6, so the
+// rescaling never triggers.)  One rounding fewer than divide-then-FMA.
+CDP_HD float cdp_half_plus_ratio_sat(float a, float b) {
+#if defined(__CUDA_ARCH__) && CDP_OPT_FAST_DIV
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return __saturatef(__fmaf_rn(a, r, 0.5f));
+#elif defined(__CUDA_ARCH__)
+  return __saturatef(a / b + 0.5f);
+#else
+  return fminf(fmaxf(a / b + 0.5f, 0.f), 1.f);
+#endif
+}
 CDP_HD float cdp_exp(float x) {
 #if defined(__CUDA_ARCH__) && CDP_OPT_FAST_EXP
   return __expf(x);

@@ -468,28 +468,25 @@ CDP_HD void cdp_rows_add(const CdpRowPair& a, const CdpRowPair& b, CdpRowPair& o
 // of the denominator is undone in the final FMA).  9 packed operations per pair instead of 13.
 #if CDP_OPT_SSIM_RAW
 struct CdpSsimTgt {  // target-side terms shared by the two candidate pairs of a pixel
-  float two_my, myy_c1, m2sy, nkd;
+  float my, myy_c1, m2sy, nkd;
 };
 CDP_HD void cdp_ssim_tgt(float sy, float syy, float ct, CdpSsimTgt& o) {
   const float my = cdp_fmaf(sy, 1.0f / 9.0f, ct);
-  o.two_my = my + my;
+  o.my = my;
   o.myy_c1 = cdp_fmaf(my, my, CDP_SSIM_C1);
   o.m2sy = -2.0f * sy;
   o.nkd = cdp_fmaf(sy, sy, cdp_fmaf(syy, -9.0f, -81.0f * CDP_SSIM_C2));
 }
 CDP_HD float2 cdp_ssim_pair_loss(float2 sx, float2 sxx, float2 sxy, const CdpSsimTgt& t, float ct) {
   const float2 mx = cdp_fma2(sx, cdp_set2(1.0f / 9.0f), cdp_set2(ct));
-  const float2 n1 = cdp_fma2(mx, cdp_set2(t.two_my), cdp_set2(CDP_SSIM_C1));
+  const float2 n1h = cdp_fma2(mx, cdp_set2(t.my), cdp_set2(0.5f * CDP_SSIM_C1));  // n1 / 2 (exactly)
   const float2 d1 = cdp_fma2(mx, mx, cdp_set2(t.myy_c1));
   const float2 n2 = cdp_fma2(sx, cdp_set2(t.m2sy), cdp_fma2(sxy, cdp_set2(18.0f), cdp_set2(81.0f * CDP_SSIM_C2)));
   const float2 nd2 = cdp_fma2(sx, sx, cdp_fma2(sxx, cdp_set2(-9.0f), cdp_set2(t.nkd)));
-  const float2 num = cdp_mul2(n1, n2), nden = cdp_mul2(d1, nd2);
-  float2 nS;  // -SSIM
-  nS.x = cdp_fdiv(num.x, nden.x);
-  nS.y = cdp_fdiv(num.y, nden.y);
-  float2 l;  // clamp((1 - S) / 2, 0, 1): one saturating FMA per lane (NaN -> 0 like fmin(fmax(NaN, 0), 1))
-  l.x = cdp_saturate(cdp_fmaf(nS.x, 0.5f, 0.5f));
-  l.y = cdp_saturate(cdp_fmaf(nS.y, 0.5f, 0.5f));
+  const float2 numh = cdp_mul2(n1h, n2), nden = cdp_mul2(d1, nd2);  // numh / nden = -SSIM / 2
+  float2 l;  // clamp((1 - S) / 2, 0, 1): reciprocal + one saturating FMA per lane (NaN -> 0 like fmin(fmax(NaN, 0), 1))
+  l.x = cdp_half_plus_ratio_sat(numh.x, nden.x);
+  l.y = cdp_half_plus_ratio_sat(numh.y, nden.y);
   return l;
 }
 #else
