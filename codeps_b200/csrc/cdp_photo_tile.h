@@ -414,15 +414,21 @@ CDP_HD void cdp_photo_phase_a(const CdpPhotoParams& p, const CdpTileCtx& c, int 
       // immediate offsets from two addresses
       const float* q0 = sbox0 + by0 * Geo::SBW + bx0;
       const float* q1 = sbox1 + by1 * Geo::SBW + bx1;
+      // (all 24 loads before the first store: the compiler cannot tell that the warped planes and the
+      // source boxes never overlap, so a store between the channels would serialise their loads)
+      float2 nw[3], ne[3], sw[3], se[3];
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        float2 nw, ne, sw, se;
-        nw.x = q0[ch * Geo::SBN]; ne.x = q0[ch * Geo::SBN + 1];
-        sw.x = q0[ch * Geo::SBN + Geo::SBW]; se.x = q0[ch * Geo::SBN + Geo::SBW + 1];
-        nw.y = q1[ch * Geo::SBN]; ne.y = q1[ch * Geo::SBN + 1];
-        sw.y = q1[ch * Geo::SBN + Geo::SBW]; se.y = q1[ch * Geo::SBN + Geo::SBW + 1];
-        cdp_warp_plane<G>(sm, ch)[ti] = cdp_lerp2(nw, ne, sw, se, fx, fy);
+        nw[ch].x = q0[ch * Geo::SBN]; ne[ch].x = q0[ch * Geo::SBN + 1];
+        sw[ch].x = q0[ch * Geo::SBN + Geo::SBW]; se[ch].x = q0[ch * Geo::SBN + Geo::SBW + 1];
+        nw[ch].y = q1[ch * Geo::SBN]; ne[ch].y = q1[ch * Geo::SBN + 1];
+        sw[ch].y = q1[ch * Geo::SBN + Geo::SBW]; se[ch].y = q1[ch * Geo::SBN + Geo::SBW + 1];
       }
+      float2 wv[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) wv[ch] = cdp_lerp2(nw[ch], ne[ch], sw[ch], se[ch], fx, fy);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) cdp_warp_plane<G>(sm, ch)[ti] = wv[ch];
     } else {
       // a footprint leaves the gather margin: global loads for that source (cold path, out of line)
       cdp_phase_a_taps_far<G>(sbox0, sbox1, src0, src1, plane, W, in0, in1, bx0, by0, bx1, by1, ax0, ay0, ax1, ay1, fx, fy,
@@ -736,6 +742,11 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
       const float2 cs2 = cdp_set2(-cs);
       CdpRowTgt hy[3];
       CdpRowPair hw[3];
+      // The coefficients of an output are stored one row later, after that row's loads: the compiler
+      // cannot tell that the coefficient planes and the planes the walk reads never overlap, so a
+      // store right after the (long) coefficient chain would hold back the next row's loads.
+      float pA = 0.f, pB = 0.f, pC = 0.f;
+      int pidx = -1;
 #pragma unroll
       for (int r = 0; r < CDP_STRIP + 2; ++r) {
         const int row = r00 + (r - 1) * Geo::TBW;
@@ -745,6 +756,12 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
         for (int t = 0; t < 3; ++t) {
           y[t] = ty[row + t - 1] - cs;
           w[t] = cdp_add2(tw[row + t - 1], cs2);
+        }
+        if (pidx >= 0) {
+          sm[Geo::O_COEF + (ch * 3 + 0) * Geo::TBN + pidx] = pA;
+          sm[Geo::O_COEF + (ch * 3 + 1) * Geo::TBN + pidx] = pB;
+          sm[Geo::O_COEF + (ch * 3 + 2) * Geo::TBN + pidx] = pC;
+          pidx = -1;
         }
         cdp_row_tgt(y, hy[r % 3]);
         cdp_row_pair(w, y, hw[r % 3]);
@@ -772,12 +789,15 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
             const float csc = cs - centre[ch];  // strip constant in the tile-centred frame
             cdp_ssim_coeffs_abc(t, mxc + csc, myc + csc, A, B, C);
 #endif
-            const int ridx = r00 + o * Geo::TBW;
-            sm[Geo::O_COEF + (ch * 3 + 0) * Geo::TBN + ridx] = A;
-            sm[Geo::O_COEF + (ch * 3 + 1) * Geo::TBN + ridx] = B;
-            sm[Geo::O_COEF + (ch * 3 + 2) * Geo::TBN + ridx] = C;
+            pA = A; pB = B; pC = C;
+            pidx = r00 + o * Geo::TBW;
           }
         }
+      }
+      if (pidx >= 0) {
+        sm[Geo::O_COEF + (ch * 3 + 0) * Geo::TBN + pidx] = pA;
+        sm[Geo::O_COEF + (ch * 3 + 1) * Geo::TBN + pidx] = pB;
+        sm[Geo::O_COEF + (ch * 3 + 2) * Geo::TBN + pidx] = pC;
       }
     }
   }
@@ -867,6 +887,8 @@ CDP_HD void cdp_photo_phase_c1(const CdpPhotoParams& p, const CdpTileCtx& c, int
 #pragma unroll
     for (int d = 0; d < 3; ++d) mxw[d] = cdp_reflect_mult(px, d - 1, W);
     float2 h[3][9];
+    float2 pg[3];   // results of the previous output, stored after the next output's loads
+    int pidx = -1;
 #pragma unroll
     for (int r = 0; r < CDP_C1_ROWS + 2; ++r) {
       const int ty = ly0 - 1 + r + Geo::TYO;  // box row of window row r
@@ -888,6 +910,19 @@ CDP_HD void cdp_photo_phase_c1(const CdpPhotoParams& p, const CdpTileCtx& c, int
         if (py < H) {
           const int ridx = (ly + Geo::TYO) * Geo::TBW + lx + Geo::TXO;
           const int kown = kplane[ridx];
+          // this output's own values, loaded before the previous output's results are stored (the
+          // compiler cannot tell that stores and loads never overlap and keeps their order)
+          float2 xr[3];
+          float yr[3];
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            xr[ch] = cdp_warp_plane<true>(sm, ch)[ridx];
+            yr[ch] = sm[Geo::O_TGT + ch * Geo::TBN + ridx];
+          }
+          if (pidx >= 0) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) cdp_warp_plane<true>(sm, ch)[pidx] = pg[ch];
+          }
           // vertical weights: rows (r-2, r-1, r) of the ring are window rows dy = -1, 0, +1
           const float2 m0 = cdp_set2(cdp_reflect_mult(py, -1, H)), m2 = cdp_set2(cdp_reflect_mult(py, 1, H));
 #pragma unroll
@@ -898,15 +933,20 @@ CDP_HD void cdp_photo_phase_c1(const CdpPhotoParams& p, const CdpTileCtx& c, int
               const int pl = ch * 3 + q;
               sabc[q] = cdp_fma2(m2, h[r % 3][pl], cdp_fma2(m0, h[(r - 2) % 3][pl], h[(r - 1) % 3][pl]));
             }
-            const float2 x = cdp_add2(cdp_warp_plane<true>(sm, ch)[ridx], cdp_set2(-centre[ch]));
-            const float y = sm[Geo::O_TGT + ch * Geo::TBN + ridx] - centre[ch];
+            const float2 x = cdp_add2(xr[ch], cdp_set2(-centre[ch]));
+            const float y = yr[ch] - centre[ch];
             float2 g = cdp_mul2(cdp_set2(w_ssim), cdp_fma2(cdp_mul2(x, cdp_set2(2.f)), sabc[1], cdp_fma2(cdp_set2(y), sabc[2], sabc[0])));
             if (kown == 0) g.x += w_l1 * (x.x > y ? 1.f : (x.x < y ? -1.f : 0.f));
             if (kown == 1) g.y += w_l1 * (x.y > y ? 1.f : (x.y < y ? -1.f : 0.f));
-            cdp_warp_plane<true>(sm, ch)[ridx] = g;
+            pg[ch] = g;
           }
+          pidx = ridx;
         }
       }
+    }
+    if (pidx >= 0) {
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) cdp_warp_plane<true>(sm, ch)[pidx] = pg[ch];
     }
   }
 }
