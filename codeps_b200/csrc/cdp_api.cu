@@ -177,23 +177,32 @@ __device__ __forceinline__ void cdp_block_reduce_store(float (&v)[N], float* red
 }
 
 // Same result type for many values per thread (N ~ 33): every thread parks its values in shared
-// memory (value-major, conflict free), then each warp sums whole values: lane l adds the entries
-// of threads l, l+32, ... in order, a shuffle tree combines the lanes.  ~4x fewer instructions
-// than N shuffle trees per warp.  red: >= N * blockDim.x floats.  Fixed order, no atomics.
+// memory (value-major, conflict free); then eight lanes share one value: lane j of the group adds
+// the entries of threads 4 (j + 8 k) .. + 3, k = 0, 1, ... (16-byte loads, four independent chains),
+// and three shuffle steps combine the eight lanes.  All warps work at once (32 values in flight per
+// 256 threads) on a short dependency chain -- a warp per value with one entry per lane and step was
+// ~5x longer on the critical path of every tile.  red: >= N * blockDim.x floats, 16-byte aligned;
+// blockDim.x a multiple of 32.  Fixed order, no atomics.
 // SKIP_AT > 0: value i >= SKIP_AT is stored at out[i + SKIP_BY] (the caller left a gap of entries
 // it knows to be zero out of the reduction).
 template <int N, int SKIP_AT = 0, int SKIP_BY = 0>
 __device__ __forceinline__ void cdp_block_reduce_store_wide(const float (&v)[N], float* red, float* out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, nt = blockDim.x;
+  const int nt = blockDim.x, j = threadIdx.x & 7, group = threadIdx.x >> 3, ngroups = nt >> 3;
 #pragma unroll
   for (int i = 0; i < N; ++i) red[i * nt + threadIdx.x] = v[i];
   __syncthreads();
-  for (int i = warp; i < N; i += nwarps) {
-    float acc = 0.f;
-    for (int t = lane; t < nt; t += 32) acc += red[i * nt + t];
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);  // the eight lanes of this group (a second pass is not warp-uniform)
+  for (int i = group; i < N; i += ngroups) {
+    const float4* row = reinterpret_cast<const float4*>(red + i * nt) + j;
+    float4 acc = row[0];
+    for (int k = 1; k < nt / 32; ++k) {
+      const float4 e = row[8 * k];
+      acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+    }
+    float a = (acc.x + acc.y) + (acc.z + acc.w);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
-    if (lane == 0) out[(SKIP_AT > 0 && i >= SKIP_AT) ? i + SKIP_BY : i] = acc;
+    for (int off = 4; off > 0; off >>= 1) a += __shfl_down_sync(gmask, a, off, 8);
+    if (j == 0) out[(SKIP_AT > 0 && i >= SKIP_AT) ? i + SKIP_BY : i] = a;
   }
 }
 

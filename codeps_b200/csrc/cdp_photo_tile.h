@@ -46,6 +46,10 @@
 #ifndef CDP_EXP_A_SKIP_TAIL
 #define CDP_EXP_A_SKIP_TAIL 0  // timing experiment only (wrong results): phase A drops its ragged last iteration
 #endif
+#ifndef CDP_EXP_HALO1
+#define CDP_EXP_HALO1 0  // timing experiment only (wrong results): the gradient instantiation computes on halo 1 like the
+                         // forward-only one -- the upper bound of what sharing halos between the CTAs of a cluster could save
+#endif
 #ifndef CDP_A_UNROLL
 #define CDP_A_UNROLL 1  // unroll factor of the position loop of phase A
 #endif
@@ -71,7 +75,7 @@
 // TXO = 4 and SBM = 4 although the window sums only need two columns left of the tile.
 template <bool G>
 struct CdpTileGeom {
-  static constexpr int HALO = G ? 2 : 1;  // ring around the tile on which warped values are needed
+  static constexpr int HALO = (G && !CDP_EXP_HALO1) ? 2 : 1;  // ring around the tile on which warped values are needed
   static constexpr int TXO = 4, TYO = 2;  // box position of the tile's first column / row
   static constexpr int OFFX = TXO - HALO, OFFY = TYO - HALO;  // first box column / row of that region
   static constexpr int RW = CDP_TILE_X + 2 * HALO, RH = CDP_TILE_Y + 2 * HALO, RN = RW * RH;
