@@ -272,6 +272,10 @@ __device__ __forceinline__ void cdp_tma_prefetch_3d(const CUtensorMap* map, int 
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+#ifndef CDP_EXP_TMA_TWICE
+#define CDP_EXP_TMA_TWICE 0  // timing experiment: both source boxes are loaded twice, at the start and in phase S2 (+101 KB of
+                             // TMA traffic per tile on top of 124 KB: +1.9 % kernel time, i.e. the mbarrier waits are latency)
+#endif
 #ifndef CDP_OPT_L2_PREFETCH
 #define CDP_OPT_L2_PREFETCH 296  // CTAs ahead whose boxes are prefetched into L2 (0 = off); one wave of 2 x 148 (measured: -0.4 %)
 #endif
@@ -297,10 +301,14 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
     __syncthreads();
     if (threadIdx.x == 0) {
       const int ox = c.x0 - Geo::TXO, oy = c.y0 - Geo::TYO;  // (multiples of 4 in x: 16-byte aligned box starts)
-      cdp_mbar_expect_tx(bar, Geo::TMA_BYTES_A);
+      cdp_mbar_expect_tx(bar, Geo::TMA_BYTES_A + (CDP_EXP_TMA_TWICE ? Geo::TMA_BYTES_SRC : 0u));
       cdp_tma_load_3d(sm + Geo::O_DEPTH, &tm.m[c.lvl][1], bar, ox, oy, c.b);
       cdp_tma_load_3d(sm + Geo::O_SRC, &tm.m[c.lvl][2], bar, ox - Geo::SBM, oy - Geo::SBM, c.b * 3);
       cdp_tma_load_3d(sm + Geo::O_SRC + Geo::SRC_STRIDE, &tm.m[c.lvl][3], bar, ox - Geo::SBM, oy - Geo::SBM, c.b * 3);
+#if CDP_EXP_TMA_TWICE  // timing experiment: the same source boxes once more (sensitivity of the kernel to TMA bytes)
+      cdp_tma_load_3d(sm + Geo::O_SRC, &tm.m[c.lvl][2], bar, ox - Geo::SBM, oy - Geo::SBM, c.b * 3);
+      cdp_tma_load_3d(sm + Geo::O_SRC + Geo::SRC_STRIDE, &tm.m[c.lvl][3], bar, ox - Geo::SBM, oy - Geo::SBM, c.b * 3);
+#endif
       cdp_mbar_expect_tx(bar + 1, Geo::TMA_BYTES_TGT);
       cdp_tma_load_3d(sm + Geo::O_TGT, &tm.m[c.lvl][0], bar + 1, ox, oy, c.b * 3);
     }
@@ -349,9 +357,13 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
     if (tma) {
       if (threadIdx.x == 0) {
         const int ox = c.x0 - Geo::TXO - Geo::SBM, oy = c.y0 - Geo::TYO - Geo::SBM;
-        cdp_mbar_expect_tx(bar, (unsigned)(2 * 3 * Geo::SBN * sizeof(float)));
+        cdp_mbar_expect_tx(bar, Geo::TMA_BYTES_SRC * (CDP_EXP_TMA_TWICE ? 2u : 1u));
         cdp_tma_load_3d(sm + Geo::O_SRC, &tm.m[c.lvl][2], bar, ox, oy, c.b * 3);
         cdp_tma_load_3d(sm + Geo::O_SRC + Geo::SRC_STRIDE, &tm.m[c.lvl][3], bar, ox, oy, c.b * 3);
+#if CDP_EXP_TMA_TWICE
+        cdp_tma_load_3d(sm + Geo::O_SRC, &tm.m[c.lvl][2], bar, ox, oy, c.b * 3);
+        cdp_tma_load_3d(sm + Geo::O_SRC + Geo::SRC_STRIDE, &tm.m[c.lvl][3], bar, ox, oy, c.b * 3);
+#endif
       }
       cdp_tile_const(p, c, kc);  // (reloaded rather than kept in 38 registers through B1 / B2 / C1)
       cdp_mbar_wait(bar, 1);     // second use of barrier 0: phase parity 1

@@ -101,7 +101,8 @@ struct CdpTileGeom {
   static constexpr size_t SMEM_BYTES = (size_t)(O_MBAR + 4) * sizeof(float);
   // barrier 0: depth + both source boxes (what phase A reads; re-armed for the sources before C2);
   // barrier 1: target box (first read in phase B1)
-  static constexpr unsigned TMA_BYTES_A = (unsigned)((TBN + 2 * 3 * SBN) * sizeof(float));
+  static constexpr unsigned TMA_BYTES_SRC = (unsigned)(2 * 3 * SBN * sizeof(float));  // both source boxes
+  static constexpr unsigned TMA_BYTES_A = (unsigned)(TBN * sizeof(float)) + TMA_BYTES_SRC;
   static constexpr unsigned TMA_BYTES_TGT = (unsigned)(3 * TBN * sizeof(float));
   // The B1/B2 strip walk always reads CDP_STRIP + 2 rows, also for the last, partial strip: the
   // rows past the box belong to the following plane (values discarded); in the source boxes they
