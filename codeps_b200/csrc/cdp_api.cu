@@ -297,9 +297,10 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
     // phase S by TMA: one thread arms the mbarriers with the byte counts and issues the four box
     // loads; every thread waits for the data it needs next (barrier 0: depth + sources for phase A,
     // barrier 1: target for phase B1) -- after fetching its own per-tile constants
-    if (threadIdx.x == 0) { cdp_mbar_init(bar, 1); cdp_mbar_init(bar + 1, 1); }
-    __syncthreads();
+    // (the issuing thread initialises the barriers and starts the loads right away; the block barrier
+    // that makes the initialised barriers visible to the waiting threads comes after the issue)
     if (threadIdx.x == 0) {
+      cdp_mbar_init(bar, 1); cdp_mbar_init(bar + 1, 1);
       const int ox = c.x0 - Geo::TXO, oy = c.y0 - Geo::TYO;  // (multiples of 4 in x: 16-byte aligned box starts)
       cdp_mbar_expect_tx(bar, Geo::TMA_BYTES_A + (CDP_EXP_TMA_TWICE ? Geo::TMA_BYTES_SRC : 0u));
       cdp_tma_load_3d(sm + Geo::O_DEPTH, &tm.m[c.lvl][1], bar, ox, oy, c.b);
@@ -312,6 +313,7 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
       cdp_mbar_expect_tx(bar + 1, Geo::TMA_BYTES_TGT);
       cdp_tma_load_3d(sm + Geo::O_TGT, &tm.m[c.lvl][0], bar + 1, ox, oy, c.b * 3);
     }
+    __syncthreads();
 #if CDP_OPT_L2_PREFETCH > 0
     if (threadIdx.x == 32) {
       // the boxes of the tile that will start about two waves from now: L2 prefetch, so that its

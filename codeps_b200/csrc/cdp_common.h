@@ -107,6 +107,7 @@ struct CdpLevel {
   float* gmot1;
   int32_t W, H;
   int32_t tiles_x, tiles_y;
+  uint32_t tiles_x_rcp;  // ceil(2^32 / tiles_x): tile / tiles_x = (tile * tiles_x_rcp) >> 32 for tile * tiles_x < 2^32
   int32_t block_begin;  // first block index (within one image) belonging to this level
   float weight;         // 1 / (B * H * W * 2^s * num_levels)
   int32_t use_tma;      // 1: the boxes of this level are staged by TMA (descriptors in CdpTmaMaps)

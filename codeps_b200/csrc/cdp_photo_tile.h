@@ -121,12 +121,17 @@ struct CdpTileCtx {
 
 CDP_HD CdpTileCtx cdp_tile_ctx(const CdpPhotoParams& p, int bx, int by) {
   CdpTileCtx c;
-  int s = p.num_levels - 1;
-  while (s > 0 && bx < p.lv[s].block_begin) --s;
+  // level = number of levels s >= 1 that start at or before this block (branch-free: the loads of
+  // all block_begin values are independent; this runs on the critical path to the tile's TMA loads)
+  int s = 0;
+#pragma unroll
+  for (int l = 1; l < CDP_MAX_LEVELS; ++l) s += (l < p.num_levels && bx >= p.lv[l].block_begin) ? 1 : 0;
   c.lvl = s;
   const int tile = bx - p.lv[s].block_begin;
-  const int ty = tile / p.lv[s].tiles_x;
-  c.x0 = (tile - ty * p.lv[s].tiles_x) * CDP_TILE_X;
+  // tile / tiles_x by the host's reciprocal (tiles_x == 1: the reciprocal wraps to 0, ty = tile)
+  const int tx_n = p.lv[s].tiles_x;
+  const int ty = tx_n == 1 ? tile : (int)(((uint64_t)(uint32_t)tile * p.lv[s].tiles_x_rcp) >> 32);
+  c.x0 = (tile - ty * tx_n) * CDP_TILE_X;
   c.y0 = ty * CDP_TILE_Y;
   c.b = p.batch_begin + by;
   return c;

@@ -79,6 +79,7 @@ static inline void cdp_fill_photo_params(const CdpPlan& plan, const cdp_photo_ar
     }
     lv.W = plan.Ws[s]; lv.H = plan.Hs[s];
     lv.tiles_x = plan.tiles_x[s]; lv.tiles_y = plan.tiles_y[s];
+    lv.tiles_x_rcp = (uint32_t)((0x100000000ull + (uint64_t)plan.tiles_x[s] - 1) / (uint64_t)plan.tiles_x[s]);
     lv.block_begin = plan.block_begin[s];
     // mean over B*H_s*W_s, / 2^s, / num_levels (algos/depth.py:325-326)
     lv.weight = (float)(1.0 / ((double)plan.B * plan.Hs[s] * plan.Ws[s] * (double)(1 << s) * plan.L));
