@@ -33,6 +33,27 @@ EMU_API size_t emu_photo_saved_bytes(int32_t b, int32_t h, int32_t w, int32_t l,
   return cdp_make_plan(b, h, w, l, &plan, m != 0) ? plan.saved_floats * sizeof(float) : 0;
 }
 
+// Tile lookup of the photo kernel for every block of one image: out[3 * bx + {0,1,2}] = level, x0, y0
+// (the level search and the reciprocal-multiply division of cdp_tile_ctx, checked against plain
+// integer arithmetic by tests/test_kernel_logic_cpu.py).  Returns the number of blocks.
+EMU_API int emu_tile_table(int32_t h, int32_t w, int32_t l, int32_t* out, int32_t capacity) {
+  CdpPlan plan;
+  if (!cdp_make_plan(1, h, w, l, &plan, false)) return -1;
+  cdp_photo_args a;
+  memset(&a, 0, sizeof(a));
+  a.batch = 1; a.height = h; a.width = w; a.num_levels = l;
+  static float base[1];  // only addresses are formed from the buffers here, nothing is read or written
+  a.scratch = base; a.saved = base;
+  CdpPhotoParams kp;
+  cdp_fill_photo_params(plan, &a, 0, 1, &kp);
+  if (plan.blocks_per_image > capacity) return -2;
+  for (int bx = 0; bx < plan.blocks_per_image; ++bx) {
+    const CdpTileCtx c = cdp_tile_ctx(kp, bx, 0);
+    out[3 * bx] = c.lvl; out[3 * bx + 1] = c.x0; out[3 * bx + 2] = c.y0;
+  }
+  return plan.blocks_per_image;
+}
+
 template <bool G, bool M>
 static void emu_photo_block(const CdpPhotoParams& kp, int bx, int by) {
   typedef CdpTileGeom<G> Geo;

@@ -54,6 +54,16 @@ def _f32(t):
     return t.detach().to(torch.float32).contiguous()
 
 
+def tile_table(h, w, levels):
+    """(level, x0, y0) of every block of one image as the photo kernel's cdp_tile_ctx computes them."""
+    lib = load()
+    cap = 1 << 20
+    out = np.zeros(3 * cap, dtype=np.int32)
+    n = lib.emu_tile_table(h, w, levels, out.ctypes.data_as(ctypes.c_void_p), cap)
+    assert n > 0, n
+    return out[:3 * n].reshape(n, 3)
+
+
 def resize_tables(h, w, levels):
     lib = load()
     n = lib.emu_resize_tables_bytes(h, w, levels)

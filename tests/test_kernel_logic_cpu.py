@@ -277,3 +277,23 @@ def test_emulated_fused_heads_equal_the_separate_conversions(w, h, scales):
     want = po.reconstruction_loss(tb.intrinsics.numpy(), [i.double() for i in tb.images], ref_depth, ref_poses, noise, scales,
                                   level_intrinsics=list(k))
     assert_loss_close(fused["recon"], want, "recon from heads", rtol=2e-5)
+
+
+@pytest.mark.parametrize("hw,levels", [((512, 1024), 5), ((376, 1408), 5), ((384, 1280), 5), ((33, 65), 2), ((32, 32), 1),
+                                       ((2048, 4096), 5), ((96, 4000), 3), ((1000, 40), 4)])
+def test_tile_lookup_matches_integer_arithmetic(hw, levels):
+    """cdp_tile_ctx finds a block's level without a loop and its tile row with the host's reciprocal
+    (a multiply-high instead of a division, on the critical path to the tile's TMA loads): every
+    block must land on the tile plain integer arithmetic gives, incl. one-tile-wide levels."""
+    import emu_binding
+    h, w = hw
+    got = emu_binding.tile_table(h, w, levels)
+    want = []
+    for s in range(levels):
+        hs, ws = h >> s, w >> s
+        tiles_x, tiles_y = (ws + 31) // 32, (hs + 31) // 32
+        for tile in range(tiles_x * tiles_y):
+            want.append((s, (tile % tiles_x) * 32, (tile // tiles_x) * 32))
+    want = np.asarray(want, dtype=np.int32)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.array_equal(got, want)
