@@ -272,6 +272,9 @@ __device__ __forceinline__ void cdp_tma_prefetch_3d(const CUtensorMap* map, int 
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+#ifndef CDP_OPT_REVERSE_TILES
+#define CDP_OPT_REVERSE_TILES 1
+#endif
 #ifndef CDP_EXP_TMA_TWICE
 #define CDP_EXP_TMA_TWICE 0  // timing experiment: both source boxes are loaded twice, at the start and in phase S2 (+101 KB of
                              // TMA traffic per tile on top of 124 KB: +1.9 % kernel time, i.e. the mbarrier waits are latency)
@@ -286,7 +289,11 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
   typedef CdpTileGeom<G> Geo;
   extern __shared__ __align__(128) float sm[];
   cdp_pdl_enter();
-  const CdpTileCtx c = cdp_tile_ctx(p, blockIdx.x, blockIdx.y);
+  // Blocks are dispatched in blockIdx.x order; the tile list is walked backwards (coarse levels first):
+  // the tiles of the coarse levels are all border tiles (reflected ring, general tap path -- the
+  // slowest ones) and would otherwise be the last blocks of the launch (CDP_OPT_REVERSE_TILES).
+  const int bx = CDP_OPT_REVERSE_TILES ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const CdpTileCtx c = cdp_tile_ctx(p, bx, blockIdx.y);
   float v[G ? 33 : 1];
 #pragma unroll
   for (int i = 0; i < (G ? 33 : 1); ++i) v[i] = 0.f;
@@ -321,7 +328,7 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
       const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x + CDP_OPT_L2_PREFETCH;
       const unsigned fy = lin / gridDim.x, fx = lin - fy * gridDim.x;
       if (fy < gridDim.y) {
-        const CdpTileCtx f = cdp_tile_ctx(p, (int)fx, (int)fy);
+        const CdpTileCtx f = cdp_tile_ctx(p, CDP_OPT_REVERSE_TILES ? (int)(gridDim.x - 1 - fx) : (int)fx, (int)fy);
         if (p.lv[f.lvl].use_tma) {
           const int ox = f.x0 - Geo::TXO, oy = f.y0 - Geo::TYO;
           cdp_tma_prefetch_3d(&tm.m[f.lvl][1], ox, oy, f.b);
@@ -377,7 +384,7 @@ cdp_photo_kernel(const __grid_constant__ CdpPhotoParams p, const __grid_constant
     cdp_photo_phase_c2<M>(p, c, threadIdx.x, blockDim.x, sm, &v[1], kc);
   }
   v[0] *= p.lv[c.lvl].weight;
-  float* rec = p.partials + ((size_t)c.b * p.blocks_per_image + blockIdx.x) * CDP_PARTIAL_STRIDE;
+  float* rec = p.partials + ((size_t)c.b * p.blocks_per_image + bx) * CDP_PARTIAL_STRIDE;  // (record order = tile order)
   if constexpr (G) {
     // The last row of dL/dT only receives something from pixels whose depth clamp is active (Q_w
     // drops out of the projection otherwise): when no thread of the block saw one, the block
