@@ -759,7 +759,14 @@ CDP_HD void cdp_photo_phase_b2(const CdpPhotoParams& p, const CdpTileCtx& c, int
       int pidx = -1;
 #pragma unroll
       for (int r = 0; r < CDP_STRIP + 2; ++r) {
-        const int row = r00 + (r - 1) * Geo::TBW;
+        // (the last, partial strip would read one row past the planes -- values that no output uses,
+        // but the warped plane of channel 2 is followed by the coefficient planes other threads are
+        // writing: the row is clamped into the box so that no such read exists)
+        int row = r00 + (r - 1) * Geo::TBW;
+        if (Geo::NSTRIP * CDP_STRIP - CDP_STRIP + r + Geo::OFFY >= Geo::TBH) {  // (compile time: only the last row(s) of the walk)
+          const int over = by0 + Geo::OFFY + r - (Geo::TBH - 1);  // box rows past the last one
+          if (over > 0) row -= over * Geo::TBW;
+        }
         float y[3];
         float2 w[3];
 #pragma unroll
