@@ -100,12 +100,15 @@ def profiled_kernel(workload: str, kernel_substr: str):
 
     def natural(path):  # r01_9_... before r01_11_...
         return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", os.path.basename(path))]
-    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "*_ncu.json")), key=natural):
+    blobs = []
+    for path in glob.glob(os.path.join(REPO, "profiles", "*_ncu.json")):
         try:
             with open(path) as f:
-                blob = json.load(f)
+                blobs.append((path, json.load(f)))
         except (OSError, ValueError):
             continue
+    # newest record last: by its "created" stamp (records written before the stamp existed sort first), then by name
+    for path, blob in sorted(blobs, key=lambda pb: (pb[1].get("created", ""), natural(pb[0]))):
         if blob.get("workload") != workload:
             continue
         for rec in blob.get("launches", []):

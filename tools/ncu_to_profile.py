@@ -10,6 +10,7 @@ import csv
 import json
 import subprocess
 import sys
+import time
 
 KEYS = {
     "gpu__time_duration.sum": "duration_us",
@@ -49,6 +50,7 @@ def main():
             rec["dram_bytes"] = rec["dram_read_bytes"] + rec.get("dram_write_bytes", 0.0)
         records.append(rec)
     blob = {"source": rep, "workload": workload, "how": "ncu --set full --clock-control none --import-source on",
+            "created": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()),  # bench.py reads the newest record
             "launches": records}
     with open(out + ".json", "w") as f:
         json.dump(blob, f, indent=1)
