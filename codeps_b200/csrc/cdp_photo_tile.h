@@ -322,25 +322,32 @@ CDP_COLD void cdp_phase_a_taps_far(const float* sbox0, const float* sbox1, const
                                    size_t plane, int W, bool in0, bool in1, int bx0, int by0, int bx1, int by1, int ax0,
                                    int ay0, int ax1, int ay1, float2 fx, float2 fy, float* sm, int ti) {
   typedef CdpTileGeom<G> Geo;
-#pragma unroll 1
+  // (all taps of the three channels requested before the first use: one memory round trip per
+  // position instead of one per channel; the stores come last because the compiler keeps loads
+  // behind earlier stores it cannot disambiguate)
+  float2 nw[3], ne[3], sw[3], se[3];
+#pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    float2 nw, ne, sw, se;
     if (in0) {
       const float* q = sbox0 + ch * Geo::SBN + by0 * Geo::SBW + bx0;
-      nw.x = q[0]; ne.x = q[1]; sw.x = q[Geo::SBW]; se.x = q[Geo::SBW + 1];
+      nw[ch].x = q[0]; ne[ch].x = q[1]; sw[ch].x = q[Geo::SBW]; se[ch].x = q[Geo::SBW + 1];
     } else {
       const float* g = src0 + ch * plane + (size_t)ay0 * W + ax0;
-      nw.x = CDP_LDG(g); ne.x = CDP_LDG(g + 1); sw.x = CDP_LDG(g + W); se.x = CDP_LDG(g + W + 1);
+      nw[ch].x = CDP_LDG(g); ne[ch].x = CDP_LDG(g + 1); sw[ch].x = CDP_LDG(g + W); se[ch].x = CDP_LDG(g + W + 1);
     }
     if (in1) {
       const float* q = sbox1 + ch * Geo::SBN + by1 * Geo::SBW + bx1;
-      nw.y = q[0]; ne.y = q[1]; sw.y = q[Geo::SBW]; se.y = q[Geo::SBW + 1];
+      nw[ch].y = q[0]; ne[ch].y = q[1]; sw[ch].y = q[Geo::SBW]; se[ch].y = q[Geo::SBW + 1];
     } else {
       const float* g = src1 + ch * plane + (size_t)ay1 * W + ax1;
-      nw.y = CDP_LDG(g); ne.y = CDP_LDG(g + 1); sw.y = CDP_LDG(g + W); se.y = CDP_LDG(g + W + 1);
+      nw[ch].y = CDP_LDG(g); ne[ch].y = CDP_LDG(g + 1); sw[ch].y = CDP_LDG(g + W); se[ch].y = CDP_LDG(g + W + 1);
     }
-    cdp_warp_plane<G>(sm, ch)[ti] = cdp_lerp2(nw, ne, sw, se, fx, fy);
   }
+  float2 wv[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) wv[ch] = cdp_lerp2(nw[ch], ne[ch], sw[ch], se[ch], fx, fy);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) cdp_warp_plane<G>(sm, ch)[ti] = wv[ch];
 }
 
 template <bool G, bool M>
@@ -977,25 +984,28 @@ CDP_COLD float4 cdp_phase_c2_taps_far(const float* sbox0, const float* sbox1, co
   const float2 neg1 = cdp_set2(-1.0f);
   const float2 wy0 = cdp_fma2(fy, neg1, cdp_set2(1.0f)), wx0 = cdp_fma2(fx, neg1, cdp_set2(1.0f));
   float2 gix = cdp_set2(0.f), giy = cdp_set2(0.f);
-#pragma unroll 1
+  float2 nw[3], ne[3], sw[3], se[3];  // (all taps requested before the first use: one memory round trip per pixel)
+#pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    float2 nw, ne, sw, se;
     if (in0) {
       const float* q = sbox0 + ch * Geo::SBN + by0 * Geo::SBW + bx0;
-      nw.x = q[0]; ne.x = q[1]; sw.x = q[Geo::SBW]; se.x = q[Geo::SBW + 1];
+      nw[ch].x = q[0]; ne[ch].x = q[1]; sw[ch].x = q[Geo::SBW]; se[ch].x = q[Geo::SBW + 1];
     } else {
       const float* g = src0 + ch * plane + (size_t)ay0 * W + ax0;
-      nw.x = CDP_LDG(g); ne.x = CDP_LDG(g + 1); sw.x = CDP_LDG(g + W); se.x = CDP_LDG(g + W + 1);
+      nw[ch].x = CDP_LDG(g); ne[ch].x = CDP_LDG(g + 1); sw[ch].x = CDP_LDG(g + W); se[ch].x = CDP_LDG(g + W + 1);
     }
     if (in1) {
       const float* q = sbox1 + ch * Geo::SBN + by1 * Geo::SBW + bx1;
-      nw.y = q[0]; ne.y = q[1]; sw.y = q[Geo::SBW]; se.y = q[Geo::SBW + 1];
+      nw[ch].y = q[0]; ne[ch].y = q[1]; sw[ch].y = q[Geo::SBW]; se[ch].y = q[Geo::SBW + 1];
     } else {
       const float* g = src1 + ch * plane + (size_t)ay1 * W + ax1;
-      nw.y = CDP_LDG(g); ne.y = CDP_LDG(g + 1); sw.y = CDP_LDG(g + W); se.y = CDP_LDG(g + W + 1);
+      nw[ch].y = CDP_LDG(g); ne[ch].y = CDP_LDG(g + 1); sw[ch].y = CDP_LDG(g + W); se[ch].y = CDP_LDG(g + W + 1);
     }
-    const float2 dix = cdp_fma2(cdp_fma2(nw, neg1, ne), wy0, cdp_mul2(cdp_fma2(sw, neg1, se), fy));
-    const float2 diy = cdp_fma2(cdp_fma2(nw, neg1, sw), wx0, cdp_mul2(cdp_fma2(ne, neg1, se), fx));
+  }
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float2 dix = cdp_fma2(cdp_fma2(nw[ch], neg1, ne[ch]), wy0, cdp_mul2(cdp_fma2(sw[ch], neg1, se[ch]), fy));
+    const float2 diy = cdp_fma2(cdp_fma2(nw[ch], neg1, sw[ch]), wx0, cdp_mul2(cdp_fma2(ne[ch], neg1, se[ch]), fx));
     const float2 g = ch == 0 ? gw0 : (ch == 1 ? gw1 : gw2);
     gix = cdp_fma2(g, dix, gix);
     giy = cdp_fma2(g, diy, giy);
